@@ -1,0 +1,304 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt by running the REAL reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the
+GPU box):    python oracle/make_golden.py
+
+The reference's Python (models/operations_lp.py, operations.py, model_lp.py, cell_lp.py,
+model_search_lp.py, compgcn.py, utils/process_data.py, utils/data_set.py, utils.weights_init)
+is imported unmodified; ``oracle/dgl_stub.py`` stands in for DGL.  Each fixture stores the
+seeded inputs, the reference ``state_dict``, outputs and gradients, so the tests can replay
+it through (a) the oracle restatement on CPU and (b) the CUDA path on the GPU box.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("MRG_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+from oracle import dgl_stub  # noqa: E402
+from oracle.mrg_oracle import synth_kg  # noqa: E402
+
+dgl_stub.install()
+sys.path.insert(0, REF)
+import models.operations_lp as ref_lp  # noqa: E402
+import models.operations as ref_nc  # noqa: E402
+import models.model_lp as ref_model_lp  # noqa: E402
+import models.cell_lp as ref_cell_lp  # noqa: E402
+import models.model_search_lp as ref_search_lp  # noqa: E402
+import models.compgcn as ref_compgcn  # noqa: E402
+from configs.genotypes import Genotype  # noqa: E402
+from utils.utils import weights_init  # noqa: E402
+from utils.process_data import process  # noqa: E402
+from utils.data_set import TrainDataset  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+README_GENOTYPE = ("[Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f_sparse_comp', 3, 2), "
+                   "('a_max', 4, 2), ('a_max', 5, 3), ('f_sparse_last', 6, 5), ('f_sparse_last', 7, 5)], "
+                   "concat_node=[4, 5, 6, 7], score_func='sf_DisMult')]")
+
+
+def ref_build_graph(num_ent, data, num_rels):
+    """Verbatim call sequence of train/mr_lp_train.py:77-89 against the stub graph."""
+    import dgl
+    g = dgl.DGLGraph()
+    g.add_nodes(num_ent)
+    g.add_edges(data[:, 0], data[:, 2])
+    g.add_edges(data[:, 2], data[:, 0])
+    in_deg = g.in_degrees(range(g.number_of_nodes())).cpu().float().numpy()
+    norm = in_deg ** -0.5
+    norm[np.isinf(norm)] = 0
+    g.ndata['n_norm'] = torch.tensor(norm)
+    g.apply_edges(lambda edges: {'norm': edges.dst['n_norm'] * edges.src['n_norm']})
+    edge_type = torch.tensor(np.concatenate([data[:, 1], data[:, 1] + num_rels]))
+    g.edata['e_type'] = edge_type
+    return g
+
+
+def _sd(module):
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def _grads(module):
+    return {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in module.named_parameters()}
+
+
+def make_graph_case(N, R, T, seed):
+    trip = synth_kg(N, R, T, seed=seed)
+    trip[:3, 2] = trip[:3, 0]          # a few self-edges
+    trip[3:6] = trip[0]                # multi-edges
+    g = ref_build_graph(N, trip, R)
+    src, dst, _ = g.edges(form='all')
+    return trip, g, {"triples": torch.from_numpy(trip), "num_ent": N, "num_rels": R,
+                     "src": src.clone(), "dst": dst.clone(), "etype": g.edata['e_type'].clone(),
+                     "norm": g.edata['norm'].clone(), "in_deg": g.in_degrees().clone()}
+
+
+def gen_ops_lp():
+    torch.manual_seed(1)
+    N, R, T, D = 37, 4, 90, 16
+    trip, g, gd = make_graph_case(N, R, T, seed=3)
+    E = g.num_edges()
+    M = E + N
+    cases = {}
+    for name in ['pre_mult', 'pre_sub', 'pre_add', 'f_zero', 'f_identity', 'f_dense', 'f_dense_comp', 'f_comp',
+                 'f_sparse', 'f_sparse_comp', 'f_dense_last', 'f_sparse_last', 'a_max', 'a_mean', 'a_sum']:
+        op = ref_lp.MIXED_OPS[name]({'feature_dim': D, 'drop_aggr': 0.0})
+        op.apply(weights_init)
+        rows = N if name.endswith('_last') else M
+        x = torch.randn(rows, D)
+        if name.startswith('a_'):
+            x = torch.relu(x)  # aggregator inputs are post-ReLU in the cell; gives exact-zero ties
+            x[:E:7] = x[1:E:7][: x[:E:7].shape[0]]  # duplicate rows -> ties between edges
+        xin = torch.randn(rows, D)
+        x.requires_grad_(True)
+        xin.requires_grad_(True)
+        out = op(g, x, xin)
+        cot = torch.randn_like(out)
+        out.backward(cot)
+        cases[name] = {"x": x.detach().clone(), "xin": xin.detach().clone(), "state": _sd(op), "out": out.detach().clone(),
+                       "cot": cot, "dx": x.grad.clone() if x.grad is not None else None,
+                       "dxin": xin.grad.clone() if xin.grad is not None else None, "dparams": _grads(op),
+                       "arg": g.last_arg.clone() if name == 'a_max' else None}
+    torch.save({"graph": gd, "D": D, "cases": cases}, os.path.join(OUT, "ops_lp.pt"))
+
+
+def gen_ops_nc():
+    torch.manual_seed(2)
+    n_dst, Eb, D = 23, 80, 8
+    rng = np.random.RandomState(5)
+    dst = rng.randint(0, n_dst - 3, size=Eb)  # last 3 dst nodes isolated
+    src = rng.randint(0, 50, size=Eb)
+    g = dgl_stub.StubGraph(n_dst, src, dst)
+    cases = {}
+    for name in ['a_max', 'a_mean', 'a_sum', 'a_std', 'f_dense', 'f_sparse', 'f_dense_last', 'f_sparse_last']:
+        op = ref_nc.MIXED_OPS[name]({'feature_dim': D})
+        op.apply(weights_init)
+        rows = Eb
+        x = torch.randn(rows, D, requires_grad=True)
+        xin = torch.randn(rows, D, requires_grad=True)
+        out = op(g, x, xin)
+        cot = torch.randn_like(out)
+        out.backward(cot)
+        cases[name] = {"x": x.detach().clone(), "xin": xin.detach().clone(), "state": _sd(op), "out": out.detach().clone(),
+                       "cot": cot, "dx": x.grad.clone() if x.grad is not None else None,
+                       "dxin": xin.grad.clone() if xin.grad is not None else None, "dparams": _grads(op)}
+    torch.save({"dst": torch.from_numpy(dst), "src": torch.from_numpy(src), "n_dst": n_dst, "D": D, "cases": cases},
+               os.path.join(OUT, "ops_nc.pt"))
+
+
+def _lp_args(D):
+    return types.SimpleNamespace(feature_dim=D, drop_aggr=0.0, drop_op=0.0, gamma=40, embed_dim=D,
+                                 conve_hid_drop=0.0, feat_drop=0.0, num_filt=4, ker_sz=3, k_w=4, k_h=D // 4)
+
+
+def gen_network_lp():
+    N, R, T, D, D0, B = 61, 5, 160, 16, 12, 8
+    trip, g, gd = make_graph_case(N, R, T, seed=7)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    genotype = eval(README_GENOTYPE)
+    model = ref_model_lp.Network('cpu', genotype, N, R, D, D0, 2 * R + 1, nn.BCELoss(), 0.0, _lp_args(D))
+    model.apply(weights_init)
+    state0 = _sd(model)
+    triplets = process({'train': trip, 'valid': trip[:5], 'test': trip[:5]}, R)
+    ds = TrainDataset(triplets['train'], N, types.SimpleNamespace(lbl_smooth=0.1))
+    items = [ds[i] for i in range(B)]
+    tr = torch.stack([it[0] for it in items])
+    labels = torch.stack([it[1] for it in items])
+    subj, rel = tr[:, 0], tr[:, 1]
+    model.train()
+    pred = model(g, subj, rel)
+    loss = model.criterion(pred, labels)
+    loss.backward()
+    state1 = _sd(model)  # running stats after one training forward
+    # a few SGD-free Adam steps to pin a short loss curve
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    losses = [loss.item()]
+    grads = _grads(model)
+    opt.step()
+    for _ in range(3):
+        opt.zero_grad()
+        l = model.criterion(model(g, subj, rel), labels)
+        l.backward()
+        opt.step()
+        losses.append(l.item())
+    model.eval()
+    with torch.no_grad():
+        pred_eval = model(g, subj, rel)
+    torch.save({"graph": gd, "genotype": README_GENOTYPE, "dims": {"N": N, "R": R, "D": D, "D0": D0, "B": B},
+                "state0": state0, "state1": state1, "subj": subj, "rel": rel, "labels": labels,
+                "pred": pred.detach(), "loss": loss.detach(), "grads": grads, "losses": losses,
+                "state_eval": _sd(model), "pred_eval": pred_eval,
+                "train_items": [(list(it['triple']), list(it['label'])) for it in triplets['train'][:B]],
+                "state_keys": list(state0.keys())},
+               os.path.join(OUT, "network_lp.pt"))
+
+
+def gen_mixed_op():
+    torch.manual_seed(4)
+    N, R, T, D = 29, 3, 70, 8
+    trip, g, gd = make_graph_case(N, R, T, seed=11)
+    E = g.num_edges()
+    M = E + N
+    cases = {}
+    for tag, names, rows in [("pre", ref_lp.PRE_OPS, M), ("first", ref_lp.FIRST_OPS, M),
+                             ("middle", ref_lp.MIDDLE_OPS, M), ("last", ref_lp.LAST_OPS, N)]:
+        mo = ref_cell_lp.MixedOp(D, 0.0, names)
+        mo.apply(weights_init)
+        mo.train()
+        alpha = (1e-1 * torch.randn(len(names))).requires_grad_(True)
+        w = torch.softmax(alpha, 0)
+        x = torch.randn(rows, D)
+        if tag == "middle":
+            x = torch.relu(x)
+        x.requires_grad_(True)
+        xin = torch.randn(rows, D, requires_grad=True)
+        out = mo(w, g, x, xin)
+        cot = torch.randn_like(out)
+        out.backward(cot)
+        cases[tag] = {"names": list(names), "alpha": alpha.detach().clone(), "x": x.detach().clone(),
+                      "xin": xin.detach().clone(), "state": _sd(mo), "out": out.detach().clone(), "cot": cot,
+                      "dalpha": alpha.grad.clone(), "dx": x.grad.clone(),
+                      "dxin": xin.grad.clone() if xin.grad is not None else None, "dparams": _grads(mo)}
+    torch.save({"graph": gd, "D": D, "cases": cases}, os.path.join(OUT, "mixed_op.pt"))
+
+
+def gen_search_lp():
+    """Supernet forward/loss (model_search_lp.py:131-194) on a small 'sampled' graph."""
+    N, R, T, D, D0 = 41, 3, 60, 8, 6
+    torch.manual_seed(5)
+    np.random.seed(5)
+    trip = synth_kg(N, R, T, seed=13)
+    # search graph: edges sorted by (rel, dst, src) -- utils/utils_rgcn.py:139-152
+    s, r, o = trip[:, 0], trip[:, 1], trip[:, 2]
+    src = np.concatenate((s, o)); dst = np.concatenate((o, s)); rel = np.concatenate((r, r + R))
+    edges = sorted(zip(rel, dst, src))
+    rel, dst, src = np.array(edges).transpose()
+    g = dgl_stub.StubGraph(N, src, dst)
+    in_deg = g.in_degrees().float().numpy()
+    nn_ = in_deg ** -0.5
+    nn_[np.isinf(nn_)] = 0
+    node_norm = torch.from_numpy(nn_).view(-1, 1)
+    g.ndata['norm'] = node_norm
+    g.apply_edges(lambda edges: {'norm': edges.dst['norm'] * edges.src['norm']})  # mr_lp_search.py:30-36
+    model = ref_search_lp.Network('cpu', N, R, 2, 1, 2, 2, D, D0, 2 * R + 1, 40, 0.0, 0.0)
+    model.apply(weights_init)
+    model.train()
+    node_id = torch.arange(N).view(-1, 1)
+    src_in = torch.from_numpy(src).long()
+    edge_type = torch.from_numpy(rel).long()
+    neg = trip.copy()
+    neg[:, 2] = np.random.randint(0, N, size=T)
+    samples = torch.from_numpy(np.concatenate([trip, neg])).long()
+    labels = torch.cat([torch.ones(T), torch.zeros(T)])
+    state0 = _sd(model)
+    alphas0 = [a.detach().clone() for a in model.arch_parameters()]
+    loss = model._loss(g, node_id, src_in, edge_type, samples, labels)
+    loss.backward()
+    torch.save({"num_ent": N, "num_rels": R, "D": D, "D0": D0, "src": src_in, "dst": torch.from_numpy(dst).long(),
+                "etype": edge_type, "norm": g.edata['norm'].clone(), "node_id": node_id, "samples": samples,
+                "labels": labels, "state0": state0, "alphas0": alphas0, "loss": loss.detach(),
+                "grads": _grads(model),
+                "dalphas": [a.grad.clone() if a.grad is not None else None for a in model.arch_parameters()],
+                "genotypes": str(model.show_genotypes()), "state_keys": list(state0.keys())},
+               os.path.join(OUT, "search_lp.pt"))
+
+
+def gen_compgcn():
+    torch.manual_seed(6)
+    N, R, T, Din, Dout = 31, 3, 64, 8, 12
+    trip, g0, gd = make_graph_case(N, R, T, seed=17)
+    E = g0.num_edges()
+    g0.edata['etype'] = g0.edata['e_type'].long()
+    g0.edata['in_edges_mask'] = torch.arange(E) < E // 2
+    g0.edata['out_edges_mask'] = torch.arange(E) >= E // 2
+    g0.edata['norm'] = g0.edata['norm'].view(-1)
+
+    class _Scope:
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    g0.local_scope = lambda: _Scope()
+    orig_apply = g0.apply_edges
+
+    def apply_edges(fn):
+        if isinstance(fn, dgl_stub._Desc):
+            u, e = g0.ndata[fn.a][g0._src], g0.edata[fn.b]
+            g0.edata['comp_h'] = u - e if fn.kind == 'u_sub_e' else u * e
+        else:
+            orig_apply(fn)
+    g0.apply_edges = apply_edges
+    # utils/utils.py:285-301 uses the removed torch.rfft; restate with torch.fft for the ccorr case only
+    ref_compgcn.ccorr = lambda a, b: torch.fft.irfft(
+        torch.conj(torch.fft.rfft(a, dim=-1)) * torch.fft.rfft(b, dim=-1), n=a.shape[-1], dim=-1)
+    cases = {}
+    for comp in ['sub', 'mul', 'ccorr']:
+        layer = ref_compgcn.CompGraphConv(Din, Dout, comp_fn=comp, batchnorm=True, dropout=0.0)
+        layer.apply(weights_init)
+        layer.train()
+        h = torch.randn(N, Din, requires_grad=True)
+        r = torch.randn(2 * R, Din, requires_grad=True)
+        n_out, r_out = layer(g0, h, r)
+        c1, c2 = torch.randn_like(n_out), torch.randn_like(r_out)
+        (n_out * c1).sum().add((r_out * c2).sum()).backward()
+        cases[comp] = {"h": h.detach().clone(), "r": r.detach().clone(), "state": _sd(layer), "n_out": n_out.detach(),
+                       "r_out": r_out.detach(), "c1": c1, "c2": c2, "dh": h.grad.clone(), "dr": r.grad.clone(),
+                       "dparams": _grads(layer)}
+    torch.save({"graph": gd, "Din": Din, "Dout": Dout, "cases": cases}, os.path.join(OUT, "compgcn.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_ops_lp()
+    gen_ops_nc()
+    gen_network_lp()
+    gen_mixed_op()
+    gen_search_lp()
+    gen_compgcn()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
