@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- MR-GNAS message-passing hot path on B200 (contract: see the task statement).
+
+A "step" is one full training step of the README-genotype link-prediction network on the
+synthetic FB15k-237-shaped KG (BASELINE.json configs[0] shape, run on 1xB200): full-graph
+message passing through the cell (fwd), DistMult 1-N scoring + BCE, backward, Adam.
+
+  value : MP edges/s = E directed edges x cells / step time, inputs already resident in HBM
+  e2e   : same metric through the public API (Network._loss) with the step's batch
+          (triples + dense smoothed labels) copied from pinned host memory and the loss read back
+  roofline : dominant libmrgnas kernel, algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline : the CPU oracle (port of the reference path) timed on the host cores
+
+--impl reference times the reference's CPU implementation of the same path (the oracle port;
+DGL is not installable) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+import types
+from collections import namedtuple
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+Genotype = namedtuple("Genotype", "alpha_cell concat_node score_func")
+README_GENOTYPE = [Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f_sparse_comp', 3, 2),
+                                        ('a_max', 4, 2), ('a_max', 5, 3), ('f_sparse_last', 6, 5),
+                                        ('f_sparse_last', 7, 5)],
+                            concat_node=[4, 5, 6, 7], score_func='sf_DisMult')]
+METRIC, UNIT = "mp_edges_per_s_train_step", "edges/s"
+
+
+def model_args(D):
+    return types.SimpleNamespace(feature_dim=D, drop_aggr=0.0, drop_op=0.0, gamma=40, embed_dim=D, conve_hid_drop=0.0,
+                                 feat_drop=0.0, num_filt=4, ker_sz=3, k_w=4, k_h=D // 4)
+
+
+def workload(name):
+    from mr_gnas_b200.synth import CONFIGS, synth_kg
+    N, R, T, D = CONFIGS[name]
+    return N, R, T, D, synth_kg(N, R, T, seed=0)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower() == "active":
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the CPU oracle port of the reference path, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import mrg_oracle as O  # the one place bench.py executes oracle/ as the measured thing
+    torch.set_num_threads(os.cpu_count())
+    N, R, T, D, trip = workload(args.workload)
+    Ts = max(1000, T // args.ref_downscale)
+    trip_s = trip[:Ts]
+    out = time_cpu_oracle(O, N, R, trip_s, D, args.batch, args.steps, args.warmup)
+    E = 2 * Ts
+    ms = out["ms_per_step"]
+    val = E * len(README_GENOTYPE) / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: README genotype LP train step, N={N} R={R} D={D} B={args.batch}",
+                       "sample": f"first {Ts} of {T} train triples (E={E} directed edges), full N, full D"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} steps on first {Ts}/{T} triples"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "triples_per_s": args.batch / (ms / 1e3)}
+    print(json.dumps(line), flush=True)
+
+
+def time_cpu_oracle(O, N, R, trip, D, B, steps, warmup):
+    graph = O.build_graph(N, trip, R)
+    from mr_gnas_b200.model_lp import Network
+    from mr_gnas_b200.utils import weights_init
+    torch.manual_seed(0)
+    m = Network('cpu', README_GENOTYPE, N, R, D, D, 2 * R + 1, nn.BCELoss(), 0.0, model_args(D))
+    m.apply(weights_init)
+    P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    params = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    items = O.process_1n(trip, R)
+    times = []
+    for it in range(warmup + steps):
+        chunk = items[(it * B) % max(1, len(items) - B):][:B]
+        subj = torch.tensor([c["triple"][0] for c in chunk])
+        rel = torch.tensor([c["triple"][1] for c in chunk])
+        labels = O.smoothed_labels(chunk, N, 0.1)
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = O.bce_loss(O.network_lp(README_GENOTYPE, P, graph, subj, rel, R, training=True), labels)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return {"ms_per_step": 1e3 * sum(times) / len(times), "loss": float(loss)}
+
+
+# ------------------------------------------------------------------------------------------
+def algo_bytes(key, M, E, N, D):
+    """Compulsory HBM bytes of one call (inputs read once + outputs written once, fp32 rows of
+    b = 4*D bytes; index / gate vectors included; L2-resident [N,D] tables excluded)."""
+    b = 4 * D
+    name = key.split("(")[0]
+    rows = int(key.split("(")[1].split(",")[0]) if "(" in key and key.split("(")[1][0].isdigit() else M
+    table = {
+        "mrg_compose_fwd": rows * (b + 8),                 # write y, read 2 int32 indices (h, r tables L2-resident)
+        "mrg_affine_act": rows * 2 * b,                    # read y, write s
+        "mrg_colstats": rows * b,
+        "mrg_bn_bwd_reduce": rows * 2 * b,                 # read ds, y
+        "mrg_bn_bwd_apply": rows * 3 * b,                  # read ds, y; write dy
+        "mrg_sparse_gate_fwd": rows * (2 * b + 8),         # read x (x is xin here or 3b), write y, gate+scale
+        "mrg_sparse_gate_bwd": rows * (3 * b + 8),         # read dy, x; write dx
+        "mrg_seg_reduce_bwd": rows * b,                    # write dm (g/arg tables L2-resident)
+    }
+    return table.get(name)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1_fb15k237")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--ref-downscale", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-call CUDA-event profile here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from mr_gnas_b200 import _lib
+    from mr_gnas_b200.graph import MRGraph
+    from mr_gnas_b200.model_lp import Network
+    from mr_gnas_b200.process_data import make_batch, process
+    from mr_gnas_b200.utils import weights_init
+    _lib.load()  # fails loudly if the CUDA extension is missing
+
+    N, R, T, D, trip = workload(args.workload)
+    E, M, B = 2 * T, 2 * T + N, args.batch
+    g = MRGraph.from_triples(N, trip, R, device=dev)
+    torch.manual_seed(0)
+    model = Network(dev, README_GENOTYPE, N, R, D, D, 2 * R + 1, nn.BCELoss(), 0.0, model_args(D))
+    model.apply(weights_init)
+    model = model.to(dev).train()
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    # data-parallel over query batches for N>1: every rank runs full-graph MP on its own batch,
+    # parameter gradients are all-reduced (NCCL) -- weak scaling, per-GPU work fixed.
+    items = process({'train': trip.tolist(), 'valid': [], 'test': []}, R)['train']
+    nb = args.steps + args.warmup
+    rng = np.random.RandomState(100 + rank)
+    host_batches = []
+    for i in range(min(nb, 8)):
+        sel = rng.choice(len(items), size=B, replace=False)
+        host_batches.append(make_batch([items[j] for j in sel], N, lbl_smooth=0.1, pin=True))
+    dev_batches = [(t.to(dev), y.to(dev)) for t, y in host_batches]
+    h2d = host_batches[0][0].numel() * 8 + host_batches[0][1].numel() * 4
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                if p.grad is not None:
+                    n = p.grad.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
+
+    def step_resident(i):
+        trip_d, y_d = dev_batches[i % len(dev_batches)]
+        opt.zero_grad(set_to_none=True)
+        loss = model._loss(g, trip_d[:, 0], trip_d[:, 1], y_d)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def step_e2e(i):
+        t_h, y_h = host_batches[i % len(host_batches)]
+        trip_d, y_d = t_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True)
+        opt.zero_grad(set_to_none=True)
+        loss = model._loss(g, trip_d[:, 0], trip_d[:, 1], y_d)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss.item()  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sample_clocks=False):
+        barrier()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (sampler.stop() if sampler else None), out
+
+    for i in range(args.warmup):
+        step_resident(i)
+    k0 = _lib.launch_count
+    ms, clocks, last_loss = timed(step_resident, args.steps, sample_clocks=True)
+    launches = (_lib.launch_count - k0)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, last_e2e = timed(step_e2e, args.steps)
+
+    cells = len(README_GENOTYPE)
+    value = world * E * cells / (ms / 1e3)
+    e2e_value = world * E * cells / (ms_e2e / 1e3)
+
+    # per-call CUDA-event profile of one step (rank 0) -> dominant kernel + roofline
+    roofline, prof_rows = None, []
+    if rank == 0:
+        _lib.start_profile()
+        for i in range(3):
+            step_resident(i)
+        prof = _lib.stop_profile()
+        tot = sum(t for _, t in prof.values()) / 3
+        hbm, how = peaks()
+        for key, (cnt, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            ab = algo_bytes(key, M, E, N, D)
+            avg_ms = t / cnt
+            prof_rows.append({"call": key, "launches_per_step": cnt / 3, "avg_ms": avg_ms, "ms_per_step": t / 3,
+                              "share_of_lib_time": t / 3 / tot if tot else None,
+                              "algo_gbs": (ab / avg_ms / 1e6) if ab else None})
+        top = next((r for r in prof_rows if r["algo_gbs"]), None)
+        if top:
+            roofline = {"bound": "hbm", "kernel": top["call"], "achieved": top["algo_gbs"], "peak": hbm, "unit": "GB/s",
+                        "frac": top["algo_gbs"] / hbm, "traffic": None, "peak_source": how,
+                        "lib_ms_per_step": tot, "step_ms": ms}
+        if args.profile_json:
+            json.dump(prof_rows, open(args.profile_json, "w"), indent=1)
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import mrg_oracle as O  # cpu_baseline leg only
+        torch.set_num_threads(os.cpu_count())
+        out = time_cpu_oracle(O, N, R, trip, D, B, steps=1, warmup=0)
+        cpu_baseline = {"value": E * cells / (out["ms_per_step"] / 1e3), "unit": UNIT, "cores": torch.get_num_threads(),
+                        "kind": "port", "sample": "1 full training step (no warm-up) on the full workload",
+                        "ms_per_step": out["ms_per_step"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: README genotype LP train step (fwd+bwd+Adam), "
+                                       f"N={N} R={R} T={T} E={E} D={D} B={B}, 1 cell",
+                           "parallelism": f"dp{world} over query batches (full-graph MP per rank, NCCL grad all-reduce)",
+                           "l2": "edge tensors are 447 MB each (> 126 MB L2); no explicit flush"},
+                "triples_per_s": world * B / (ms / 1e3),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e, "triples_per_s": world * B / (ms_e2e / 1e3)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "loss": float(last_loss)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,210 @@
+/*
+ * mrgnas.h -- C ABI of libmrgnas.so: hand-written sm_100a kernels for the MR-GNAS
+ * multi-relational message-passing hot path (BASELINE.json:north_star).
+ *
+ * The upstream project (Amanda-Zheng/MR-GNAS) is pure Python: it has no FFI of its own.
+ * On this path it reaches native code through two third-party libraries, DGL
+ * (update_all / apply_edges -> libdgl gspmm/gsddmm) and torch ATen (index_select,
+ * index_add_, batch_norm, sigmoid, binary_cross_entropy).  Each entry point below states
+ * the reference call site(s) (file:line, relative to the upstream repo root) whose native
+ * work it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all feature matrices are fp32, row-major, leading dimension == D, D % 4 == 0,
+ *     D <= 512, base pointers 16-byte aligned; indices are int32;
+ *   - the library never allocates, frees or retains memory: outputs, saved tensors and
+ *     workspaces are owned by the caller (sizes from the *_bytes / *_count helpers);
+ *   - calls only enqueue work on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, and are re-entrant across streams/devices (one process per GPU);
+ *   - return value 0 = ok, otherwise an mrg_status; mrg_last_error() gives the message of
+ *     the last failure on the calling thread; no C++ exception crosses the boundary;
+ *   - results are deterministic run to run (no floating-point atomics anywhere).
+ */
+#ifndef MRGNAS_H_
+#define MRGNAS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRG_ABI_VERSION 1
+
+typedef enum {
+  MRG_OK = 0,
+  MRG_ERR_INVALID = 1,  /* bad argument (null pointer, D % 4 != 0, ...) */
+  MRG_ERR_CUDA = 2,     /* a CUDA runtime call / launch failed            */
+  MRG_ERR_WORKSPACE = 3 /* workspace too small                            */
+} mrg_status;
+
+/* composition of source-entity and relation features (operations_lp.py:71-98) */
+typedef enum { MRG_COMP_SUB = 0, MRG_COMP_MULT = 1, MRG_COMP_ADD = 2 } mrg_comp;
+/* destination reductions = DGL update_all(copy_e, max|sum|mean) (operations_lp.py:233,248,262)
+ * and the NC std reducer (operations.py:167-190) */
+typedef enum { MRG_RED_SUM = 0, MRG_RED_MEAN = 1, MRG_RED_MAX = 2, MRG_RED_STD = 3 } mrg_reduce;
+
+/* A feature matrix read through an optional per-column affine + ReLU:
+ *   value(i,c) = relu?( scale[c] * data[i,c] + shift[c] )       (scale == NULL: identity affine)
+ * This is how BatchNorm1d(+ReLU) that follows every op in the reference
+ * (model_lp.py:31-33, cell_lp.py:21,31-32) is folded into the consumer's loads. */
+typedef struct {
+  const float* data;
+  const float* scale;
+  const float* shift;
+  int32_t relu;
+} mrg_act;
+
+int mrg_abi_version(void);
+const char* mrg_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * K0  graph build (integer, bit-exact).  Replaces dgl.DGLGraph()/add_edges/in_degrees/
+ * apply_edges in build_graph (train/mr_lp_train.py:77-89), comp_deg_norm
+ * (utils/utils_rgcn.py:120-127) and the stable COO->CSR DGL does inside update_all.
+ *
+ * Inputs: E directed edges (src,dst,etype) in EDGE-ID order, N nodes, n_rel_rows relation
+ * rows (2R+1; id n_rel_rows-1 is the self-loop relation).  "Rows" are the M = E + N
+ * edge-expanded rows of the reference (model_lp.py:126-131): row i<E is edge i, row E+n is
+ * node n's self loop with src n and relation n_rel_rows-1.
+ * Outputs (caller-allocated):
+ *   in_deg[N], n_norm[N] = in_deg^-1/2 (inf->0), edge_norm[E] = n_norm[dst]*n_norm[src]
+ *     (norm pointers may be NULL to skip);
+ *   dst-CSR  csr_ptr[N+1], csr_eid[E]   : edge ids ascending inside each destination;
+ *   src-CSC  csc_ptr[N+1], csc_row[M]   : row ids ascending inside each source;
+ *   relation rel_ptr[n_rel_rows+1], rel_row[M] : row ids ascending inside each relation.
+ * ---------------------------------------------------------------------------------- */
+size_t mrg_graph_workspace_bytes(int64_t E, int64_t N, int64_t n_rel_rows);
+int mrg_graph_build(const int32_t* src, const int32_t* dst, const int32_t* etype, int64_t E, int64_t N,
+                    int64_t n_rel_rows, int32_t* in_deg, float* n_norm, float* edge_norm, int32_t* csr_ptr,
+                    int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_row, int32_t* rel_ptr, int32_t* rel_row,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Chunk table over a segment list (ptr[nseg+1]): splits every segment into pieces of at
+ * most MRG_CHUNK_ROWS rows so hub nodes / frequent relations are reduced by many warps.
+ * chunk_first[nseg+1] (exclusive scan of chunks per segment) and chunk_seg[max_chunks].
+ * max_chunks = mrg_chunk_capacity(total_rows, nseg). */
+#define MRG_CHUNK_ROWS 32
+int64_t mrg_chunk_capacity(int64_t total_rows, int64_t nseg);
+size_t mrg_chunk_workspace_bytes(int64_t nseg);
+int mrg_chunk_build(const int32_t* ptr, int64_t nseg, int32_t* chunk_first, int32_t* chunk_seg, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * column statistics for training-mode BatchNorm1d over edge rows
+ * (model_lp.py:23,32,50,72; cell_lp.py:21; torch native_batch_norm).
+ * Producers write per-block partial (sum, sum of squares) in double to `stats`
+ * ([mrg_stats_nparts(rows)][2][D] doubles); mrg_bn_finalize folds them in a fixed order.
+ * ---------------------------------------------------------------------------------- */
+int32_t mrg_stats_nparts(int64_t rows);
+int32_t mrg_stats_max_parts(void);
+int mrg_colstats(mrg_act x, int64_t rows, int32_t D, double* stats, void* stream);
+/* mean/invstd (biased var, eps), a = gamma*invstd, b = beta - a*mean; updates
+ * running_mean/var (unbiased var, momentum) when non-NULL.  nparts = total partial blocks. */
+int mrg_bn_finalize(const double* stats, int32_t nparts, int64_t rows, int32_t D, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* mean, float* invstd, float* a, float* b, void* stream);
+/* out = relu?(a*x+b): materialises an activation (BN-apply + ReLU in one pass). */
+int mrg_affine_act(mrg_act x, int64_t rows, int32_t D, float* out, void* stream);
+/* backward of s = relu?(a*y+b) with a,b from batch statistics of y:
+ *   reduce: partial sums of dz and dz*y, dz = ds * [s>0]          -> bwd_stats
+ *   finalize: dgamma, dbeta and coef[3][D] with dy = coef2*dz + coef0 + coef1*y
+ *   apply:  dy (may alias ds).  accumulate!=0 adds into dy instead of overwriting. */
+int mrg_bn_bwd_reduce(const float* ds, mrg_act y, int64_t rows, int32_t D, double* bwd_stats, void* stream);
+int mrg_bn_bwd_finalize(const double* bwd_stats, int32_t nparts, int64_t rows, int32_t D, const float* gamma,
+                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
+                        void* stream);
+int mrg_bn_bwd_apply(const float* ds, mrg_act y, const float* coef, int64_t rows, int32_t D, float* dy,
+                     int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K1  edge-expanded gather + composition.  Replaces all_ent_emb[src_id_final],
+ * rel_embed[edge_type_final] (model_lp.py:126-131; ATen index_select) fused with
+ * pre_sub/pre_mult/pre_add (operations_lp.py:71-98):
+ *   y[i,:] = h[h_idx[i],:]  (-|*|+)  r[r_idx[i],:]      (idx NULL: identity rows)
+ * plus the BN column statistics of y (stats may be NULL).
+ * Backward (replaces ATen index_add_ atomics with deterministic segmented sums) is
+ * expressed with mrg_seg_reduce over the src-CSC and the relation segments.
+ * ---------------------------------------------------------------------------------- */
+int mrg_compose_fwd(const float* h, const int32_t* h_idx, const float* r, const int32_t* r_idx, int64_t rows,
+                    int32_t D, int32_t comp, float* y, double* stats, void* stream);
+/* elementwise backward for the un-gathered op form: dx = dy (*r), dr = (+|-)dy (*x) */
+int mrg_compose_bwd_rows(const float* dy, const float* x, const float* r, int64_t rows, int32_t D, int32_t comp,
+                         float* dx, float* dr, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3/K6  collapsed sparse gate.  Replaces f_sparse_op_comp (operations_lp.py:304-343),
+ * f_sparse_op (345-354; operations.py:205-216) and f_sparse_op_last (405-416) on a
+ * contiguous row range that shares one (W,a) pair:
+ *   t_i = x_i . v1 + xin_i . v2 + c ;  gate_i = sigmoid(t_i)
+ *   y[i,:] = base_scale * (row_scale ? row_scale[i] : 1) * gate_i * x[i,:]
+ * where v = a.weight @ W.weight (split into the x / xin halves) and c = a.weight . W.bias
+ * (no non-linearity sits between W and a in the reference).  xin.data == NULL drops the
+ * second term; xin.data == x.data reads the row once.  `gate` [rows] is saved for backward.
+ * Backward returns dx/dxin w.r.t. the activated inputs (accumulate!=0: +=) and per-block
+ * partials of dv1, dv2, dc in `dparam` ([nparts][2*D+1] doubles... see mrg_gate_dparam_count).
+ * ---------------------------------------------------------------------------------- */
+int mrg_sparse_gate_fwd(mrg_act x, mrg_act xin, int64_t rows, int32_t D, const float* v1, const float* v2,
+                        const float* c, const float* row_scale, float base_scale, float* y, float* gate,
+                        double* stats, void* stream);
+int64_t mrg_gate_dparam_count(int64_t rows, int32_t D);
+int mrg_sparse_gate_bwd(const float* dy, mrg_act x, mrg_act xin, const float* gate, int64_t rows, int32_t D,
+                        const float* v1, const float* v2, const float* row_scale, float base_scale, float* dx,
+                        float* dxin, int32_t accumulate, double* dparam, void* stream);
+/* folds the partials: dv1[D], dv2[D] (NULL if no xin), dc[1] */
+int mrg_sparse_gate_bwd_finalize(const double* dparam, int64_t rows, int32_t D, float* dv1, float* dv2, float* dc,
+                                 void* stream);
+
+/* dense gate epilogue: y = scale_i * sigmoid?(z) * x  (f_dense_op_comp / f_comp_op /
+ * f_dense_op(_last), operations_lp.py:266-288,356-401) after the edge-tile GEMM z. */
+int mrg_dense_gate_fwd(const float* z, mrg_act x, int64_t rows, int32_t D, int32_t use_sigmoid,
+                       const float* row_scale, float base_scale, float* y, double* stats, void* stream);
+int mrg_dense_gate_bwd(const float* dy, const float* z, mrg_act x, int64_t rows, int32_t D, int32_t use_sigmoid,
+                       const float* row_scale, float base_scale, float* dz, float* dx, int32_t accumulate,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5/K11  segmented reduction of gathered rows.  One kernel family serves
+ *   (i)  DGL update_all(copy_e, max|sum|mean) over the dst-CSR (operations_lp.py:233,248,
+ *        262; compgcn.py:87) and the NC UDF reducers incl. std (operations.py:105-190);
+ *   (ii) the backward of the edge-expanded gathers (ATen index_add_ in the reference):
+ *        dh over the src-CSC, d rel_embed over the relation segments.
+ *   red[s,:] = REDUCE_{j in [ptr[s],ptr[s+1])}  value(idx[j])  (.*  mul[mul_idx[idx[j]],:])
+ *   out[s,:] = alpha * red (/ max(len,1) for MEAN) + (residual ? residual(s,:) : 0)
+ * MAX: empty segment -> 0; arg[s,c] = lowest idx attaining the max (-1 if empty) = the
+ * stated tie-break; values are compared after the optional ReLU of `m`.
+ * workspace: mrg_seg_reduce_workspace_bytes(n_chunks, D, kind).
+ * ---------------------------------------------------------------------------------- */
+size_t mrg_seg_reduce_workspace_bytes(int64_t max_chunks, int32_t D, int32_t kind);
+int mrg_seg_reduce_fwd(int32_t kind, mrg_act m, const int32_t* ptr, const int32_t* idx, const int32_t* chunk_first,
+                       const int32_t* chunk_seg, int64_t nseg, int64_t max_chunks, int32_t D, const float* mul,
+                       const int32_t* mul_idx, float alpha, mrg_act residual, int32_t accumulate, float* out,
+                       int32_t* arg, void* workspace, size_t workspace_bytes, void* stream);
+/* backward of (i) w.r.t. the (pre-ReLU) message rows, in edge-id order:
+ *   SUM : dm[e,:] = g[dst[e],:]              MEAN: g[dst[e],:] / max(deg,1)
+ *   MAX : dm[e,c] = g[n,c] if arg[n,c]==e    (all gated by [m>0] when m.relu)
+ *   STD : dm[e,c] = g[n,c] * (m[e,c]-mean[n,c]) / (deg*out[n,c])  where var>0
+ * rows >= E (self-loop rows, when n_self>0) receive g[row-E,:] (the residual path). */
+int mrg_seg_reduce_bwd(int32_t kind, const float* g, const int32_t* arg, const float* out, mrg_act m,
+                       const int32_t* dst, const int32_t* ptr, int64_t E, int64_t n_self, int32_t D, float* dm,
+                       int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K8  DistMult 1-N scoring epilogue + BCE.  Replaces torch.sigmoid + nn.BCELoss
+ * (operations_lp.py:121-127; train/mr_lp_train.py:116,235): loss = mean over n elements of
+ * -(y*max(log p,-100) + (1-y)*max(log(1-p),-100)), p = sigmoid(logit).
+ * fwd writes per-block partial sums (double) then the mean to loss[0]; pred (nullable)
+ * receives p.  bwd: dlogit = gscale * (p - y) * p(1-p) / max(p(1-p), 1e-12) / n.
+ * ---------------------------------------------------------------------------------- */
+int32_t mrg_bce_nparts(int64_t n);
+int mrg_sigmoid_bce_fwd(const float* logit, const float* label, int64_t n, float* pred, double* partial,
+                        float* loss, void* stream);
+int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64_t n, const float* gscale, float* dlogit,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRGNAS_H_ */

@@ -1,0 +1,156 @@
+"""ctypes binding of libmrgnas.so (include/mrgnas.h).  No torch types cross the boundary:
+tensors are passed as raw device pointers + sizes, the stream as a cudaStream_t handle.
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised (build it with ``python -m mr_gnas_b200.build``)."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmrgnas.so")
+
+COMP = {"pre_sub": 0, "pre_mult": 1, "pre_add": 2, "sub": 0, "mult": 1, "add": 2}
+RED = {"sum": 0, "mean": 1, "max": 2}
+CHUNK_ROWS = 32
+
+
+class MrgAct(Structure):
+    _fields_ = [("data", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("relu", c_int32)]
+
+
+P, I32, I64, F32, SZ = c_void_p, c_int32, c_int64, c_float, c_size_t
+
+_SIGNATURES = {
+    "mrg_abi_version": (c_int32, []),
+    "mrg_last_error": (c_char_p, []),
+    "mrg_graph_workspace_bytes": (SZ, [I64, I64, I64]),
+    "mrg_graph_build": (I32, [P, P, P, I64, I64, I64, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "mrg_chunk_capacity": (I64, [I64, I64]),
+    "mrg_chunk_workspace_bytes": (SZ, [I64]),
+    "mrg_chunk_build": (I32, [P, I64, P, P, P, SZ, P]),
+    "mrg_stats_nparts": (I32, [I64]),
+    "mrg_stats_max_parts": (I32, []),
+    "mrg_colstats": (I32, [MrgAct, I64, I32, P, P]),
+    "mrg_bn_finalize": (I32, [P, I32, I64, I32, P, P, F32, F32, P, P, P, P, P, P, P]),
+    "mrg_affine_act": (I32, [MrgAct, I64, I32, P, P]),
+    "mrg_bn_bwd_reduce": (I32, [P, MrgAct, I64, I32, P, P]),
+    "mrg_bn_bwd_finalize": (I32, [P, I32, I64, I32, P, P, P, P, P, P, P]),
+    "mrg_bn_bwd_apply": (I32, [P, MrgAct, P, I64, I32, P, I32, P]),
+    "mrg_compose_fwd": (I32, [P, P, P, P, I64, I32, I32, P, P, P]),
+    "mrg_compose_bwd_rows": (I32, [P, P, P, I64, I32, I32, P, P, P]),
+    "mrg_sparse_gate_fwd": (I32, [MrgAct, MrgAct, I64, I32, P, P, P, P, F32, P, P, P, P]),
+    "mrg_gate_dparam_count": (I64, [I64, I32]),
+    "mrg_sparse_gate_bwd": (I32, [P, MrgAct, MrgAct, P, I64, I32, P, P, P, F32, P, P, I32, P, P]),
+    "mrg_sparse_gate_bwd_finalize": (I32, [P, I64, I32, P, P, P, P]),
+    "mrg_dense_gate_fwd": (I32, [P, MrgAct, I64, I32, I32, P, F32, P, P, P]),
+    "mrg_dense_gate_bwd": (I32, [P, P, MrgAct, I64, I32, I32, P, F32, P, P, I32, P]),
+    "mrg_seg_reduce_workspace_bytes": (SZ, [I64, I32, I32]),
+    "mrg_seg_reduce_fwd": (I32, [I32, MrgAct, P, P, P, P, I64, I64, I32, P, P, F32, MrgAct, I32, P, P, P, SZ, P]),
+    "mrg_seg_reduce_bwd": (I32, [I32, P, P, P, MrgAct, P, P, I64, I64, I32, P, I32, P]),
+    "mrg_bce_nparts": (I32, [I64]),
+    "mrg_sigmoid_bce_fwd": (I32, [P, P, I64, P, P, P, P]),
+    "mrg_sigmoid_bce_bwd": (I32, [P, P, I64, P, P, P]),
+}
+# optional tensor-core entry points (declared in mrgnas.h once built)
+_OPTIONAL = {}
+
+_lib = None
+# kernels enqueued per C-ABI call (default 1); used for the gpu_launches count bench.py reports
+KERNELS_PER_CALL = {"mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_chunk_build": 3}
+launch_count = 0   # libmrgnas kernels launched so far
+_profile = None    # when a list: (name, start_event, end_event) per call (bench.py per-kernel timing)
+
+
+def declared_symbols():
+    return sorted(list(_SIGNATURES) + list(_OPTIONAL))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"libmrgnas.so not found at {LIB_PATH}: run `python -m mr_gnas_b200.build` "
+                           "(the product path has no CPU / eager fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in {**_SIGNATURES, **_OPTIONAL}.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mrg_abi_version() != 1:
+        raise RuntimeError("libmrgnas ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check_f32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"libmrgnas expects contiguous fp32 CUDA tensors, got {t.dtype} {t.device} "
+                               f"contiguous={t.is_contiguous()}")
+
+
+def check_i32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+            raise RuntimeError("libmrgnas expects contiguous int32 CUDA index tensors")
+
+
+def act(data, scale=None, shift=None, relu=False):
+    """mrg_act view of `data` read through relu?(scale*x+shift)."""
+    if data is None:
+        return MrgAct(None, None, None, 0)
+    check_f32(data, scale, shift)
+    return MrgAct(data.data_ptr(), scale.data_ptr() if scale is not None else None,
+                  shift.data_ptr() if shift is not None else None, 1 if relu else 0)
+
+
+def call(name, *args):
+    global launch_count
+    lib = load()
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.mrg_last_error().decode()}")
+    if _profile is not None:
+        e1.record()
+        ints = tuple(a for a in args if type(a) is int)[:3]
+        _profile.append((name + str(ints), e0, e1))
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    return rc
+
+
+def start_profile():
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """-> {call name: (count, total ms)} measured with CUDA events around each C-ABI call."""
+    global _profile
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _profile or []:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    _profile = None
+    return out

@@ -1,0 +1,175 @@
+// Shared device/host helpers for libmrgnas (sm_100a).  Warp-per-row kernels: each lane owns
+// NV float4 column groups (col4 = lane + 32*v), so a D<=512 fp32 row is moved with 128-bit
+// loads/stores and per-column statistics stay in registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mrgnas.h"
+
+namespace mrg {
+
+constexpr int kThreads = 256;            // 8 warps per CTA
+constexpr int kWarpsPerBlock = kThreads / 32;
+constexpr int kNumSMs = 148;             // B200
+constexpr int kStatsBlocksPerSM = 4;
+constexpr int kMaxParts = kNumSMs * kStatsBlocksPerSM;  // 592 persistent CTAs
+constexpr int kFoldRows = 16;            // fold fp32 partial sums into double every 16 rows
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define MRG_CHECK_ARG(cond, msg)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      mrg::set_error("invalid argument: %s", msg); \
+      return MRG_ERR_INVALID;                    \
+    }                                            \
+  } while (0)
+
+#define MRG_LAUNCH_CHECK(what)                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return mrg::cuda_fail(e__, what);    \
+  } while (0)
+
+inline bool valid_D(int D) { return D > 0 && D % 4 == 0 && D <= 512; }
+inline int nv_for(int D) { return D <= 128 ? 1 : (D <= 256 ? 2 : 4); }
+inline int stats_grid(int64_t rows) {
+  int64_t need = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (need < 1) need = 1;
+  return (int)(need < kMaxParts ? need : kMaxParts);
+}
+
+// dispatch on NV (float4 groups per lane)
+#define MRG_DISPATCH_NV(D, ...)                      \
+  do {                                               \
+    int nv__ = mrg::nv_for(D);                       \
+    if (nv__ == 1) { constexpr int NV = 1; __VA_ARGS__; } \
+    else if (nv__ == 2) { constexpr int NV = 2; __VA_ARGS__; } \
+    else { constexpr int NV = 4; __VA_ARGS__; }      \
+  } while (0)
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming (read-once) load: bypass L1 allocation
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float t) { return 1.0f / (1.0f + expf(-t)); }
+
+// Per-lane view of an mrg_act: column affine held in registers.
+template <int NV>
+struct ActRegs {
+  float4 sc[NV], sh[NV];
+  bool affine, relu;
+  __device__ __forceinline__ void init(const mrg_act& a, int lane, int D4) {
+    affine = a.scale != nullptr;
+    relu = a.relu != 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (affine && c4 < D4) {
+        sc[v] = ldg4(a.scale + 4 * c4);
+        sh[v] = ldg4(a.shift + 4 * c4);
+      } else {
+        sc[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+        sh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  __device__ __forceinline__ float4 apply(float4 x, int v) const {
+    if (affine) {
+      x.x = fmaf(sc[v].x, x.x, sh[v].x);
+      x.y = fmaf(sc[v].y, x.y, sh[v].y);
+      x.z = fmaf(sc[v].z, x.z, sh[v].z);
+      x.w = fmaf(sc[v].w, x.w, sh[v].w);
+    }
+    if (relu) {
+      x.x = x.x > 0.f ? x.x : 0.f;
+      x.y = x.y > 0.f ? x.y : 0.f;
+      x.z = x.z > 0.f ? x.z : 0.f;
+      x.w = x.w > 0.f ? x.w : 0.f;
+    }
+    return x;
+  }
+};
+
+// Column (sum, sum of squares) accumulation: fp32 per lane, folded into double every
+// kFoldRows rows, reduced over the CTA's warps in a fixed order, written as this CTA's partial.
+template <int NV>
+struct ColStats {
+  float4 fs[NV], fq[NV];
+  double ds[NV][4], dq[NV][4];
+  int pending;
+  __device__ __forceinline__ void init() {
+    pending = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      fs[v] = fq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ds[v][k] = dq[v][k] = 0.0;
+    }
+  }
+  __device__ __forceinline__ void add(float4 a, float4 b, int v) {  // sum += a ; sq += b
+    fs[v].x += a.x; fs[v].y += a.y; fs[v].z += a.z; fs[v].w += a.w;
+    fq[v].x += b.x; fq[v].y += b.y; fq[v].z += b.z; fq[v].w += b.w;
+  }
+  __device__ __forceinline__ void add_sq(float4 a, int v) {
+    add(a, make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w), v);
+  }
+  __device__ __forceinline__ void fold() {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      ds[v][0] += fs[v].x; ds[v][1] += fs[v].y; ds[v][2] += fs[v].z; ds[v][3] += fs[v].w;
+      dq[v][0] += fq[v].x; dq[v][1] += fq[v].y; dq[v][2] += fq[v].z; dq[v][3] += fq[v].w;
+      fs[v] = fq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    pending = 0;
+  }
+  __device__ __forceinline__ void row_done() {
+    if (++pending == kFoldRows) fold();
+  }
+  // part: this CTA's [2][D] doubles.  smem: kWarpsPerBlock*D doubles of scratch.
+  __device__ __forceinline__ void write_block(double* part, int D, int D4, double* smem) {
+    fold();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        int c4 = lane + 32 * v;
+        if (c4 < D4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) smem[warp * D + 4 * c4 + k] = pass == 0 ? ds[v][k] : dq[v][k];
+        }
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; ++w) t += smem[w * D + c];
+        part[pass * D + c] = t;
+      }
+    }
+  }
+};
+
+}  // namespace mrg

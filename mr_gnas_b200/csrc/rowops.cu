@@ -1,0 +1,850 @@
+// Row-streaming kernels (HBM-bound): gather+compose, BatchNorm statistics/apply/backward,
+// collapsed sparse gate, dense-gate epilogue, sigmoid+BCE.  One warp per row, 128-bit
+// accesses, persistent grid of <= 148*4 CTAs so per-column statistics reduce in registers.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mrg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return MRG_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 gather + compose (+ column stats)
+// ---------------------------------------------------------------------------------------
+template <int NV, int COMP, bool STATS>
+__global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const float* __restrict__ h,
+                                                               const int32_t* __restrict__ h_idx,
+                                                               const float* __restrict__ r,
+                                                               const int32_t* __restrict__ r_idx, int64_t rows, int D,
+                                                               float* __restrict__ y, double* __restrict__ stats) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ColStats<NV> cs;
+  if (STATS) cs.init();
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const int64_t hi = h_idx ? (int64_t)__ldg(h_idx + row) : row;
+    const int64_t ri = r_idx ? (int64_t)__ldg(r_idx + row) : row;
+    const float* hp = h + hi * D;
+    const float* rp = r + ri * D;
+    float4 a[NV], b[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        a[v] = ldg4(hp + 4 * c4);
+        b[v] = ldg4(rp + 4 * c4);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        float4 o;
+        if (COMP == MRG_COMP_SUB) o = make_float4(a[v].x - b[v].x, a[v].y - b[v].y, a[v].z - b[v].z, a[v].w - b[v].w);
+        else if (COMP == MRG_COMP_MULT) o = make_float4(a[v].x * b[v].x, a[v].y * b[v].y, a[v].z * b[v].z, a[v].w * b[v].w);
+        else o = make_float4(a[v].x + b[v].x, a[v].y + b[v].y, a[v].z + b[v].z, a[v].w + b[v].w);
+        st_stream4(y + row * D + 4 * c4, o);
+        if (STATS) cs.add_sq(o, v);
+      }
+    }
+    if (STATS) cs.row_done();
+  }
+  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+}
+
+template <int NV, int COMP>
+__global__ void __launch_bounds__(kThreads) compose_bwd_rows_kernel(const float* __restrict__ dy,
+                                                                    const float* __restrict__ x,
+                                                                    const float* __restrict__ r, int64_t rows, int D,
+                                                                    float* __restrict__ dx, float* __restrict__ dr) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 g = ld_stream4(dy + off);
+        if (COMP == MRG_COMP_MULT) {
+          float4 xv = ld_stream4(x + off), rv = ld_stream4(r + off);
+          if (dx) st_stream4(dx + off, make_float4(g.x * rv.x, g.y * rv.y, g.z * rv.z, g.w * rv.w));
+          if (dr) st_stream4(dr + off, make_float4(g.x * xv.x, g.y * xv.y, g.z * xv.z, g.w * xv.w));
+        } else {
+          if (dx) st_stream4(dx + off, g);
+          if (dr) {
+            if (COMP == MRG_COMP_SUB) g = make_float4(-g.x, -g.y, -g.z, -g.w);
+            st_stream4(dr + off, g);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// column stats / BN finalize / affine-act / BN backward
+// ---------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kThreads) colstats_kernel(mrg_act x, int64_t rows, int D,
+                                                            double* __restrict__ stats) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ax;
+  ax.init(x, lane, D4);
+  ColStats<NV> cs;
+  cs.init();
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) cs.add_sq(ax.apply(ld_stream4(x.data + (size_t)row * D + 4 * c4), v), v);
+    }
+    cs.row_done();
+  }
+  cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int nparts, int64_t rows, int D,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean_o,
+                                   float* invstd_o, float* a_o, float* b_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    s += stats[(size_t)p * 2 * D + c];
+    q += stats[(size_t)p * 2 * D + D + c];
+  }
+  const double n = (double)rows;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + (double)eps);
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  if (mean_o) mean_o[c] = (float)mean;
+  if (invstd_o) invstd_o[c] = (float)invstd;
+  const double a = (double)g * invstd;
+  a_o[c] = (float)a;
+  b_o[c] = (float)((double)bt - a * mean);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads) affine_act_kernel(mrg_act x, int64_t rows, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ax;
+  ax.init(x, lane, D4);
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        st_stream4(out + off, ax.apply(ld_stream4(x.data + off), v));
+      }
+    }
+  }
+}
+
+// dz = ds * [act(y) > 0] (if relu);  partial sums of dz and dz*y
+template <int NV>
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __restrict__ ds, mrg_act y, int64_t rows,
+                                                                 int D, double* __restrict__ stats) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ay;
+  ay.init(y, lane, D4);
+  ColStats<NV> cs;
+  cs.init();
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 yv = ld_stream4(y.data + off);
+        float4 g = ld_stream4(ds + off);
+        if (ay.relu) {
+          float4 s = ay.apply(yv, v);
+          g.x = s.x > 0.f ? g.x : 0.f;
+          g.y = s.y > 0.f ? g.y : 0.f;
+          g.z = s.z > 0.f ? g.z : 0.f;
+          g.w = s.w > 0.f ? g.w : 0.f;
+        }
+        cs.add(g, make_float4(g.x * yv.x, g.y * yv.y, g.z * yv.z, g.w * yv.w), v);
+      }
+    }
+    cs.row_done();
+  }
+  cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int nparts, int64_t rows, int D,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    s1 += stats[(size_t)p * 2 * D + c];
+    s2 += stats[(size_t)p * 2 * D + D + c];
+  }
+  const double mu = mean[c], is = invstd[c], g = gamma ? gamma[c] : 1.0, n = (double)rows;
+  const double dg = is * (s2 - mu * s1);  // sum dz * xhat
+  if (dgamma) dgamma[c] = (float)dg;
+  if (dbeta) dbeta[c] = (float)s1;
+  const double c2 = g * is;
+  const double c1 = -g * is * is * dg / n;
+  const double c0 = -c2 * s1 / n - c1 * mu;
+  coef[c] = (float)c0;
+  coef[D + c] = (float)c1;
+  coef[2 * D + c] = (float)c2;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __restrict__ ds, mrg_act y,
+                                                                const float* __restrict__ coef, int64_t rows, int D,
+                                                                float* dy, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ay;
+  ay.init(y, lane, D4);
+  float4 c0[NV], c1[NV], c2[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    int c4 = lane + 32 * v;
+    if (c4 < D4) {
+      c0[v] = ldg4(coef + 4 * c4);
+      c1[v] = ldg4(coef + D + 4 * c4);
+      c2[v] = ldg4(coef + 2 * D + 4 * c4);
+    }
+  }
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 yv = ld_stream4(y.data + off);
+        float4 g = *reinterpret_cast<const float4*>(ds + off);  // may alias dy
+        if (ay.relu) {
+          float4 s = ay.apply(yv, v);
+          g.x = s.x > 0.f ? g.x : 0.f;
+          g.y = s.y > 0.f ? g.y : 0.f;
+          g.z = s.z > 0.f ? g.z : 0.f;
+          g.w = s.w > 0.f ? g.w : 0.f;
+        }
+        float4 o;
+        o.x = fmaf(c2[v].x, g.x, fmaf(c1[v].x, yv.x, c0[v].x));
+        o.y = fmaf(c2[v].y, g.y, fmaf(c1[v].y, yv.y, c0[v].y));
+        o.z = fmaf(c2[v].z, g.z, fmaf(c1[v].z, yv.z, c0[v].z));
+        o.w = fmaf(c2[v].w, g.w, fmaf(c1[v].w, yv.w, c0[v].w));
+        if (accumulate) {
+          float4 p = *reinterpret_cast<const float4*>(dy + off);
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        st4(dy + off, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3/K6 collapsed sparse gate
+// ---------------------------------------------------------------------------------------
+template <int NV, bool HAS_IN, bool SAME, bool STATS>
+__global__ void __launch_bounds__(kThreads) sparse_gate_fwd_kernel(mrg_act x, mrg_act xin, int64_t rows, int D,
+                                                                   const float* __restrict__ v1,
+                                                                   const float* __restrict__ v2,
+                                                                   const float* __restrict__ cptr,
+                                                                   const float* __restrict__ row_scale,
+                                                                   float base_scale, float* __restrict__ y,
+                                                                   float* __restrict__ gate,
+                                                                   double* __restrict__ stats) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ax, ai;
+  ax.init(x, lane, D4);
+  if (HAS_IN) ai.init(xin, lane, D4);
+  float4 w1[NV], w2[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    int c4 = lane + 32 * v;
+    w1[v] = w2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < D4) {
+      w1[v] = ldg4(v1 + 4 * c4);
+      if (HAS_IN) w2[v] = ldg4(v2 + 4 * c4);
+    }
+  }
+  const float c = __ldg(cptr);
+  ColStats<NV> cs;
+  if (STATS) cs.init();
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    float4 xv[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      xv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 raw = ld_stream4(x.data + off);
+        xv[v] = ax.apply(raw, v);
+        dot += xv[v].x * w1[v].x + xv[v].y * w1[v].y + xv[v].z * w1[v].z + xv[v].w * w1[v].w;
+        if (HAS_IN) {
+          float4 iv = SAME ? ai.apply(raw, v) : ai.apply(ld_stream4(xin.data + off), v);
+          dot += iv.x * w2[v].x + iv.y * w2[v].y + iv.z * w2[v].z + iv.w * w2[v].w;
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    const float g = sigmoidf_(dot + c);
+    const float sc = base_scale * (row_scale ? __ldg(row_scale + row) : 1.f) * g;
+    if (lane == 0) gate[row] = g;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        float4 o = make_float4(sc * xv[v].x, sc * xv[v].y, sc * xv[v].z, sc * xv[v].w);
+        st_stream4(y + (size_t)row * D + 4 * c4, o);
+        if (STATS) cs.add_sq(o, v);
+      }
+    }
+    if (STATS) cs.row_done();
+  }
+  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+}
+
+// dparam partial per CTA: [dv1[D] | dv2[D] | dc] doubles
+template <int NV, bool HAS_IN, bool SAME>
+__global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* __restrict__ dy, mrg_act x,
+                                                                   mrg_act xin, const float* __restrict__ gate,
+                                                                   int64_t rows, int D, const float* __restrict__ v1,
+                                                                   const float* __restrict__ v2,
+                                                                   const float* __restrict__ row_scale,
+                                                                   float base_scale, float* dx, float* dxin,
+                                                                   int accumulate, double* __restrict__ dparam) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ax, ai;
+  ax.init(x, lane, D4);
+  if (HAS_IN) ai.init(xin, lane, D4);
+  float4 w1[NV], w2[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    int c4 = lane + 32 * v;
+    w1[v] = w2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < D4) {
+      w1[v] = ldg4(v1 + 4 * c4);
+      if (HAS_IN) w2[v] = ldg4(v2 + 4 * c4);
+    }
+  }
+  // ColStats reused: "sum" slot accumulates dt*x (dv1), "sq" slot accumulates dt*xin (dv2)
+  ColStats<NV> cs;
+  cs.init();
+  float dc_f = 0.f;
+  double dc_d = 0.0;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    float4 xv[NV], iv[NV], gv[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      xv[v] = iv[v] = gv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 raw = ld_stream4(x.data + off);
+        xv[v] = ax.apply(raw, v);
+        if (HAS_IN) iv[v] = SAME ? ai.apply(raw, v) : ai.apply(ld_stream4(xin.data + off), v);
+        gv[v] = ld_stream4(dy + off);
+        dot += gv[v].x * xv[v].x + gv[v].y * xv[v].y + gv[v].z * xv[v].z + gv[v].w * xv[v].w;
+      }
+    }
+    dot = warp_sum(dot);
+    const float g = __ldg(gate + row);
+    const float sc = base_scale * (row_scale ? __ldg(row_scale + row) : 1.f);
+    const float dt = sc * g * (1.f - g) * dot;
+    const float sg = sc * g;
+    if (lane == 0) dc_f += dt;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 o;
+        o.x = fmaf(sg, gv[v].x, dt * w1[v].x);
+        o.y = fmaf(sg, gv[v].y, dt * w1[v].y);
+        o.z = fmaf(sg, gv[v].z, dt * w1[v].z);
+        o.w = fmaf(sg, gv[v].w, dt * w1[v].w);
+        float4 oi = make_float4(dt * w2[v].x, dt * w2[v].y, dt * w2[v].z, dt * w2[v].w);
+        if (HAS_IN && SAME) {  // dx and dxin are the same buffer: one combined write
+          o.x += oi.x; o.y += oi.y; o.z += oi.z; o.w += oi.w;
+        }
+        if (dx) {
+          if (accumulate) {
+            float4 p = *reinterpret_cast<const float4*>(dx + off);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          st4(dx + off, o);
+        }
+        if (HAS_IN && !SAME && dxin) {
+          if (accumulate) {
+            float4 p = *reinterpret_cast<const float4*>(dxin + off);
+            oi.x += p.x; oi.y += p.y; oi.z += p.z; oi.w += p.w;
+          }
+          st4(dxin + off, oi);
+        }
+        cs.add(make_float4(dt * xv[v].x, dt * xv[v].y, dt * xv[v].z, dt * xv[v].w),
+               make_float4(dt * iv[v].x, dt * iv[v].y, dt * iv[v].z, dt * iv[v].w), v);
+      }
+    }
+    cs.row_done();
+    if (cs.pending == 0) {
+      dc_d += dc_f;
+      dc_f = 0.f;
+    }
+  }
+  dc_d += dc_f;
+  double* part = dparam + (size_t)blockIdx.x * (2 * D + 1);
+  cs.write_block(part, D, D4, smem_d);
+  __syncthreads();
+  if (lane == 0) smem_d[warp] = dc_d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += smem_d[w];
+    part[2 * D] = t;
+  }
+}
+
+__global__ void sparse_gate_bwd_finalize_kernel(const double* __restrict__ dparam, int nparts, int D, float* dv1,
+                                                float* dv2, float* dc) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > 2 * D) return;
+  double t = 0.0;
+  for (int p = 0; p < nparts; ++p) t += dparam[(size_t)p * (2 * D + 1) + c];
+  if (c < D) {
+    if (dv1) dv1[c] = (float)t;
+  } else if (c < 2 * D) {
+    if (dv2) dv2[c - D] = (float)t;
+  } else if (dc) {
+    dc[0] = (float)t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// dense gate epilogue (after the edge-tile GEMM)
+// ---------------------------------------------------------------------------------------
+template <int NV, bool STATS>
+__global__ void __launch_bounds__(kThreads) dense_gate_fwd_kernel(const float* __restrict__ z, mrg_act x, int64_t rows,
+                                                                  int D, int use_sigmoid,
+                                                                  const float* __restrict__ row_scale,
+                                                                  float base_scale, float* __restrict__ y,
+                                                                  double* __restrict__ stats) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ax;
+  if (use_sigmoid) ax.init(x, lane, D4);
+  ColStats<NV> cs;
+  if (STATS) cs.init();
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const float sc = base_scale * (row_scale ? __ldg(row_scale + row) : 1.f);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 zv = ld_stream4(z + off);
+        float4 o;
+        if (use_sigmoid) {
+          float4 xv = ax.apply(ld_stream4(x.data + off), v);
+          o = make_float4(sc * sigmoidf_(zv.x) * xv.x, sc * sigmoidf_(zv.y) * xv.y, sc * sigmoidf_(zv.z) * xv.z,
+                          sc * sigmoidf_(zv.w) * xv.w);
+        } else {
+          o = make_float4(sc * zv.x, sc * zv.y, sc * zv.z, sc * zv.w);
+        }
+        st_stream4(y + off, o);
+        if (STATS) cs.add_sq(o, v);
+      }
+    }
+    if (STATS) cs.row_done();
+  }
+  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads) dense_gate_bwd_kernel(const float* __restrict__ dy,
+                                                                  const float* __restrict__ z, mrg_act x, int64_t rows,
+                                                                  int D, int use_sigmoid,
+                                                                  const float* __restrict__ row_scale,
+                                                                  float base_scale, float* __restrict__ dz, float* dx,
+                                                                  int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  ActRegs<NV> ax;
+  if (use_sigmoid) ax.init(x, lane, D4);
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const float sc = base_scale * (row_scale ? __ldg(row_scale + row) : 1.f);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 g = ld_stream4(dy + off);
+        if (!use_sigmoid) {
+          st_stream4(dz + off, make_float4(sc * g.x, sc * g.y, sc * g.z, sc * g.w));
+          continue;
+        }
+        float4 zv = ld_stream4(z + off);
+        float4 xv = ax.apply(ld_stream4(x.data + off), v);
+        float4 s = make_float4(sigmoidf_(zv.x), sigmoidf_(zv.y), sigmoidf_(zv.z), sigmoidf_(zv.w));
+        st_stream4(dz + off, make_float4(sc * g.x * xv.x * s.x * (1.f - s.x), sc * g.y * xv.y * s.y * (1.f - s.y),
+                                         sc * g.z * xv.z * s.z * (1.f - s.z), sc * g.w * xv.w * s.w * (1.f - s.w)));
+        if (dx) {
+          float4 o = make_float4(sc * g.x * s.x, sc * g.y * s.y, sc * g.z * s.z, sc * g.w * s.w);
+          if (accumulate) {
+            float4 p = *reinterpret_cast<const float4*>(dx + off);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          st4(dx + off, o);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K8 epilogue: sigmoid + BCE (elementwise over B*N logits)
+// ---------------------------------------------------------------------------------------
+constexpr int kBceBlocks = kNumSMs * 8;
+
+__device__ __forceinline__ float bce_term(float logit, float yv, float* p_out) {
+  const float p = sigmoidf_(logit);
+  *p_out = p;
+  const float lp = fmaxf(logf(p), -100.f);
+  const float l1p = fmaxf(logf(1.f - p), -100.f);
+  return -(yv * lp + (1.f - yv) * l1p);
+}
+
+__global__ void __launch_bounds__(kThreads) sigmoid_bce_fwd_kernel(const float* __restrict__ logit,
+                                                                   const float* __restrict__ label, int64_t n,
+                                                                   float* __restrict__ pred,
+                                                                   double* __restrict__ partial) {
+  __shared__ double sm[kWarpsPerBlock];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  double acc = 0.0;
+  float facc = 0.f;
+  int cnt = 0;
+  for (int64_t i = tid; i < n4; i += nthreads) {
+    float4 l = ld_stream4(logit + 4 * i), yv = ld_stream4(label + 4 * i), p;
+    facc += bce_term(l.x, yv.x, &p.x) + bce_term(l.y, yv.y, &p.y) + bce_term(l.z, yv.z, &p.z) +
+            bce_term(l.w, yv.w, &p.w);
+    if (pred) st_stream4(pred + 4 * i, p);
+    if (++cnt == 8) {
+      acc += facc;
+      facc = 0.f;
+      cnt = 0;
+    }
+  }
+  for (int64_t i = 4 * n4 + tid; i < n; i += nthreads) {
+    float p;
+    facc += bce_term(logit[i], label[i], &p);
+    if (pred) pred[i] = p;
+  }
+  acc += facc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += sm[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void bce_finalize_kernel(const double* __restrict__ partial, int nparts, int64_t n, float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int p = 0; p < nparts; ++p) t += partial[p];
+    loss[0] = (float)(t / (double)n);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sigmoid_bce_bwd_kernel(const float* __restrict__ logit,
+                                                                   const float* __restrict__ label, int64_t n,
+                                                                   const float* __restrict__ gscale,
+                                                                   float* __restrict__ dlogit) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const float gs = (gscale ? __ldg(gscale) : 1.f) / (float)n;
+  auto f = [gs](float l, float yv) {
+    const float p = sigmoidf_(l);
+    const float pq = p * (1.f - p);
+    return gs * (p - yv) * pq / fmaxf(pq, 1e-12f);
+  };
+  const int64_t n4 = n >> 2;
+  for (int64_t i = tid; i < n4; i += nthreads) {
+    float4 l = ld_stream4(logit + 4 * i), yv = ld_stream4(label + 4 * i);
+    st_stream4(dlogit + 4 * i, make_float4(f(l.x, yv.x), f(l.y, yv.y), f(l.z, yv.z), f(l.w, yv.w)));
+  }
+  for (int64_t i = 4 * n4 + tid; i < n; i += nthreads) dlogit[i] = f(logit[i], label[i]);
+}
+
+}  // namespace mrg
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace mrg;
+
+extern "C" int mrg_abi_version(void) { return MRG_ABI_VERSION; }
+extern "C" const char* mrg_last_error(void) { return g_err; }
+extern "C" int32_t mrg_stats_nparts(int64_t rows) { return stats_grid(rows); }
+extern "C" int32_t mrg_stats_max_parts(void) { return kMaxParts; }
+
+static inline size_t stats_smem(int D) { return (size_t)kWarpsPerBlock * D * sizeof(double); }
+
+extern "C" int mrg_compose_fwd(const float* h, const int32_t* h_idx, const float* r, const int32_t* r_idx,
+                               int64_t rows, int32_t D, int32_t comp, float* y, double* stats, void* stream) {
+  MRG_CHECK_ARG(h && r && y, "compose_fwd: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "compose_fwd: D must be a multiple of 4 and <= 512");
+  MRG_CHECK_ARG(comp >= 0 && comp <= 2, "compose_fwd: comp");
+  if (rows <= 0 && !stats) return MRG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stats_grid(rows);
+  const size_t sm = stats ? stats_smem(D) : 0;
+#define L(COMP)                                                                                              \
+  MRG_DISPATCH_NV(D, if (stats) compose_fwd_kernel<NV, COMP, true><<<grid, kThreads, sm, st>>>(h, h_idx, r, r_idx, rows, D, y, stats); \
+                  else compose_fwd_kernel<NV, COMP, false><<<grid, kThreads, 0, st>>>(h, h_idx, r, r_idx, rows, D, y, stats))
+  if (comp == MRG_COMP_SUB) L(MRG_COMP_SUB);
+  else if (comp == MRG_COMP_MULT) L(MRG_COMP_MULT);
+  else L(MRG_COMP_ADD);
+#undef L
+  MRG_LAUNCH_CHECK("compose_fwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_compose_bwd_rows(const float* dy, const float* x, const float* r, int64_t rows, int32_t D,
+                                    int32_t comp, float* dx, float* dr, void* stream) {
+  MRG_CHECK_ARG(dy, "compose_bwd_rows: null dy");
+  MRG_CHECK_ARG(valid_D(D), "compose_bwd_rows: D");
+  MRG_CHECK_ARG(comp != MRG_COMP_MULT || (x && r), "compose_bwd_rows: mult needs x and r");
+  if (rows <= 0) return MRG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stats_grid(rows);
+  if (comp == MRG_COMP_SUB) MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, MRG_COMP_SUB><<<grid, kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr));
+  else if (comp == MRG_COMP_MULT) MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, MRG_COMP_MULT><<<grid, kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr));
+  else MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, MRG_COMP_ADD><<<grid, kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr));
+  MRG_LAUNCH_CHECK("compose_bwd_rows");
+  return MRG_OK;
+}
+
+extern "C" int mrg_colstats(mrg_act x, int64_t rows, int32_t D, double* stats, void* stream) {
+  MRG_CHECK_ARG(x.data && stats, "colstats: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "colstats: D");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stats_grid(rows);
+  MRG_DISPATCH_NV(D, colstats_kernel<NV><<<grid, kThreads, stats_smem(D), st>>>(x, rows, D, stats));
+  MRG_LAUNCH_CHECK("colstats");
+  return MRG_OK;
+}
+
+extern "C" int mrg_bn_finalize(const double* stats, int32_t nparts, int64_t rows, int32_t D, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean,
+                               float* running_var, float* mean, float* invstd, float* a, float* b, void* stream) {
+  MRG_CHECK_ARG(stats && a && b, "bn_finalize: null pointer");
+  MRG_CHECK_ARG(rows > 0 && nparts > 0, "bn_finalize: rows/nparts");
+  bn_finalize_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, nparts, rows, D, gamma, beta, eps,
+                                                                        momentum, running_mean, running_var, mean,
+                                                                        invstd, a, b);
+  MRG_LAUNCH_CHECK("bn_finalize");
+  return MRG_OK;
+}
+
+extern "C" int mrg_affine_act(mrg_act x, int64_t rows, int32_t D, float* out, void* stream) {
+  MRG_CHECK_ARG(x.data && out, "affine_act: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "affine_act: D");
+  if (rows <= 0) return MRG_OK;
+  MRG_DISPATCH_NV(D, affine_act_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(x, rows, D, out));
+  MRG_LAUNCH_CHECK("affine_act");
+  return MRG_OK;
+}
+
+extern "C" int mrg_bn_bwd_reduce(const float* ds, mrg_act y, int64_t rows, int32_t D, double* bwd_stats,
+                                 void* stream) {
+  MRG_CHECK_ARG(ds && y.data && bwd_stats, "bn_bwd_reduce: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "bn_bwd_reduce: D");
+  MRG_DISPATCH_NV(D, bn_bwd_reduce_kernel<NV><<<stats_grid(rows), kThreads, stats_smem(D), (cudaStream_t)stream>>>(
+                         ds, y, rows, D, bwd_stats));
+  MRG_LAUNCH_CHECK("bn_bwd_reduce");
+  return MRG_OK;
+}
+
+extern "C" int mrg_bn_bwd_finalize(const double* bwd_stats, int32_t nparts, int64_t rows, int32_t D,
+                                   const float* gamma, const float* mean, const float* invstd, float* dgamma,
+                                   float* dbeta, float* coef, void* stream) {
+  MRG_CHECK_ARG(bwd_stats && mean && invstd && coef, "bn_bwd_finalize: null pointer");
+  bn_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bwd_stats, nparts, rows, D, gamma, mean,
+                                                                            invstd, dgamma, dbeta, coef);
+  MRG_LAUNCH_CHECK("bn_bwd_finalize");
+  return MRG_OK;
+}
+
+extern "C" int mrg_bn_bwd_apply(const float* ds, mrg_act y, const float* coef, int64_t rows, int32_t D, float* dy,
+                                int32_t accumulate, void* stream) {
+  MRG_CHECK_ARG(ds && y.data && coef && dy, "bn_bwd_apply: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "bn_bwd_apply: D");
+  if (rows <= 0) return MRG_OK;
+  MRG_DISPATCH_NV(D, bn_bwd_apply_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(
+                         ds, y, coef, rows, D, dy, accumulate));
+  MRG_LAUNCH_CHECK("bn_bwd_apply");
+  return MRG_OK;
+}
+
+extern "C" int mrg_sparse_gate_fwd(mrg_act x, mrg_act xin, int64_t rows, int32_t D, const float* v1, const float* v2,
+                                   const float* c, const float* row_scale, float base_scale, float* y, float* gate,
+                                   double* stats, void* stream) {
+  MRG_CHECK_ARG(x.data && v1 && c && y && gate, "sparse_gate_fwd: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "sparse_gate_fwd: D");
+  MRG_CHECK_ARG(!xin.data || v2, "sparse_gate_fwd: xin needs v2");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stats_grid(rows);
+  const bool has_in = xin.data != nullptr, same = has_in && xin.data == x.data;
+#define L(HI, SM_, ST_) sparse_gate_fwd_kernel<NV, HI, SM_, ST_><<<grid, kThreads, ST_ ? stats_smem(D) : 0, st>>>( \
+      x, xin, rows, D, v1, v2, c, row_scale, base_scale, y, gate, stats)
+  MRG_DISPATCH_NV(D, if (stats) { if (!has_in) L(false, false, true); else if (same) L(true, true, true); else L(true, false, true); }
+                     else { if (!has_in) L(false, false, false); else if (same) L(true, true, false); else L(true, false, false); });
+#undef L
+  MRG_LAUNCH_CHECK("sparse_gate_fwd");
+  return MRG_OK;
+}
+
+extern "C" int64_t mrg_gate_dparam_count(int64_t rows, int32_t D) { return (int64_t)stats_grid(rows) * (2 * D + 1); }
+
+extern "C" int mrg_sparse_gate_bwd(const float* dy, mrg_act x, mrg_act xin, const float* gate, int64_t rows,
+                                   int32_t D, const float* v1, const float* v2, const float* row_scale,
+                                   float base_scale, float* dx, float* dxin, int32_t accumulate, double* dparam,
+                                   void* stream) {
+  MRG_CHECK_ARG(dy && x.data && gate && v1 && dparam, "sparse_gate_bwd: null pointer");
+  MRG_CHECK_ARG(valid_D(D), "sparse_gate_bwd: D");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stats_grid(rows);
+  const bool has_in = xin.data != nullptr;
+  const bool same = has_in && xin.data == x.data && dxin == dx;
+#define L(HI, SM_) sparse_gate_bwd_kernel<NV, HI, SM_><<<grid, kThreads, stats_smem(D), st>>>( \
+      dy, x, xin, gate, rows, D, v1, v2, row_scale, base_scale, dx, dxin, accumulate, dparam)
+  MRG_DISPATCH_NV(D, if (!has_in) L(false, false); else if (same) L(true, true); else L(true, false));
+#undef L
+  MRG_LAUNCH_CHECK("sparse_gate_bwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_sparse_gate_bwd_finalize(const double* dparam, int64_t rows, int32_t D, float* dv1, float* dv2,
+                                            float* dc, void* stream) {
+  MRG_CHECK_ARG(dparam, "sparse_gate_bwd_finalize: null pointer");
+  const int n = 2 * D + 1;
+  sparse_gate_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dparam, stats_grid(rows), D, dv1,
+                                                                                     dv2, dc);
+  MRG_LAUNCH_CHECK("sparse_gate_bwd_finalize");
+  return MRG_OK;
+}
+
+extern "C" int mrg_dense_gate_fwd(const float* z, mrg_act x, int64_t rows, int32_t D, int32_t use_sigmoid,
+                                  const float* row_scale, float base_scale, float* y, double* stats, void* stream) {
+  MRG_CHECK_ARG(z && y, "dense_gate_fwd: null pointer");
+  MRG_CHECK_ARG(!use_sigmoid || x.data, "dense_gate_fwd: sigmoid form needs x");
+  MRG_CHECK_ARG(valid_D(D), "dense_gate_fwd: D");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stats_grid(rows);
+  MRG_DISPATCH_NV(D, if (stats) dense_gate_fwd_kernel<NV, true><<<grid, kThreads, stats_smem(D), st>>>(z, x, rows, D, use_sigmoid, row_scale, base_scale, y, stats);
+                     else dense_gate_fwd_kernel<NV, false><<<grid, kThreads, 0, st>>>(z, x, rows, D, use_sigmoid, row_scale, base_scale, y, stats));
+  MRG_LAUNCH_CHECK("dense_gate_fwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_dense_gate_bwd(const float* dy, const float* z, mrg_act x, int64_t rows, int32_t D,
+                                  int32_t use_sigmoid, const float* row_scale, float base_scale, float* dz, float* dx,
+                                  int32_t accumulate, void* stream) {
+  MRG_CHECK_ARG(dy && dz, "dense_gate_bwd: null pointer");
+  MRG_CHECK_ARG(!use_sigmoid || (x.data && z), "dense_gate_bwd: sigmoid form needs x and z");
+  MRG_CHECK_ARG(valid_D(D), "dense_gate_bwd: D");
+  if (rows <= 0) return MRG_OK;
+  MRG_DISPATCH_NV(D, dense_gate_bwd_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(
+                         dy, z, x, rows, D, use_sigmoid, row_scale, base_scale, dz, dx, accumulate));
+  MRG_LAUNCH_CHECK("dense_gate_bwd");
+  return MRG_OK;
+}
+
+static inline int bce_grid(int64_t n) {
+  int64_t need = (n / 4 + kThreads - 1) / kThreads;
+  if (need < 1) need = 1;
+  return (int)(need < kBceBlocks ? need : kBceBlocks);
+}
+extern "C" int32_t mrg_bce_nparts(int64_t n) { return bce_grid(n); }
+
+extern "C" int mrg_sigmoid_bce_fwd(const float* logit, const float* label, int64_t n, float* pred, double* partial,
+                                   float* loss, void* stream) {
+  MRG_CHECK_ARG(logit && label && partial && loss && n > 0, "sigmoid_bce_fwd: null pointer / n");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = bce_grid(n);
+  sigmoid_bce_fwd_kernel<<<grid, kThreads, 0, st>>>(logit, label, n, pred, partial);
+  bce_finalize_kernel<<<1, 32, 0, st>>>(partial, grid, n, loss);
+  MRG_LAUNCH_CHECK("sigmoid_bce_fwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64_t n, const float* gscale,
+                                   float* dlogit, void* stream) {
+  MRG_CHECK_ARG(logit && label && dlogit && n > 0, "sigmoid_bce_bwd: null pointer / n");
+  sigmoid_bce_bwd_kernel<<<bce_grid(n), kThreads, 0, (cudaStream_t)stream>>>(logit, label, n, gscale, dlogit);
+  MRG_LAUNCH_CHECK("sigmoid_bce_bwd");
+  return MRG_OK;
+}

@@ -1,0 +1,370 @@
+"""torch.autograd glue over the libmrgnas C ABI: one Function per kernel family.  torch is
+used for device memory, streams and the tape only; all arithmetic on [rows, D] feature
+matrices happens in the hand-written CUDA kernels (no eager / CPU fallback)."""
+import torch
+
+from . import _lib
+from ._lib import act, call, ptr, stream
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stats_buf(nparts, D, device):
+    return torch.empty(max(nparts, 1) * 2 * D, dtype=torch.float64, device=device)
+
+
+def stats_nparts(rows):
+    return int(_lib.load().mrg_stats_nparts(int(rows)))
+
+
+# ------------------------------------------------------------------------------------------
+# K1: compose (elementwise op form) and gather+compose (fused network form)
+# ------------------------------------------------------------------------------------------
+class ComposeRows(torch.autograd.Function):
+    """pre_sub / pre_mult / pre_add on already gathered rows (operations_lp.py:71-98)."""
+
+    @staticmethod
+    def forward(ctx, x, hr, comp):
+        x, hr = _f32c(x), _f32c(hr)
+        rows, D = x.shape
+        y = torch.empty_like(x)
+        call("mrg_compose_fwd", ptr(x), None, ptr(hr), None, rows, D, comp, ptr(y), None, stream())
+        ctx.comp = comp
+        ctx.save_for_backward(*((x, hr) if comp == 1 else ()))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32c(dy)
+        rows, D = dy.shape
+        x, hr = ctx.saved_tensors if ctx.comp == 1 else (None, None)
+        dx = torch.empty_like(dy) if ctx.needs_input_grad[0] else None
+        dr = torch.empty_like(dy) if ctx.needs_input_grad[1] else None
+        call("mrg_compose_bwd_rows", ptr(dy), ptr(x), ptr(hr), rows, D, ctx.comp, ptr(dx), ptr(dr), stream())
+        return dx, dr, None
+
+
+def seg_reduce_raw(seg, kind, m_act, D, out, arg=None, mul=None, mul_idx=None, alpha=1.0, residual=None,
+                   accumulate=False):
+    ws = seg.workspace(D, kind)
+    res = residual if residual is not None else act(None)
+    call("mrg_seg_reduce_fwd", kind, m_act, ptr(seg.ptr), ptr(seg.idx), ptr(seg.chunk_first), ptr(seg.chunk_seg),
+         seg.nseg, seg.max_chunks, D, ptr(mul), ptr(mul_idx), float(alpha), res, 1 if accumulate else 0, ptr(out),
+         ptr(arg), ptr(ws), ws.numel(), stream())
+    return out
+
+
+class GatherCompose(torch.autograd.Function):
+    """y[i] = h[src_final[i]] (-|*|+) r[et_final[i]] over the M edge-expanded rows, plus BN
+    column statistics -- model_lp.py:126-131 fused with operations_lp.py:71-98.  Backward is
+    a deterministic segmented sum over the src-CSC (dh) and the relation segments (dr)
+    instead of the reference's atomic index_add_."""
+
+    @staticmethod
+    def forward(ctx, h, r, g, comp):
+        h, r = _f32c(h), _f32c(r)
+        D = h.shape[1]
+        y = torch.empty(g.M, D, dtype=torch.float32, device=h.device)
+        nparts = stats_nparts(g.M)
+        stats = _stats_buf(nparts, D, h.device)
+        call("mrg_compose_fwd", ptr(h), ptr(g.src_final), ptr(r), ptr(g.et_final), g.M, D, comp, ptr(y), ptr(stats),
+             stream())
+        ctx.g, ctx.comp = g, comp
+        ctx.save_for_backward(h, r)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        g, comp = ctx.g, ctx.comp
+        h, r = ctx.saved_tensors
+        dy = _f32c(dy)
+        D = dy.shape[1]
+        dh = dr = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty_like(h)
+            if comp == 1:
+                seg_reduce_raw(g.csc, 0, act(dy), D, dh, mul=r, mul_idx=g.et_final)
+            else:
+                seg_reduce_raw(g.csc, 0, act(dy), D, dh)
+        if ctx.needs_input_grad[1]:
+            dr = torch.empty_like(r)
+            if comp == 1:
+                seg_reduce_raw(g.rel, 0, act(dy), D, dr, mul=h, mul_idx=g.src_final)
+            else:
+                seg_reduce_raw(g.rel, 0, act(dy), D, dr, alpha=-1.0 if comp == 0 else 1.0)
+        return dh, dr, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# BatchNorm1d (+ReLU) over rows
+# ------------------------------------------------------------------------------------------
+class BNAct(torch.autograd.Function):
+    """s = relu?(BN(y)) in one pass after a deterministic column-statistics reduction.
+    Replaces nn.BatchNorm1d + ReLU after every op (model_lp.py:31-33, cell_lp.py:21,31-32).
+    `stats` may carry partial sums already produced by y's producer kernel."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, training, momentum, eps, relu, stats):
+        y = _f32c(y)
+        rows, D = y.shape
+        dev = y.device
+        a = torch.empty(D, dtype=torch.float32, device=dev)
+        b = torch.empty_like(a)
+        if training:
+            nparts = stats_nparts(rows)
+            if stats is None:
+                stats = _stats_buf(nparts, D, dev)
+                call("mrg_colstats", act(y), rows, D, ptr(stats), stream())
+            else:
+                nparts = stats.numel() // (2 * D)
+            mean = torch.empty_like(a)
+            invstd = torch.empty_like(a)
+            call("mrg_bn_finalize", ptr(stats), nparts, rows, D, ptr(gamma), ptr(beta), float(eps), float(momentum),
+                 ptr(running_mean), ptr(running_var), ptr(mean), ptr(invstd), ptr(a), ptr(b), stream())
+        else:
+            invstd = torch.rsqrt(running_var + eps)
+            mean = running_mean
+            a = (gamma * invstd).contiguous()
+            b = (beta - a * mean).contiguous()
+        s = torch.empty_like(y)
+        call("mrg_affine_act", act(y, a, b, relu), rows, D, ptr(s), stream())
+        ctx.training, ctx.relu = training, relu
+        ctx.save_for_backward(y, gamma, mean, invstd, a, b)
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        y, gamma, mean, invstd, a, b = ctx.saved_tensors
+        ds = _f32c(ds)
+        rows, D = y.shape
+        dev = y.device
+        yact = act(y, a, b, ctx.relu)
+        dy = torch.empty_like(y)
+        if ctx.training:
+            nparts = stats_nparts(rows)
+            bst = _stats_buf(nparts, D, dev)
+            call("mrg_bn_bwd_reduce", ptr(ds), yact, rows, D, ptr(bst), stream())
+            dgamma = torch.empty(D, dtype=torch.float32, device=dev)
+            dbeta = torch.empty_like(dgamma)
+            coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
+            call("mrg_bn_bwd_finalize", ptr(bst), nparts, rows, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
+                 ptr(dbeta), ptr(coef), stream())
+            call("mrg_bn_bwd_apply", ptr(ds), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
+        else:
+            coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
+            call("mrg_bn_bwd_apply", ptr(ds), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
+            # eval-mode parameter grads (rarely needed): plain reductions
+            dz = dy / a
+            dgamma = (dz * (y - mean) * invstd).sum(0)
+            dbeta = dz.sum(0)
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def bn_act(y, bn, relu=True, stats=None):
+    """Apply an nn.BatchNorm1d module's parameters/buffers through the fused kernels."""
+    training = bn.training or not bn.track_running_stats
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return BNAct.apply(y, bn.weight, bn.bias, rm, rv, training, momentum, bn.eps, relu, stats)
+
+
+# ------------------------------------------------------------------------------------------
+# K3/K6: collapsed sparse gate over one or more row segments
+# ------------------------------------------------------------------------------------------
+class SparseGate(torch.autograd.Function):
+    """y = scale_i * sigmoid(x.v1 + xin.v2 + c) * x per row segment (v,c collapsed from the
+    reference's W,a Linear pair) -- f_sparse_op_comp / f_sparse_op / f_sparse_op_last."""
+
+    @staticmethod
+    def forward(ctx, x, xin, v1, v2, c, bounds, row_scale, n_scaled, base_scales):
+        x, xin = _f32c(x), _f32c(xin)
+        v1, c = _f32c(v1), _f32c(c)
+        v2 = _f32c(v2) if xin is not None else None
+        rows, D = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        gate = torch.empty(rows, dtype=torch.float32, device=dev)
+        nparts = [stats_nparts(hi - lo) for lo, hi in bounds]
+        stats = _stats_buf(sum(nparts), D, dev)
+        off = 0
+        for s, (lo, hi) in enumerate(bounds):
+            n = hi - lo
+            rs = row_scale[lo:] if (row_scale is not None and lo < n_scaled) else None
+            xa = act(x[lo:hi])
+            ia = act(xin[lo:hi]) if xin is not None else act(None)
+            call("mrg_sparse_gate_fwd", xa, ia, n, D, ptr(v1[s]), ptr(v2[s]) if v2 is not None else None,
+                 ptr(c[s:s + 1]), ptr(rs), float(base_scales[s]), ptr(y[lo:hi]), ptr(gate[lo:hi]),
+                 ptr(stats[off * 2 * D:]), stream())
+            off += nparts[s]
+        ctx.bounds, ctx.n_scaled, ctx.base_scales = bounds, n_scaled, base_scales
+        ctx.has_in = xin is not None
+        ctx.save_for_backward(x, xin, v1, v2, gate, row_scale)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        x, xin, v1, v2, gate, row_scale = ctx.saved_tensors
+        dy = _f32c(dy)
+        rows, D = x.shape
+        dev = x.device
+        dx = torch.empty_like(x)
+        same = ctx.has_in and xin.data_ptr() == x.data_ptr()
+        dxin = dx if same else (torch.empty_like(x) if ctx.has_in else None)
+        dv1 = torch.empty_like(v1)
+        dv2 = torch.empty_like(v2) if ctx.has_in else None
+        dc = torch.empty(len(ctx.bounds), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        for s, (lo, hi) in enumerate(ctx.bounds):
+            n = hi - lo
+            rs = row_scale[lo:] if (row_scale is not None and lo < ctx.n_scaled) else None
+            dparam = torch.empty(int(lib.mrg_gate_dparam_count(n, D)), dtype=torch.float64, device=dev)
+            xa = act(x[lo:hi])
+            ia = act(xin[lo:hi]) if ctx.has_in else act(None)
+            call("mrg_sparse_gate_bwd", ptr(dy[lo:hi]), xa, ia, ptr(gate[lo:hi]), n, D, ptr(v1[s]),
+                 ptr(v2[s]) if ctx.has_in else None, ptr(rs), float(ctx.base_scales[s]), ptr(dx[lo:hi]),
+                 ptr(dxin[lo:hi]) if ctx.has_in else None, 0, ptr(dparam), stream())
+            call("mrg_sparse_gate_bwd_finalize", ptr(dparam), n, D, ptr(dv1[s]), ptr(dv2[s]) if ctx.has_in else None,
+                 ptr(dc[s:s + 1]), stream())
+        if same:
+            return dx, torch.zeros_like(dx), dv1, dv2, dc, None, None, None, None
+        return dx, dxin, dv1, dv2, dc, None, None, None, None
+
+
+class DenseGate(torch.autograd.Function):
+    """y = scale_i * sigmoid?(z) * x : epilogue of f_dense_op_comp / f_comp_op / f_dense_op(_last)
+    after the edge-tile GEMM z = W_s [x, xin] (+b)."""
+
+    @staticmethod
+    def forward(ctx, z, x, use_sigmoid, row_scale, n_scaled, base_scales, bounds):
+        z, x = _f32c(z), _f32c(x)
+        rows, D = z.shape
+        y = torch.empty_like(z)
+        nparts = [stats_nparts(hi - lo) for lo, hi in bounds]
+        stats = _stats_buf(sum(nparts), D, z.device)
+        off = 0
+        for s, (lo, hi) in enumerate(bounds):
+            rs = row_scale[lo:] if (row_scale is not None and lo < n_scaled) else None
+            call("mrg_dense_gate_fwd", ptr(z[lo:hi]), act(x[lo:hi]) if use_sigmoid else act(None), hi - lo, D,
+                 1 if use_sigmoid else 0, ptr(rs), float(base_scales[s]), ptr(y[lo:hi]), ptr(stats[off * 2 * D:]),
+                 stream())
+            off += nparts[s]
+        ctx.meta = (use_sigmoid, n_scaled, base_scales, bounds)
+        ctx.save_for_backward(z, x, row_scale)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        use_sigmoid, n_scaled, base_scales, bounds = ctx.meta
+        z, x, row_scale = ctx.saved_tensors
+        dy = _f32c(dy)
+        D = z.shape[1]
+        dz = torch.empty_like(z)
+        dx = torch.empty_like(z) if use_sigmoid else None
+        for s, (lo, hi) in enumerate(bounds):
+            rs = row_scale[lo:] if (row_scale is not None and lo < n_scaled) else None
+            call("mrg_dense_gate_bwd", ptr(dy[lo:hi]), ptr(z[lo:hi]), act(x[lo:hi]) if use_sigmoid else act(None),
+                 hi - lo, D, 1 if use_sigmoid else 0, ptr(rs), float(base_scales[s]), ptr(dz[lo:hi]),
+                 ptr(dx[lo:hi]) if use_sigmoid else None, 0, stream())
+        return dz, dx, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# K5: destination aggregation (DGL update_all replacement)
+# ------------------------------------------------------------------------------------------
+def decode_arg(arg):
+    """Encoded argmax -> original edge ids (-1 = isolated node); see segreduce.cu."""
+    return torch.where(arg < -1, -2 - arg, arg)
+
+
+class SegReduce(torch.autograd.Function):
+    """out[n] = REDUCE_{e: dst[e]=n} relu?(m[e]) (+ residual[n]) with REDUCE in sum|mean|max.
+    max: isolated node -> 0, arg = lowest edge id attaining the max, gradient to that edge."""
+
+    @staticmethod
+    def forward(ctx, m, residual, g, kind, relu):
+        m, residual = _f32c(m), _f32c(residual)
+        E, D = m.shape
+        N = g.N
+        out = torch.empty(N, D, dtype=torch.float32, device=m.device)
+        arg = torch.empty(N, D, dtype=torch.int32, device=m.device) if kind == 2 else None
+        seg_reduce_raw(g.csr, kind, act(m, relu=relu), D, out, arg=arg,
+                       residual=act(residual) if residual is not None else None)
+        ctx.g, ctx.kind, ctx.relu, ctx.has_res = g, kind, relu, residual is not None
+        need_m = relu and kind != 2
+        ctx.save_for_backward(m if need_m else None, arg)
+        g.last_arg = arg
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g, kind = ctx.g, ctx.kind
+        m, arg = ctx.saved_tensors
+        gout = _f32c(gout)
+        D = gout.shape[1]
+        dm = torch.empty(g.E, D, dtype=torch.float32, device=gout.device)
+        call("mrg_seg_reduce_bwd", kind, ptr(gout), ptr(arg), None, act(m, relu=ctx.relu) if m is not None else act(None),
+             ptr(g.dst), ptr(g.csr.ptr), g.E, 0, D, ptr(dm), 0, stream())
+        return dm, (gout if ctx.has_res else None), None, None, None
+
+
+class AggSumLP(torch.autograd.Function):
+    """a_sum_op (LP, operations_lp.py:259-264) on the full [M,D] input: sum of the E edge rows
+    by destination + the N self-loop rows; one backward kernel writes all M gradient rows."""
+
+    @staticmethod
+    def forward(ctx, x, g):
+        x = _f32c(x)
+        D = x.shape[1]
+        out = torch.empty(g.N, D, dtype=torch.float32, device=x.device)
+        seg_reduce_raw(g.csr, 0, act(x), D, out, residual=act(x[g.E:]))
+        ctx.g = g
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = ctx.g
+        gout = _f32c(gout)
+        D = gout.shape[1]
+        dx = torch.empty(g.M, D, dtype=torch.float32, device=gout.device)
+        call("mrg_seg_reduce_bwd", 0, ptr(gout), None, None, act(None), ptr(g.dst), ptr(g.csr.ptr), g.E, g.N, D,
+             ptr(dx), 0, stream())
+        return dx, None
+
+
+# ------------------------------------------------------------------------------------------
+# K8: sigmoid + BCE over the 1-N logits
+# ------------------------------------------------------------------------------------------
+class SigmoidBCE(torch.autograd.Function):
+    """mean BCE(sigmoid(logit), label) with torch's log clamp at -100 -- replaces
+    torch.sigmoid (operations_lp.py:126) + nn.BCELoss (mr_lp_train.py:116,235)."""
+
+    @staticmethod
+    def forward(ctx, logit, label):
+        logit, label = _f32c(logit), _f32c(label)
+        n = logit.numel()
+        nparts = int(_lib.load().mrg_bce_nparts(n))
+        partial = torch.empty(nparts, dtype=torch.float64, device=logit.device)
+        loss = torch.empty(1, dtype=torch.float32, device=logit.device)
+        call("mrg_sigmoid_bce_fwd", ptr(logit), ptr(label), n, None, ptr(partial), ptr(loss), stream())
+        ctx.save_for_backward(logit, label)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        logit, label = ctx.saved_tensors
+        dl = torch.empty_like(logit)
+        gs = gl.reshape(1).float().contiguous()
+        call("mrg_sigmoid_bce_bwd", ptr(logit), ptr(label), logit.numel(), ptr(gs), ptr(dl), stream())
+        return dl, None

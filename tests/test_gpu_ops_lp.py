@@ -1,0 +1,235 @@
+"""GPU parity: libmrgnas kernels (through the C ABI) vs the CPU oracle / golden vectors.
+
+Tolerances: fp32 outputs and gradients within REL = 1e-5 of the oracle, measured as
+max|a-b| / max(1, max|b|) (the north_star's "1e-5 relative in fp32"); integer graph arrays
+and argmax indices bit-exact (tie-break: lowest original edge id)."""
+import os
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrg_oracle as O
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+Genotype = namedtuple("Genotype", "alpha_cell concat_node score_func")
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+def _check(name, a, b, tol=REL):
+    assert a.shape == b.shape, f"{name}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    e = _err(a, b)
+    assert e <= tol, f"{name}: rel err {e:.3e} > {tol:.1e}"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _graph_from_golden(gd, dev):
+    from mr_gnas_b200.graph import MRGraph
+    return MRGraph.from_triples(gd["num_ent"], gd["triples"].numpy(), gd["num_rels"], device=dev)
+
+
+# ------------------------------------------------------------------------------ K0
+@pytest.mark.parametrize("N,R,T,seed", [(37, 4, 90, 3), (500, 7, 4000, 1), (2000, 11, 30000, 2), (64, 1, 1, 5)])
+def test_graph_build_bit_exact(dev, N, R, T, seed):
+    from mr_gnas_b200.graph import MRGraph
+    trip = O.synth_kg(N, R, T, seed=seed)
+    ref = O.build_graph(N, trip, R)
+    g = MRGraph.from_triples(N, trip, R, device=dev)
+    E = 2 * T
+    assert np.array_equal(g.src.cpu().numpy(), ref["src"])
+    assert np.array_equal(g.dst.cpu().numpy(), ref["dst"])
+    assert np.array_equal(g.etype.cpu().numpy(), ref["etype"])
+    assert np.array_equal(g.in_deg.cpu().numpy(), ref["in_deg"])
+    ptr, eid = O.csr_by_dst(ref["dst"], N)
+    assert np.array_equal(g.csr.ptr.cpu().numpy(), ptr)
+    assert np.array_equal(g.csr.idx.cpu().numpy()[:E], eid)
+    src_final = np.concatenate([ref["src"], np.arange(N)])
+    ptr2, row2 = O.csr_by_dst(src_final, N)
+    assert np.array_equal(g.csc.ptr.cpu().numpy(), ptr2)
+    assert np.array_equal(g.csc.idx.cpu().numpy(), row2)
+    et_final = np.concatenate([ref["etype"], np.full(N, 2 * R)])
+    ptr3, row3 = O.csr_by_dst(et_final, 2 * R + 1)
+    assert np.array_equal(g.rel.ptr.cpu().numpy(), ptr3)
+    assert np.array_equal(g.rel.idx.cpu().numpy(), row3)
+    # chunk tables cover every segment exactly
+    cf = g.csr.chunk_first.cpu().numpy()
+    assert np.array_equal(np.diff(cf), (np.diff(ptr) + 31) // 32)
+    # degree norm: float32 in_deg**-0.5 products (mr_lp_train.py:82-86), <= 1 ulp
+    np.testing.assert_allclose(g.edge_norm.cpu().numpy(), ref["norm"], rtol=2e-7, atol=0)
+
+
+def test_graph_golden(dev, golden_dir):
+    for f in ["ops_lp.pt", "network_lp.pt"]:
+        gd = _load(golden_dir, f)["graph"]
+        g = _graph_from_golden(gd, dev)
+        assert torch.equal(g.src.cpu().long(), gd["src"])
+        assert torch.equal(g.dst.cpu().long(), gd["dst"])
+        assert torch.equal(g.etype.cpu().long(), gd["etype"])
+        assert torch.equal(g.in_deg.cpu().long(), gd["in_deg"])
+        np.testing.assert_allclose(g.edge_norm.cpu().numpy(), gd["norm"].numpy(), rtol=2e-7)
+
+
+# ------------------------------------------------------------------------------ ops vs golden
+LP_OPS = ['pre_mult', 'pre_sub', 'pre_add', 'f_zero', 'f_identity', 'f_dense', 'f_dense_comp', 'f_comp',
+          'f_sparse', 'f_sparse_comp', 'f_dense_last', 'f_sparse_last', 'a_max', 'a_mean', 'a_sum']
+
+
+def _run_op(name, dev, g, D, c, state):
+    from mr_gnas_b200 import operations_lp as ops
+    from mr_gnas_b200.functional import decode_arg
+    op = ops.MIXED_OPS[name]({'feature_dim': D, 'drop_aggr': 0.0}).to(dev)
+    op.load_state_dict(state)
+    x = c["x"].to(dev).requires_grad_(True)
+    xin = c["xin"].to(dev).requires_grad_(True)
+    out = op(g, x, xin)
+    res = {"out": out}
+    if out.requires_grad:
+        out.backward(c["cot"].to(dev))
+    res["dx"], res["dxin"] = x.grad, xin.grad
+    res["dparams"] = {k: p.grad for k, p in op.named_parameters()}
+    if name == "a_max":
+        res["arg"] = decode_arg(g.last_arg)
+    return res
+
+
+@pytest.mark.parametrize("name", LP_OPS)
+def test_lp_op_golden(dev, golden_dir, name):
+    G = _load(golden_dir, "ops_lp.pt")
+    g = _graph_from_golden(G["graph"], dev)
+    c = G["cases"][name]
+    r = _run_op(name, dev, g, G["D"], c, c["state"])
+    _check("out", r["out"], c["out"])
+    if c["dx"] is not None:
+        _check("dx", r["dx"], c["dx"])
+    if c["dxin"] is not None:
+        got = r["dxin"] if r["dxin"] is not None else torch.zeros_like(c["dxin"])
+        _check("dxin", got, c["dxin"])
+    for k, gref in c["dparams"].items():
+        if gref is not None:
+            _check("d" + k, r["dparams"][k], gref)
+    if name == "a_max":
+        assert torch.equal(r["arg"].cpu().long(), c["arg"]), "argmax edge ids differ"
+
+
+# ------------------------------------------------------------------------------ ops vs oracle, larger
+@pytest.mark.parametrize("name", ['pre_sub', 'pre_mult', 'f_sparse_comp', 'f_dense_comp', 'f_comp', 'f_sparse_last',
+                                  'a_max', 'a_mean', 'a_sum'])
+@pytest.mark.parametrize("D", [64, 200, 256])
+def test_lp_op_oracle_seeded(dev, name, D):
+    from mr_gnas_b200 import operations_lp as ops
+    from mr_gnas_b200.graph import MRGraph
+    from mr_gnas_b200.functional import decode_arg
+    N, R, T = 3000, 9, 20000
+    trip = O.synth_kg(N, R, T, seed=D)
+    ref = O.build_graph(N, trip, R)
+    g = MRGraph.from_triples(N, trip, R, device=dev)
+    E = 2 * T
+    M = E + N
+    torch.manual_seed(D + len(name))
+    op = ops.MIXED_OPS[name]({'feature_dim': D, 'drop_aggr': 0.0})
+    for m in op.modules():
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.xavier_normal_(m.weight)
+    rows = N if name.endswith("_last") else M
+    x = torch.randn(rows, D)
+    if name.startswith("a_"):
+        x = torch.relu(x)
+    xin = torch.randn(rows, D)
+    cot = torch.randn(N if (name.startswith("a_") or name.endswith("_last")) else M, D)
+    # oracle (CPU fp32)
+    P = {"op." + k: v.detach().clone().requires_grad_(True) for k, v in op.state_dict().items()}
+    xo, xino = x.clone().requires_grad_(True), xin.clone().requires_grad_(True)
+    dst = torch.from_numpy(ref["dst"])
+    norm = torch.from_numpy(ref["norm"])
+    out_o = O.apply_op_lp(name, P, "op", xo, xino, E, norm, dst, N)
+    out_o.backward(cot)
+    # CUDA
+    opg = op.to(dev)
+    xg, xing = x.to(dev).requires_grad_(True), xin.to(dev).requires_grad_(True)
+    out_g = opg(g, xg, xing)
+    out_g.backward(cot.to(dev))
+    _check("out", out_g, out_o)
+    _check("dx", xg.grad, xo.grad)
+    if xino.grad is not None:
+        _check("dxin", xing.grad if xing.grad is not None else torch.zeros_like(xin), xino.grad)
+    for k, p in opg.named_parameters():
+        _check("d" + k, p.grad, P["op." + k].grad)
+    if name == "a_max":
+        _, arg_o = O.a_op_lp(name, {k: v.detach() for k, v in P.items()}, "op", x, E, dst, N, return_arg=True)
+        arg_g = decode_arg(g.last_arg).cpu().long()
+        # fp32 GEMM rounding differs CPU vs GPU, so compare arg only where the max is unambiguous:
+        # recompute on the GPU's own messages for a bit-exact check of the tie-break rule
+        m_gpu = torch.relu(opg.linear(x.to(dev)[:E])).cpu()
+        _, arg_exact = O.seg_max(m_gpu, dst, N)
+        assert torch.equal(arg_g, arg_exact), "argmax tie-break (lowest edge id) violated"
+        assert (arg_g == arg_o).float().mean() > 0.999
+
+
+def test_bn_act_matches_torch(dev):
+    from mr_gnas_b200 import functional as K
+    torch.manual_seed(0)
+    for rows, D in [(5000, 200), (33, 64), (100000, 128)]:
+        bn_ref = torch.nn.BatchNorm1d(D)
+        bn_ref.weight.data.uniform_(0.5, 1.5)
+        bn_ref.bias.data.uniform_(-0.5, 0.5)
+        bn_gpu = torch.nn.BatchNorm1d(D).to(dev)
+        bn_gpu.load_state_dict(bn_ref.state_dict())
+        y = torch.randn(rows, D) * 2 + 0.7
+        cot = torch.randn(rows, D)
+        yo = y.clone().double().requires_grad_(True)
+        bn64 = torch.nn.BatchNorm1d(D).double()
+        bn64.load_state_dict(bn_ref.state_dict())
+        so = torch.relu(bn64(yo))
+        so.backward(cot.double())
+        yg = y.to(dev).requires_grad_(True)
+        sg = K.bn_act(yg, bn_gpu, relu=True)
+        sg.backward(cot.to(dev))
+        _check("s", sg, so.float())
+        _check("dy", yg.grad, yo.grad.float())
+        _check("dgamma", bn_gpu.weight.grad, bn64.weight.grad.float())
+        _check("dbeta", bn_gpu.bias.grad, bn64.bias.grad.float())
+        _check("running_mean", bn_gpu.running_mean, bn64.running_mean.float())
+        _check("running_var", bn_gpu.running_var, bn64.running_var.float())
+        assert int(bn_gpu.num_batches_tracked) == 1
+
+
+def test_sigmoid_bce(dev):
+    from mr_gnas_b200 import functional as K
+    torch.manual_seed(1)
+    B, N = 64, 1237
+    logit = (torch.randn(B, N) * 6)
+    logit[0, :5] = torch.tensor([200., -200., 90., -90., 0.])  # exercises the -100 log clamp
+    y = (torch.rand(B, N) < 0.01).float() * 0.9 + 1.0 / N
+    lo = logit.clone().requires_grad_(True)
+    loss_o = O.bce_loss(torch.sigmoid(lo), y)
+    loss_o.backward()
+    lt = logit.clone().requires_grad_(True)
+    loss_t = torch.nn.BCELoss()(torch.sigmoid(lt), y)
+    loss_t.backward()
+    lg = logit.to(dev).requires_grad_(True)
+    loss_g = K.SigmoidBCE.apply(lg, y.to(dev))
+    loss_g.backward()
+    _check("loss", loss_g.view(1), loss_t.view(1))
+    _check("loss_oracle", loss_g.view(1), loss_o.view(1))
+    _check("dlogit", lg.grad * (B * N), lt.grad * (B * N))
+
+
+def test_fail_loudly_on_cpu_tensor():
+    from mr_gnas_b200 import functional as K
+    with pytest.raises(RuntimeError):
+        K.ComposeRows.apply(torch.randn(4, 8), torch.randn(4, 8), 0)
