@@ -44,7 +44,7 @@ typedef enum {
 typedef enum { MRG_COMP_SUB = 0, MRG_COMP_MULT = 1, MRG_COMP_ADD = 2 } mrg_comp;
 /* destination reductions = DGL update_all(copy_e, max|sum|mean) (operations_lp.py:233,248,262)
  * and the NC std reducer (operations.py:167-190) */
-typedef enum { MRG_RED_SUM = 0, MRG_RED_MEAN = 1, MRG_RED_MAX = 2, MRG_RED_STD = 3 } mrg_reduce;
+typedef enum { MRG_RED_SUM = 0, MRG_RED_MEAN = 1, MRG_RED_MAX = 2 } mrg_reduce;
 
 /* A feature matrix read through an optional per-column affine + ReLU:
  *   value(i,c) = relu?( scale[c] * data[i,c] + shift[c] )       (scale == NULL: identity affine)
@@ -81,6 +81,11 @@ int mrg_graph_build(const int32_t* src, const int32_t* dst, const int32_t* etype
                     int64_t n_rel_rows, int32_t* in_deg, float* n_norm, float* edge_norm, int32_t* csr_ptr,
                     int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_row, int32_t* rel_ptr, int32_t* rel_row,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* edge_norm[e] = n_norm[dst[e]] * n_norm[src[e]] (one IEEE fp32 multiply; the apply_edges UDF of
+ * train/mr_lp_train.py:86 and search/mr_lp_search.py:30-36) for a caller-supplied node norm. */
+int mrg_edge_norm(const int32_t* src, const int32_t* dst, const float* n_norm, int64_t E, float* edge_norm,
+                  void* stream);
 
 /* Chunk table over a segment list (ptr[nseg+1]): splits every segment into pieces of at
  * most MRG_CHUNK_ROWS rows so hub nodes / frequent relations are reduced by many warps.
@@ -184,12 +189,26 @@ int mrg_seg_reduce_fwd(int32_t kind, mrg_act m, const int32_t* ptr, const int32_
                        int32_t* arg, void* workspace, size_t workspace_bytes, void* stream);
 /* backward of (i) w.r.t. the (pre-ReLU) message rows, in edge-id order:
  *   SUM : dm[e,:] = g[dst[e],:]              MEAN: g[dst[e],:] / max(deg,1)
- *   MAX : dm[e,c] = g[n,c] if arg[n,c]==e    (all gated by [m>0] when m.relu)
- *   STD : dm[e,c] = g[n,c] * (m[e,c]-mean[n,c]) / (deg*out[n,c])  where var>0
+ *   MAX : dm[e,c] = g[n,c] if arg[n,c]==e    (SUM/MEAN gated by [m>0] when m.relu; MAX by the arg code)
  * rows >= E (self-loop rows, when n_self>0) receive g[row-E,:] (the residual path). */
 int mrg_seg_reduce_bwd(int32_t kind, const float* g, const int32_t* arg, const float* out, mrg_act m,
                        const int32_t* dst, const int32_t* ptr, int64_t E, int64_t n_self, int32_t D, float* dm,
                        int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5 (tensor-core form)  fused a_max: edge-tile GEMM + bias + ReLU + destination max in one
+ * tcgen05 kernel (3xTF32 split for fp32-class accuracy), never materialising the [E,D]
+ * messages.  Replaces F.relu(self.linear(src_emb[:E])) + update_all(copy_e, max) + the self-loop
+ * residual of a_max_op (operations_lp.py:230-235; NC: operations.py:112-121, residual = null).
+ *   out[n,f] = max_{e: dst[e]=n} relu(W[f,:] . x(e,:) + bias[f]) + residual(n,f)
+ * x rows are addressed by edge id through the dst-CSR (csr_eid); `arg` gets the same encoded
+ * argmax as mrg_seg_reduce_fwd(MAX).  Requires D % 8 == 0, D <= 256 (mrg_amax_tc_supported).
+ * ---------------------------------------------------------------------------------- */
+int mrg_amax_tc_supported(int32_t D);
+size_t mrg_amax_tc_workspace_bytes(int64_t N, int32_t D);
+int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid, const int32_t* dst,
+                    int64_t E, int64_t N, int32_t D, mrg_act residual, float* out, int32_t* arg, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K8  DistMult 1-N scoring epilogue + BCE.  Replaces torch.sigmoid + nn.BCELoss

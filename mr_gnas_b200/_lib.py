@@ -28,6 +28,7 @@ _SIGNATURES = {
     "mrg_last_error": (c_char_p, []),
     "mrg_graph_workspace_bytes": (SZ, [I64, I64, I64]),
     "mrg_graph_build": (I32, [P, P, P, I64, I64, I64, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "mrg_edge_norm": (I32, [P, P, P, I64, P, P]),
     "mrg_chunk_capacity": (I64, [I64, I64]),
     "mrg_chunk_workspace_bytes": (SZ, [I64]),
     "mrg_chunk_build": (I32, [P, I64, P, P, P, SZ, P]),
@@ -50,6 +51,9 @@ _SIGNATURES = {
     "mrg_seg_reduce_workspace_bytes": (SZ, [I64, I32, I32]),
     "mrg_seg_reduce_fwd": (I32, [I32, MrgAct, P, P, P, P, I64, I64, I32, P, P, F32, MrgAct, I32, P, P, P, SZ, P]),
     "mrg_seg_reduce_bwd": (I32, [I32, P, P, P, MrgAct, P, P, I64, I64, I32, P, I32, P]),
+    "mrg_amax_tc_supported": (I32, [I32]),
+    "mrg_amax_tc_workspace_bytes": (SZ, [I64, I32]),
+    "mrg_amax_tc_fwd": (I32, [MrgAct, P, P, P, P, I64, I64, I32, MrgAct, P, P, P, SZ, P]),
     "mrg_bce_nparts": (I32, [I64]),
     "mrg_sigmoid_bce_fwd": (I32, [P, P, I64, P, P, P, P]),
     "mrg_sigmoid_bce_bwd": (I32, [P, P, I64, P, P, P]),
@@ -59,7 +63,7 @@ _OPTIONAL = {}
 
 _lib = None
 # kernels enqueued per C-ABI call (default 1); used for the gpu_launches count bench.py reports
-KERNELS_PER_CALL = {"mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_chunk_build": 3}
+KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_chunk_build": 3}
 launch_count = 0   # libmrgnas kernels launched so far
 _profile = None    # when a list: (name, start_event, end_event) per call (bench.py per-kernel timing)
 
@@ -87,8 +91,13 @@ def load():
 
 
 def ptr(t):
+    """Raw device pointer of a tensor; refuses anything the kernels cannot address."""
     if t is None:
         return None
+    if not t.is_cuda:
+        raise RuntimeError("libmrgnas got a CPU tensor: the message-passing path has no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError("libmrgnas expects contiguous tensors")
     return c_void_p(t.data_ptr())
 
 

@@ -1,0 +1,459 @@
+// K5 (tensor-core form): fused edge-tile GEMM + bias + ReLU + destination max aggregation
+//   out[n,f] = max_{e in CSR row n} relu( sum_k W[f,k] * X[eid(e),k] + b[f] )  (+ residual[n,f])
+// for a_max_op (operations_lp.py:230-235; operations.py:112-121) without ever materialising
+// the [E,D] message matrix.
+//
+// tcgen05 mapping (sm_100a): the GEMM is computed TRANSPOSED, C^T[f, e] = W[f,:] . X[e,:],
+// so the UMMA "M" axis (TMEM lanes) is the output feature and the "N" axis (TMEM columns)
+// is the edge position inside a 128-edge tile of the dst-sorted CSR.  Every epilogue thread
+// then owns ONE feature and walks its TMEM row across the tile's edges, so the segmented
+// max over destinations is a register-only scan and the writes out[n, f0..f0+31] of a warp are
+// coalesced.  Segments that straddle tiles are merged with a 64-bit atomicMax on the packed
+// key (float bits of the non-negative value, ~edge id): order independent, hence deterministic,
+// and the lowest edge id wins ties (the stated tie-break).
+//
+// fp32 accuracy on the TF32 pipe: both operands are split x = hi + lo (hi = rna_tf32(x),
+// lo = rna_tf32(x - hi)) and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM
+// ("3xTF32"), giving ~2^-21 relative operand error, i.e. SGEMM-class results.
+//
+// Pipeline per CTA (persistent over tiles, one CTA per SM):
+//   warps 0-3  producers : X rows gathered by CSR edge id -> (BN affine + ReLU) -> hi/lo split ->
+//                          128B-swizzled K-major smem; W hi/lo K-chunk via cp.async
+//   warp  8    MMA issuer: one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
+//   warps 4-7  epilogue  : tcgen05.ld -> +bias, ReLU -> segmented max scan -> atomicMax
+#include "common.cuh"
+
+namespace mrg {
+namespace tc {
+
+constexpr int TILE_E = 128;   // edges per tile  (UMMA N)
+constexpr int KCH = 32;       // fp32 elements per K chunk = one 128-byte swizzled row
+constexpr int STAGES = 2;
+constexpr int PROD_THREADS = 128;
+constexpr int EPI_THREADS = 128;
+constexpr int THREADS = PROD_THREADS + EPI_THREADS + 32;
+constexpr uint32_t TILE_BYTES = 128 * 128;  // 128 rows x 128 B
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_cpasync_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, 128B-swizzled smem matrix descriptor: start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 |
+// version 1 << 46 | SWIZZLE_128B (2) << 61     (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=128   (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// W [Dout, Din] fp32 -> hi/lo TF32 pair, zero padded to [MH*128, Kp]:  out[0]=hi, out[1]=lo
+__global__ void tf32_split_kernel(const float* __restrict__ W, int Dout, int Din, int rows_pad, int Kp,
+                                  float* __restrict__ out) {
+  const int64_t n = (int64_t)rows_pad * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / Kp), k = (int)(i % Kp);
+    const float x = (r < Dout && k < Din) ? W[(size_t)r * Din + k] : 0.f;
+    const float hi = tf32_rna(x);
+    out[i] = hi;
+    out[n + i] = tf32_rna(x - hi);
+  }
+}
+
+struct AmaxParams {
+  mrg_act x;                 // [rows, D] message source rows, read through act
+  const int32_t* csr_eid;    // [E] row id per CSR position
+  const int32_t* dst;        // [E] destination per edge id
+  const float* wsplit;       // [2][MH*128][Kp]
+  const float* bias;         // [D] or null
+  unsigned long long* packed;  // [N, D] zero-initialised
+  int64_t E;
+  int D, MH, Kp, nchunks, num_tiles;
+};
+
+// dynamic smem: [stage][ Whi MH tiles | Wlo MH tiles | Xhi | Xlo ] (1024-B aligned) then small arrays
+template <int MH>
+__global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t STAGE_BYTES = (2 * MH + 2) * TILE_BYTES;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tail = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = (uint64_t*)tail;               // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;            // [STAGES]
+  uint64_t* tfull_bar = empty_bar + STAGES;           // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;               // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);  // [1] (+pad)
+  float* s_scale = (float*)(tmem_slot + 4);           // [256]
+  float* s_shift = s_scale + 256;                     // [256]
+  float* s_bias = s_shift + 256;                      // [256]
+  int32_t* s_dst = (int32_t*)(s_bias + 256);          // [2][128]
+  int32_t* s_eid = s_dst + 2 * TILE_E;                // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = p.D;
+  constexpr uint32_t TMEM_COLS = 2 * MH * TILE_E;  // 256 or 512
+
+  for (int c = threadIdx.x; c < 256; c += THREADS) {
+    s_scale[c] = (p.x.scale && c < D) ? p.x.scale[c] : 1.f;
+    s_shift[c] = (p.x.scale && c < D) ? p.x.shift[c] : 0.f;
+    s_bias[c] = (p.bias && c < D) ? p.bias[c] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], PROD_THREADS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================================ PRODUCERS ================================
+    const int r = threadIdx.x;  // tile row owned by this thread
+    const bool affine = p.x.scale != nullptr, relu = p.x.relu != 0;
+    uint32_t it = 0;            // global chunk counter -> stage / phase
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t pos = (int64_t)tile * TILE_E + r;
+      const bool valid = pos < p.E;
+      const float* xrow = valid ? p.x.data + (size_t)__ldg(p.csr_eid + pos) * D : nullptr;
+      float4 nxt[8];
+      auto load_chunk = [&](int c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = c * KCH + 4 * j;
+          nxt[j] = (valid && col < D) ? ld_stream4(xrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_chunk(0);
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        // W hi/lo chunk -> smem (async): 2*MH*128 rows x 8 x 16B, swizzled
+        {
+          const int rows_pad = MH * 128;
+          const int total = 2 * rows_pad * 8;
+          const uint32_t wbase = smem_u32(st);
+          for (int q = threadIdx.x; q < total; q += PROD_THREADS) {
+            const int j = q & 7, row = (q >> 3) % rows_pad, hl = (q >> 3) / rows_pad;
+            const float* src = p.wsplit + ((size_t)hl * rows_pad + row) * p.Kp + c * KCH + 4 * j;
+            const uint32_t dst = wbase + (uint32_t)hl * MH * TILE_BYTES + (uint32_t)(row >> 3) * 1024 +
+                                 (uint32_t)(row & 7) * 128 + (uint32_t)((j ^ (row & 7)) << 4);
+            cp_async16(dst, src);
+          }
+          mbar_cpasync_arrive(&full_bar[s]);
+        }
+        // X chunk: registers -> affine/ReLU -> hi/lo -> swizzled smem
+        float4 cur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        if (c + 1 < p.nchunks) load_chunk(c + 1);
+        uint8_t* xhi = st + 2 * MH * TILE_BYTES;
+        uint8_t* xlo = xhi + TILE_BYTES;
+        const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = c * KCH + 4 * j;
+          float4 v = cur[j];
+          if (valid && col < D) {
+            if (affine) {
+              v.x = fmaf(s_scale[col], v.x, s_shift[col]);
+              v.y = fmaf(s_scale[col + 1], v.y, s_shift[col + 1]);
+              v.z = fmaf(s_scale[col + 2], v.z, s_shift[col + 2]);
+              v.w = fmaf(s_scale[col + 3], v.w, s_shift[col + 3]);
+            }
+            if (relu) {
+              v.x = v.x > 0.f ? v.x : 0.f;
+              v.y = v.y > 0.f ? v.y : 0.f;
+              v.z = v.z > 0.f ? v.z : 0.f;
+              v.w = v.w > 0.f ? v.w : 0.f;
+            }
+          }
+          float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          float4 lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z),
+                                  tf32_rna(v.w - hi.w));
+          const uint32_t off = roff + (uint32_t)((j ^ (r & 7)) << 4);
+          *reinterpret_cast<float4*>(xhi + off) = hi;
+          *reinterpret_cast<float4*>(xlo + off) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ================================ MMA ISSUER ================================
+    const uint32_t idesc = umma_idesc(128, TILE_E);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1;
+      mbar_wait(&tempty_bar[buf], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_proxy_async();
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sbase = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t xhi = sbase + 2 * MH * TILE_BYTES, xlo = xhi + TILE_BYTES;
+          const int ksteps = min(KCH, D - c * KCH) / 8;
+          for (int h = 0; h < MH; ++h) {
+            const uint32_t whi = sbase + h * TILE_BYTES, wlo = sbase + (MH + h) * TILE_BYTES;
+            const uint32_t d_tmem = tmem_base + buf * (MH * TILE_E) + h * TILE_E;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the swizzled 128B row
+              const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+              umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);   // small terms first
+              umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
+              umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);                       // frees the smem stage when the MMAs retire
+          if (c == p.nchunks - 1) umma_commit(&tfull_bar[buf]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ EPILOGUE ================================
+    const int et = threadIdx.x - PROD_THREADS;       // 0..127 == TMEM lane
+    const int quad = warp & 3;                       // warps 4..7 -> lane quadrants 0..3
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1;
+      const int64_t pos0 = (int64_t)tile * TILE_E;
+      const int cnt = (int)min((int64_t)TILE_E, p.E - pos0);
+      {
+        int32_t e = -1, d = -1;
+        if (et < cnt) {
+          e = __ldg(p.csr_eid + pos0 + et);
+          d = __ldg(p.dst + e);
+        }
+        s_eid[buf * TILE_E + et] = e;
+        s_dst[buf * TILE_E + et] = d;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const int32_t* sd = s_dst + buf * TILE_E;
+      const int32_t* se = s_eid + buf * TILE_E;
+      for (int h = 0; h < MH; ++h) {
+        const int f = h * 128 + et;
+        const bool fvalid = f < D;
+        const float bias = s_bias[f & 255];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MH * TILE_E) + h * TILE_E;
+        int32_t cur = sd[0];
+        float best = -1.f;
+        int32_t barg = -1;
+        for (int cb = 0; cb < TILE_E; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cb, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = cb + j;
+            if (col < cnt) {
+              const int32_t d = sd[col];
+              if (d != cur) {
+                if (fvalid) {
+                  const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) |
+                                                 (unsigned long long)(0xFFFFFFFFu - (uint32_t)barg);
+                  atomicMax(p.packed + (size_t)cur * D + f, key);
+                }
+                cur = d;
+                best = -1.f;
+                barg = -1;
+              }
+              float val = __uint_as_float(v[j]) + bias;
+              val = val > 0.f ? val : 0.f;
+              if (val > best) {
+                best = val;
+                barg = se[col];
+              }
+            }
+          }
+        }
+        if (fvalid && cnt > 0) {
+          const unsigned long long key =
+              ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)barg);
+          atomicMax(p.packed + (size_t)cur * D + f, key);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// packed key -> out (+ residual) and the encoded argmax (see segreduce.cu for the code)
+__global__ void amax_finalize_kernel(const unsigned long long* __restrict__ packed, int64_t n, int D, mrg_act res,
+                                     float* __restrict__ out, int32_t* __restrict__ arg) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = packed[i];
+    float val = 0.f;
+    int32_t a = -1;
+    if (key != 0ull) {
+      val = __uint_as_float((uint32_t)(key >> 32));
+      const int32_t e = (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+      a = val > 0.f ? e : -2 - e;
+    }
+    if (res.data) {
+      float rv = res.data[i];
+      const int c = (int)(i % D);
+      if (res.scale) rv = fmaf(res.scale[c], rv, res.shift[c]);
+      if (res.relu) rv = rv > 0.f ? rv : 0.f;
+      val += rv;
+    }
+    out[i] = val;
+    if (arg) arg[i] = a;
+  }
+}
+
+}  // namespace tc
+}  // namespace mrg
+
+using namespace mrg;
+
+extern "C" size_t mrg_amax_tc_workspace_bytes(int64_t N, int32_t D) {
+  const int MH = D <= 128 ? 1 : 2;
+  const int Kp = (D + tc::KCH - 1) / tc::KCH * tc::KCH;
+  return (size_t)N * D * sizeof(unsigned long long) + (size_t)2 * MH * 128 * Kp * sizeof(float) + 512;
+}
+
+extern "C" int mrg_amax_tc_supported(int32_t D) { return (D % 8 == 0 && D >= 8 && D <= 256) ? 1 : 0; }
+
+extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid,
+                               const int32_t* dst, int64_t E, int64_t N, int32_t D, mrg_act residual, float* out,
+                               int32_t* arg, void* workspace, size_t workspace_bytes, void* stream) {
+  MRG_CHECK_ARG(x.data && W && out && workspace, "amax_tc_fwd: null pointer");
+  MRG_CHECK_ARG(E == 0 || (csr_eid && dst), "amax_tc_fwd: null graph arrays");
+  MRG_CHECK_ARG(mrg_amax_tc_supported(D), "amax_tc_fwd: D must be a multiple of 8 and <= 256");
+  if (workspace_bytes < mrg_amax_tc_workspace_bytes(N, D)) {
+    set_error("amax_tc_fwd: workspace too small");
+    return MRG_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int MH = D <= 128 ? 1 : 2;
+  const int Kp = (D + tc::KCH - 1) / tc::KCH * tc::KCH;
+  unsigned long long* packed = (unsigned long long*)workspace;
+  const size_t packed_bytes = ((size_t)N * D * sizeof(unsigned long long) + 255) / 256 * 256;
+  float* wsplit = (float*)((char*)workspace + packed_bytes);
+  cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)N * D * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd memset");
+  tc::tf32_split_kernel<<<64, 256, 0, st>>>(W, D, D, MH * 128, Kp, wsplit);
+  tc::AmaxParams p;
+  p.x = x;
+  p.csr_eid = csr_eid;
+  p.dst = dst;
+  p.wsplit = wsplit;
+  p.bias = bias;
+  p.packed = packed;
+  p.E = E;
+  p.D = D;
+  p.MH = MH;
+  p.Kp = Kp;
+  p.nchunks = Kp / tc::KCH;
+  p.num_tiles = (int)((E + tc::TILE_E - 1) / tc::TILE_E);
+  if (p.num_tiles > 0) {
+    const size_t smem = (size_t)tc::STAGES * (2 * MH + 2) * tc::TILE_BYTES + 1024 /*align*/ + 8192 /*tail*/;
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    if (MH == 1) {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+      tc::amax_tc_kernel<1><<<grid, tc::THREADS, smem, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+      tc::amax_tc_kernel<2><<<grid, tc::THREADS, smem, st>>>(p);
+    }
+  }
+  const int64_t n = N * D;
+  tc::amax_finalize_kernel<<<(int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(packed, n, D, residual,
+                                                                                                  out, arg);
+  MRG_LAUNCH_CHECK("amax_tc_fwd");
+  return MRG_OK;
+}

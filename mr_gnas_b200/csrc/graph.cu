@@ -127,3 +127,11 @@ extern "C" int mrg_graph_build(const int32_t* src, const int32_t* dst, const int
   MRG_LAUNCH_CHECK("graph_build");
   return MRG_OK;
 }
+
+extern "C" int mrg_edge_norm(const int32_t* src, const int32_t* dst, const float* n_norm, int64_t E, float* edge_norm,
+                             void* stream) {
+  MRG_CHECK_ARG(E == 0 || (src && dst && n_norm && edge_norm), "edge_norm: null pointer");
+  if (E > 0) edge_norm_kernel<<<(int)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_norm, E, edge_norm);
+  MRG_LAUNCH_CHECK("edge_norm");
+  return MRG_OK;
+}

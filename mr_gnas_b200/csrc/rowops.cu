@@ -125,17 +125,38 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(mrg_act x, int64_t r
   cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Deterministic folding of per-CTA partials: a 256-thread block owns 8 columns; 32 "part
+// lanes" stride over the partial rows, then combine through shared memory in a fixed order.
+// ---------------------------------------------------------------------------------------
+constexpr int kFinCols = 8;
+constexpr int kFinLanes = 32;
+__device__ __forceinline__ double fold_parts(const double* __restrict__ base, int nparts, size_t row_stride, int col,
+                                             bool valid, double* sm /* [kFinLanes][kFinCols] */) {
+  const int cc = threadIdx.x % kFinCols, pl = threadIdx.x / kFinCols;
+  double t = 0.0;
+  if (valid)
+    for (int p = pl; p < nparts; p += kFinLanes) t += base[(size_t)p * row_stride + col];
+  sm[pl * kFinCols + cc] = t;
+  __syncthreads();
+  double r = 0.0;
+  if (pl == 0)
+    for (int q = 0; q < kFinLanes; ++q) r += sm[q * kFinCols + cc];
+  __syncthreads();
+  return r;  // valid in part-lane 0 threads
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int nparts, int64_t rows, int D,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean_o,
                                    float* invstd_o, float* a_o, float* b_o) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s += stats[(size_t)p * 2 * D + c];
-    q += stats[(size_t)p * 2 * D + D + c];
-  }
+  __shared__ double sm[kFinLanes * kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols;
+  const bool valid = c < D;
+  const double s = fold_parts(stats, nparts, 2 * (size_t)D, c, valid, sm);
+  const double q = fold_parts(stats + D, nparts, 2 * (size_t)D, c, valid, sm);
+  if (!valid || threadIdx.x >= kFinCols) return;
   const double n = (double)rows;
   const double mean = s / n;
   double var = q / n - mean * mean;
@@ -213,13 +234,12 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int nparts, int64_t rows, int D,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s1 += stats[(size_t)p * 2 * D + c];
-    s2 += stats[(size_t)p * 2 * D + D + c];
-  }
+  __shared__ double sm[kFinLanes * kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols;
+  const bool valid = c < D;
+  const double s1 = fold_parts(stats, nparts, 2 * (size_t)D, c, valid, sm);
+  const double s2 = fold_parts(stats + D, nparts, 2 * (size_t)D, c, valid, sm);
+  if (!valid || threadIdx.x >= kFinCols) return;
   const double mu = mean[c], is = invstd[c], g = gamma ? gamma[c] : 1.0, n = (double)rows;
   const double dg = is * (s2 - mu * s1);  // sum dz * xhat
   if (dgamma) dgamma[c] = (float)dg;
@@ -459,10 +479,11 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
 
 __global__ void sparse_gate_bwd_finalize_kernel(const double* __restrict__ dparam, int nparts, int D, float* dv1,
                                                 float* dv2, float* dc) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > 2 * D) return;
-  double t = 0.0;
-  for (int p = 0; p < nparts; ++p) t += dparam[(size_t)p * (2 * D + 1) + c];
+  __shared__ double sm[kFinLanes * kFinCols];
+  const int c = blockIdx.x * kFinCols + threadIdx.x % kFinCols;
+  const bool valid = c <= 2 * D;
+  const double t = fold_parts(dparam, nparts, 2 * (size_t)D + 1, c, valid, sm);
+  if (!valid || threadIdx.x >= kFinCols) return;
   if (c < D) {
     if (dv1) dv1[c] = (float)t;
   } else if (c < 2 * D) {
@@ -702,7 +723,7 @@ extern "C" int mrg_bn_finalize(const double* stats, int32_t nparts, int64_t rows
                                float* running_var, float* mean, float* invstd, float* a, float* b, void* stream) {
   MRG_CHECK_ARG(stats && a && b, "bn_finalize: null pointer");
   MRG_CHECK_ARG(rows > 0 && nparts > 0, "bn_finalize: rows/nparts");
-  bn_finalize_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, nparts, rows, D, gamma, beta, eps,
+  bn_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, (cudaStream_t)stream>>>(stats, nparts, rows, D, gamma, beta, eps,
                                                                         momentum, running_mean, running_var, mean,
                                                                         invstd, a, b);
   MRG_LAUNCH_CHECK("bn_finalize");
@@ -732,7 +753,7 @@ extern "C" int mrg_bn_bwd_finalize(const double* bwd_stats, int32_t nparts, int6
                                    const float* gamma, const float* mean, const float* invstd, float* dgamma,
                                    float* dbeta, float* coef, void* stream) {
   MRG_CHECK_ARG(bwd_stats && mean && invstd && coef, "bn_bwd_finalize: null pointer");
-  bn_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bwd_stats, nparts, rows, D, gamma, mean,
+  bn_bwd_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, (cudaStream_t)stream>>>(bwd_stats, nparts, rows, D, gamma, mean,
                                                                             invstd, dgamma, dbeta, coef);
   MRG_LAUNCH_CHECK("bn_bwd_finalize");
   return MRG_OK;
@@ -791,7 +812,7 @@ extern "C" int mrg_sparse_gate_bwd_finalize(const double* dparam, int64_t rows, 
                                             float* dc, void* stream) {
   MRG_CHECK_ARG(dparam, "sparse_gate_bwd_finalize: null pointer");
   const int n = 2 * D + 1;
-  sparse_gate_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dparam, stats_grid(rows), D, dv1,
+  sparse_gate_bwd_finalize_kernel<<<(n + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, (cudaStream_t)stream>>>(dparam, stats_grid(rows), D, dv1,
                                                                                      dv2, dc);
   MRG_LAUNCH_CHECK("sparse_gate_bwd_finalize");
   return MRG_OK;

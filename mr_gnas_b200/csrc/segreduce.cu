@@ -160,21 +160,23 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_chunk_kernel(
   }
 }
 
-// Segments with 0 or >1 chunks: combine partials in ascending chunk order, then finalize.
+// Segments with 0 or >1 chunks: one CTA per segment.  Warp w folds chunks c0+w, c0+w+8, ... in
+// ascending order, then warp 0 merges the 8 warp partials in warp order (fixed order => bit
+// reproducible; MAX ties resolve to the lowest row id explicitly).
 template <int NV, int KIND>
 __global__ void __launch_bounds__(kThreads) seg_reduce_combine_kernel(
     mrg_act m, const int32_t* __restrict__ ptr, const int32_t* __restrict__ chunk_first, int64_t nseg, int D,
     float alpha, mrg_act res, int accumulate, float* __restrict__ out, int32_t* __restrict__ arg,
     const float* __restrict__ pval, const int32_t* __restrict__ parg) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float smem_f[];  // [kWarpsPerBlock][D] values, then [kWarpsPerBlock][D] args (MAX)
+  int32_t* smem_a = reinterpret_cast<int32_t*>(smem_f + kWarpsPerBlock * D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D4 = D >> 2;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   ActRegs<NV> ares;
   ares.init(res, lane, D4);
-  for (int64_t seg = warp0; seg < nseg; seg += nwarps) {
+  for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
     const int32_t c0 = chunk_first[seg], c1 = chunk_first[seg + 1];
-    if (c1 - c0 == 1) continue;
+    if (c1 - c0 == 1) continue;  // finalized by the chunk kernel (uniform over the CTA)
     RedRegs<NV> acc;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_combine_kernel(
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       acc.arg[v] = make_int4(-1, -1, -1, -1);
     }
-    for (int32_t ch = c0; ch < c1; ++ch) {
+    for (int32_t ch = c0 + warp; ch < c1; ch += kWarpsPerBlock) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         int c4 = lane + 32 * v;
@@ -200,8 +202,44 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_combine_kernel(
         }
       }
     }
-    finalize_seg<NV, KIND>(acc, seg, ptr[seg + 1] - ptr[seg], D, D4, lane, alpha, m.relu != 0, ares, res, accumulate,
-                           out, arg);
+    const int nw = min(c1 - c0, kWarpsPerBlock);  // warps that hold a partial
+    __syncthreads();
+    if (warp > 0 && warp < nw) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        int c4 = lane + 32 * v;
+        if (c4 < D4) {
+          *reinterpret_cast<float4*>(smem_f + warp * D + 4 * c4) = acc.val[v];
+          if (KIND == MRG_RED_MAX) *reinterpret_cast<int4*>(smem_a + warp * D + 4 * c4) = acc.arg[v];
+        }
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < nw; ++w) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          int c4 = lane + 32 * v;
+          if (c4 < D4) {
+            float4 x = *reinterpret_cast<const float4*>(smem_f + w * D + 4 * c4);
+            if (KIND == MRG_RED_MAX) {
+              int4 a = *reinterpret_cast<const int4*>(smem_a + w * D + 4 * c4);
+#define MRG_MAXTIE(F)                                                                              \
+  if (x.F > acc.val[v].F || (x.F == acc.val[v].F && a.F >= 0 && (acc.arg[v].F < 0 || a.F < acc.arg[v].F))) { \
+    acc.val[v].F = x.F;                                                                            \
+    acc.arg[v].F = a.F;                                                                            \
+  }
+              MRG_MAXTIE(x) MRG_MAXTIE(y) MRG_MAXTIE(z) MRG_MAXTIE(w)
+#undef MRG_MAXTIE
+            } else {
+              acc.val[v].x += x.x; acc.val[v].y += x.y; acc.val[v].z += x.z; acc.val[v].w += x.w;
+            }
+          }
+        }
+      }
+      finalize_seg<NV, KIND>(acc, seg, ptr[seg + 1] - ptr[seg], D, D4, lane, alpha, m.relu != 0, ares, res, accumulate,
+                             out, arg);
+    }
   }
 }
 
@@ -319,12 +357,13 @@ extern "C" int mrg_seg_reduce_fwd(int32_t kind, mrg_act m, const int32_t* ptr, c
   float* pval = (float*)workspace;
   int32_t* parg = (int32_t*)(pval + (size_t)max_chunks * D);
   const int grid_c = stats_grid(max_chunks);
-  const int grid_s = stats_grid(nseg);
+  const int grid_s = (int)(nseg < 4 * kMaxParts ? nseg : 4 * kMaxParts);
+  const size_t comb_smem = (size_t)kWarpsPerBlock * D * 8;
 #define L(KIND)                                                                                                   \
   MRG_DISPATCH_NV(D, {                                                                                            \
     if (mul) seg_reduce_chunk_kernel<NV, KIND, true><<<grid_c, kThreads, 0, st>>>(m, ptr, idx, chunk_first, chunk_seg, nseg, D, mul, mul_idx, alpha, residual, accumulate, out, arg, pval, parg); \
     else seg_reduce_chunk_kernel<NV, KIND, false><<<grid_c, kThreads, 0, st>>>(m, ptr, idx, chunk_first, chunk_seg, nseg, D, mul, mul_idx, alpha, residual, accumulate, out, arg, pval, parg); \
-    seg_reduce_combine_kernel<NV, KIND><<<grid_s, kThreads, 0, st>>>(m, ptr, chunk_first, nseg, D, alpha, residual, accumulate, out, arg, pval, parg); \
+    seg_reduce_combine_kernel<NV, KIND><<<grid_s, kThreads, comb_smem, st>>>(m, ptr, chunk_first, nseg, D, alpha, residual, accumulate, out, arg, pval, parg); \
   })
   if (kind == MRG_RED_SUM) L(MRG_RED_SUM);
   else if (kind == MRG_RED_MEAN) L(MRG_RED_MEAN);

@@ -237,7 +237,7 @@ class SparseGate(torch.autograd.Function):
             call("mrg_sparse_gate_bwd_finalize", ptr(dparam), n, D, ptr(dv1[s]), ptr(dv2[s]) if ctx.has_in else None,
                  ptr(dc[s:s + 1]), stream())
         if same:
-            return dx, torch.zeros_like(dx), dv1, dv2, dc, None, None, None, None
+            return dx, None, dv1, dv2, dc, None, None, None, None
         return dx, dxin, dv1, dv2, dc, None, None, None, None
 
 
@@ -317,6 +317,61 @@ class SegReduce(torch.autograd.Function):
         call("mrg_seg_reduce_bwd", kind, ptr(gout), ptr(arg), None, act(m, relu=ctx.relu) if m is not None else act(None),
              ptr(g.dst), ptr(g.csr.ptr), g.E, 0, D, ptr(dm), 0, stream())
         return dm, (gout if ctx.has_res else None), None, None, None
+
+
+def amax_tc_supported(D):
+    return bool(_lib.load().mrg_amax_tc_supported(int(D)))
+
+
+_tc_ws = {}
+
+
+def _tc_workspace(N, D, device):
+    key = (N, D, str(device))
+    if key not in _tc_ws:
+        nbytes = int(_lib.load().mrg_amax_tc_workspace_bytes(N, D))
+        _tc_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return _tc_ws[key]
+
+
+class AMaxTC(torch.autograd.Function):
+    """a_max_op as ONE tcgen05 kernel: relu(W x_e + b) for the E edge rows, destination max with
+    argmax, + residual rows; the [E,D] messages never reach HBM (operations_lp.py:230-235).
+    x is [M,D] (LP: E edge rows then N self-loop rows, n_res=N) or [E,D] (NC blocks, n_res=0)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, g, has_residual):
+        x, weight, bias = _f32c(x), _f32c(weight), _f32c(bias)
+        D = x.shape[1]
+        E, N = g.E, g.N
+        out = torch.empty(N, D, dtype=torch.float32, device=x.device)
+        arg = torch.empty(N, D, dtype=torch.int32, device=x.device)
+        ws = _tc_workspace(N, D, x.device)
+        res = act(x[E:]) if has_residual else act(None)
+        call("mrg_amax_tc_fwd", act(x), ptr(weight), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, res, ptr(out),
+             ptr(arg), ptr(ws), ws.numel(), stream())
+        ctx.g, ctx.has_residual = g, has_residual
+        ctx.save_for_backward(x, weight, arg)
+        g.last_arg = arg
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = ctx.g
+        x, weight, arg = ctx.saved_tensors
+        gout = _f32c(gout)
+        D = gout.shape[1]
+        E = g.E
+        dm = torch.empty(E, D, dtype=torch.float32, device=gout.device)
+        call("mrg_seg_reduce_bwd", 2, ptr(gout), ptr(arg), None, act(None), ptr(g.dst), ptr(g.csr.ptr), E, 0, D,
+             ptr(dm), 0, stream())
+        dx = torch.empty_like(x)
+        torch.mm(dm, weight, out=dx[:E])          # edge-tile GEMM (library) -- tcgen05 backward: see DESIGN.md
+        if ctx.has_residual:
+            dx[E:].copy_(gout)
+        dw = dm.t().mm(x[:E])
+        db = dm.sum(0)
+        return dx, dw, db, None, None
 
 
 class AggSumLP(torch.autograd.Function):

@@ -140,6 +140,16 @@ class MRGraph:
         _lib.call("mrg_graph_build", p(self.src), p(self.dst), p(self.etype), E, N, self.n_rel_rows, p(self.in_deg),
                   p(self.n_norm), p(self.edge_norm), p(csr_ptr), p(csr_eid), p(csc_ptr), p(csc_row), p(rel_ptr),
                   p(rel_row), p(ws), wsb, _lib.stream())
+        if with_norm:
+            # n_norm exactly as the reference computes it: numpy float32 in_deg ** -0.5, inf -> 0
+            # (train/mr_lp_train.py:81-84); N floats, one-off, so the host does it and the result is
+            # bit-identical to the reference's.  The per-edge product is one fp32 multiply on the device.
+            deg = self.in_deg.cpu().numpy().astype(np.float32)
+            with np.errstate(divide="ignore"):
+                nn_ = deg ** -0.5
+            nn_[np.isinf(nn_)] = 0
+            self.n_norm = torch.from_numpy(nn_).to(dev)
+            _lib.call("mrg_edge_norm", p(self.src), p(self.dst), p(self.n_norm), E, p(self.edge_norm), _lib.stream())
         self.csr = _Segments(csr_ptr, csr_eid, N, E, dev)
         if not dst_only:
             self.csc = _Segments(csc_ptr, csc_row, N, M, dev)

@@ -79,7 +79,7 @@ class Cell(nn.Module):
             for i in range(n + 1):
                 if len(self._ops[n][i]) > 0:
                     hs.append(self._ops[n][i][0](g, states[i], zero_out))
-            states.append(sum(hs))
+            states.append(hs[0] if len(hs) == 1 else sum(hs))  # 0 + t == t exactly; skip the extra pass
         h = self.concat(torch.cat([states[idx] for idx in self._concat_node], dim=1))
         return K.bn_act(h, self.batchnorm_h, relu=True)
 

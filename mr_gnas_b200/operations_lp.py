@@ -86,6 +86,9 @@ class f_zero_op(nn.Module):
 
 
 # ------------------------------------------------------------------ aggregators (K5)
+USE_TENSOR_CORES = True  # fused tcgen05 a_max kernel when the feature dim allows it (D % 8 == 0, D <= 256)
+
+
 class a_max_op(nn.Module):
     """reference: operations_lp.py:223-235"""
     kind = 2
@@ -97,6 +100,8 @@ class a_max_op(nn.Module):
 
     def forward(self, block, src_emb, src_emb_in):
         E = block.num_edges()
+        if self.kind == 2 and USE_TENSOR_CORES and K.amax_tc_supported(src_emb.shape[1]):
+            return K.AMaxTC.apply(src_emb, self.linear.weight, self.linear.bias, block, True)
         m_pre = self.linear(src_emb[:E, :])  # edge-tile GEMM (bias fused); ReLU is applied on load by the reducer
         return K.SegReduce.apply(m_pre, src_emb[E:, :], block, self.kind, True)
 
