@@ -57,6 +57,13 @@ typedef struct {
   int32_t relu;
 } mrg_act;
 
+/* up to MRG_MAX_MIXED candidate outputs of one DARTS MixedOp */
+#define MRG_MAX_MIXED 8
+typedef struct {
+  mrg_act acts[MRG_MAX_MIXED];
+  int32_t n;
+} mrg_act_list;
+
 int mrg_abi_version(void);
 const char* mrg_last_error(void);
 
@@ -171,6 +178,14 @@ int mrg_dense_gate_bwd(const float* dy, const float* z, mrg_act x, int64_t rows,
                        void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K9  DARTS MixedOp (cell_lp.py:25-33; cell.py:23-31):
+ *   out = sum_k w[k] * relu?(scale_k * y_k + shift_k)     (left-to-right, as Python's sum())
+ * i.e. every candidate's BatchNorm-apply + ReLU and the softmax(alpha)-weighted sum in one
+ * pass over the rows.  The backward reuses mrg_bn_bwd_reduce/apply per candidate (ds_k = w_k*dout).
+ * ---------------------------------------------------------------------------------- */
+int mrg_mixed_sum_fwd(mrg_act_list ys, const float* w, int64_t rows, int32_t D, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K5/K11  segmented reduction of gathered rows.  One kernel family serves
  *   (i)  DGL update_all(copy_e, max|sum|mean) over the dst-CSR (operations_lp.py:233,248,
  *        262; compgcn.py:87) and the NC UDF reducers incl. std (operations.py:105-190);
@@ -209,6 +224,16 @@ size_t mrg_amax_tc_workspace_bytes(int64_t N, int32_t D);
 int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid, const int32_t* dst,
                     int64_t E, int64_t N, int32_t D, mrg_act residual, float* out, int32_t* arg, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* K5 backward (sparse): gradients of a_max w.r.t. the E message-source rows (dX, edge-id order,
+ * every row written once), the Linear weight (dW [D,D]) and bias (db [D]) from g = dL/d(out),
+ * the encoded argmax and the (lazily activated) input rows.  Replaces the reference's two dense
+ * [E,D]x[D,D] backward GEMMs with 2*N*D*D FMAs on the routed entries only.  dX / dW may be NULL. */
+size_t mrg_amax_bwd_workspace_bytes(int32_t D);
+int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,
+                 const int32_t* csr_eid, const int32_t* chunk_first, const int32_t* chunk_seg, int64_t N, int64_t E,
+                 int64_t max_chunks, int32_t D, float* dX, float* dW, float* db, void* workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K8  DistMult 1-N scoring epilogue + BCE.  Replaces torch.sigmoid + nn.BCELoss

@@ -21,6 +21,10 @@ class MrgAct(Structure):
     _fields_ = [("data", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("relu", c_int32)]
 
 
+class MrgActList(Structure):
+    _fields_ = [("acts", MrgAct * 8), ("n", c_int32)]
+
+
 P, I32, I64, F32, SZ = c_void_p, c_int32, c_int64, c_float, c_size_t
 
 _SIGNATURES = {
@@ -48,12 +52,15 @@ _SIGNATURES = {
     "mrg_sparse_gate_bwd_finalize": (I32, [P, I64, I32, P, P, P, P]),
     "mrg_dense_gate_fwd": (I32, [P, MrgAct, I64, I32, I32, P, F32, P, P, P]),
     "mrg_dense_gate_bwd": (I32, [P, P, MrgAct, I64, I32, I32, P, F32, P, P, I32, P]),
+    "mrg_mixed_sum_fwd": (I32, [MrgActList, P, I64, I32, P, P]),
     "mrg_seg_reduce_workspace_bytes": (SZ, [I64, I32, I32]),
     "mrg_seg_reduce_fwd": (I32, [I32, MrgAct, P, P, P, P, I64, I64, I32, P, P, F32, MrgAct, I32, P, P, P, SZ, P]),
     "mrg_seg_reduce_bwd": (I32, [I32, P, P, P, MrgAct, P, P, I64, I64, I32, P, I32, P]),
     "mrg_amax_tc_supported": (I32, [I32]),
     "mrg_amax_tc_workspace_bytes": (SZ, [I64, I32]),
     "mrg_amax_tc_fwd": (I32, [MrgAct, P, P, P, P, I64, I64, I32, MrgAct, P, P, P, SZ, P]),
+    "mrg_amax_bwd_workspace_bytes": (SZ, [I32]),
+    "mrg_amax_bwd": (I32, [P, P, MrgAct, P, P, P, P, P, I64, I64, I64, I32, P, P, P, P, SZ, P]),
     "mrg_bce_nparts": (I32, [I64]),
     "mrg_sigmoid_bce_fwd": (I32, [P, P, I64, P, P, P, P]),
     "mrg_sigmoid_bce_bwd": (I32, [P, P, I64, P, P, P]),
@@ -63,7 +70,7 @@ _OPTIONAL = {}
 
 _lib = None
 # kernels enqueued per C-ABI call (default 1); used for the gpu_launches count bench.py reports
-KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_chunk_build": 3}
+KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_amax_bwd": 3, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_chunk_build": 3}
 launch_count = 0   # libmrgnas kernels launched so far
 _profile = None    # when a list: (name, start_event, end_event) per call (bench.py per-kernel timing)
 

@@ -659,6 +659,49 @@ __global__ void __launch_bounds__(kThreads) sigmoid_bce_bwd_kernel(const float* 
   for (int64_t i = 4 * n4 + tid; i < n; i += nthreads) dlogit[i] = f(logit[i], label[i]);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// K9 DARTS MixedOp: out = sum_k w_k * relu?(a_k * y_k + b_k)  (cell_lp.py:25-33, cell.py:23-31)
+// All candidates' BatchNorm+ReLU and the alpha-weighted sum in ONE pass: K reads + 1 write
+// instead of K BN passes + K scalings + K-1 adds.
+// ---------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kThreads) mixed_sum_kernel(mrg_act_list ys, const float* __restrict__ w,
+                                                             int64_t rows, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float wk[MRG_MAX_MIXED];
+  for (int k = 0; k < ys.n; ++k) wk[k] = __ldg(w + k);
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < ys.n; ++k) {
+          const mrg_act& a = ys.acts[k];
+          float4 x = ld_stream4(a.data + off);
+          if (a.scale) {
+            const float4 sc = ldg4(a.scale + 4 * c4), sh = ldg4(a.shift + 4 * c4);
+            x.x = fmaf(sc.x, x.x, sh.x); x.y = fmaf(sc.y, x.y, sh.y);
+            x.z = fmaf(sc.z, x.z, sh.z); x.w = fmaf(sc.w, x.w, sh.w);
+          }
+          if (a.relu) {
+            x.x = x.x > 0.f ? x.x : 0.f; x.y = x.y > 0.f ? x.y : 0.f;
+            x.z = x.z > 0.f ? x.z : 0.f; x.w = x.w > 0.f ? x.w : 0.f;
+          }
+          // Python's sum(): ((0 + w0*s0) + w1*s1) + ... -- same association order
+          acc.x += wk[k] * x.x; acc.y += wk[k] * x.y; acc.z += wk[k] * x.z; acc.w += wk[k] * x.w;
+        }
+        st_stream4(out + off, acc);
+      }
+    }
+  }
+}
+
 }  // namespace mrg
 
 // =========================================================================================
@@ -867,5 +910,15 @@ extern "C" int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64
   MRG_CHECK_ARG(logit && label && dlogit && n > 0, "sigmoid_bce_bwd: null pointer / n");
   sigmoid_bce_bwd_kernel<<<bce_grid(n), kThreads, 0, (cudaStream_t)stream>>>(logit, label, n, gscale, dlogit);
   MRG_LAUNCH_CHECK("sigmoid_bce_bwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_mixed_sum_fwd(mrg_act_list ys, const float* w, int64_t rows, int32_t D, float* out, void* stream) {
+  MRG_CHECK_ARG(w && out && ys.n > 0 && ys.n <= MRG_MAX_MIXED, "mixed_sum_fwd: arguments");
+  MRG_CHECK_ARG(valid_D(D), "mixed_sum_fwd: D");
+  for (int k = 0; k < ys.n; ++k) MRG_CHECK_ARG(ys.acts[k].data, "mixed_sum_fwd: null candidate");
+  if (rows <= 0) return MRG_OK;
+  MRG_DISPATCH_NV(D, mixed_sum_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(ys, w, rows, D, out));
+  MRG_LAUNCH_CHECK("mixed_sum_fwd");
   return MRG_OK;
 }

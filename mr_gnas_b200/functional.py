@@ -423,3 +423,122 @@ class SigmoidBCE(torch.autograd.Function):
         gs = gl.reshape(1).float().contiguous()
         call("mrg_sigmoid_bce_bwd", ptr(logit), ptr(label), logit.numel(), ptr(gs), ptr(dl), stream())
         return dl, None
+
+
+# ------------------------------------------------------------------------------------------
+# plain ReLU through the same row kernels (NC OpModule without op_norm: model.py:22-28)
+# ------------------------------------------------------------------------------------------
+class ReluAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y):
+        y = _f32c(y)
+        rows, D = y.shape
+        s = torch.empty_like(y)
+        call("mrg_affine_act", act(y, relu=True), rows, D, ptr(s), stream())
+        ctx.save_for_backward(y)
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        (y,) = ctx.saved_tensors
+        ds = _f32c(ds)
+        rows, D = y.shape
+        coef = torch.cat([torch.zeros(2 * D, device=y.device), torch.ones(D, device=y.device)]).contiguous()
+        dy = torch.empty_like(y)
+        call("mrg_bn_bwd_apply", ptr(ds), act(y, relu=True), ptr(coef), rows, D, ptr(dy), 0, stream())
+        return dy
+
+
+# ------------------------------------------------------------------------------------------
+# K9: DARTS MixedOp = sum_k w_k * ReLU(BN_k(y_k)) in one pass
+# ------------------------------------------------------------------------------------------
+class MixedSum(torch.autograd.Function):
+    """cell_lp.py:25-33 / cell.py:23-31.  Inputs: w [K] (a softmax(alpha) row), then per candidate
+    (y_k, gamma_k, beta_k).  BN statistics, normalisation, ReLU and the weighted sum are fused; the
+    backward folds w_k into each candidate's BatchNorm backward (no [rows,D] temporaries per candidate
+    besides the returned dy_k)."""
+
+    @staticmethod
+    def forward(ctx, w, training, eps, momentum, bns, stats_list, *tensors):
+        K_ = len(tensors) // 3
+        ys = [_f32c(t) for t in tensors[0::3]]
+        gammas, betas = tensors[1::3], tensors[2::3]
+        rows, D = ys[0].shape
+        dev = ys[0].device
+        w = _f32c(w)
+        acts, saved = [], []
+        lst = _lib.MrgActList()
+        lst.n = K_
+        for k in range(K_):
+            a = torch.empty(D, dtype=torch.float32, device=dev)
+            b = torch.empty_like(a)
+            rm, rv = bns[k]
+            if training:
+                st = stats_list[k]
+                nparts = stats_nparts(rows)
+                if st is None:
+                    st = _stats_buf(nparts, D, dev)
+                    call("mrg_colstats", act(ys[k]), rows, D, ptr(st), stream())
+                else:
+                    nparts = st.numel() // (2 * D)
+                mean, invstd = torch.empty_like(a), torch.empty_like(a)
+                call("mrg_bn_finalize", ptr(st), nparts, rows, D, ptr(gammas[k]), ptr(betas[k]), float(eps),
+                     float(momentum), ptr(rm), ptr(rv), ptr(mean), ptr(invstd), ptr(a), ptr(b), stream())
+            else:
+                invstd = torch.rsqrt(rv + eps)
+                mean = rm
+                a = (gammas[k] * invstd).contiguous()
+                b = (betas[k] - a * mean).contiguous()
+            lst.acts[k] = act(ys[k], a, b, True)
+            saved += [ys[k], gammas[k], mean, invstd, a, b]
+        out = torch.empty_like(ys[0])
+        call("mrg_mixed_sum_fwd", lst, ptr(w), rows, D, ptr(out), stream())
+        ctx.K_, ctx.training = K_, training
+        ctx.save_for_backward(w, *saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, *saved = ctx.saved_tensors
+        K_ = ctx.K_
+        dout = _f32c(dout)
+        rows, D = dout.shape
+        dev = dout.device
+        dw = torch.empty(K_, dtype=torch.float32, device=dev)
+        grads = []
+        nparts = stats_nparts(rows)
+        for k in range(K_):
+            y, gamma, mean, invstd, a, b = saved[6 * k:6 * k + 6]
+            yact = act(y, a, b, True)
+            bst = _stats_buf(nparts, D, dev)
+            call("mrg_bn_bwd_reduce", ptr(dout), yact, rows, D, ptr(bst), stream())
+            dgamma = torch.empty(D, dtype=torch.float32, device=dev)
+            dbeta = torch.empty_like(dgamma)
+            coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
+            call("mrg_bn_bwd_finalize", ptr(bst), nparts, rows, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
+                 ptr(dbeta), ptr(coef), stream())
+            # sum(dout * s_k) = sum_c a_c * S2_c + b_c * S1_c  with S1 = dbeta, S2 = dgamma/invstd + mean*S1
+            s1 = dbeta
+            s2 = dgamma / invstd + mean * s1
+            dw[k] = (a * s2 + b * s1).sum()
+            if not ctx.training:  # eval: no statistics path -> dy = w_k * a * dz
+                coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
+            coef = (coef * w[k]).contiguous()
+            dy = torch.empty_like(y)
+            call("mrg_bn_bwd_apply", ptr(dout), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
+            grads += [dy, dgamma * w[k], dbeta * w[k]]
+        return (dw, None, None, None, None, None, *grads)
+
+
+def mixed_sum(weights, ys, bn_modules):
+    """sum_k weights[k] * ReLU(bn_k(ys[k])) with nn.BatchNorm1d modules supplying parameters/buffers."""
+    training = bn_modules[0].training
+    bns, flat, stats = [], [], []
+    for y, bn in zip(ys, bn_modules):
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        bns.append((bn.running_mean, bn.running_var))
+        stats.append(getattr(y, 'mrg_stats', None))
+        flat += [y, bn.weight, bn.bias]
+    mom = 0.1 if bn_modules[0].momentum is None else bn_modules[0].momentum
+    return MixedSum.apply(weights, training, bn_modules[0].eps, mom, bns, stats, *flat)

@@ -219,3 +219,43 @@ class MRGraph:
         if n.dtype != torch.float32 or not n.is_contiguous() or n.dim() != 1:
             n = n.reshape(-1).float().contiguous()
         return n
+
+
+class MRBlock(MRGraph):
+    """One message-flow block of the NC path (DGL ``blocks[i]`` of MultiLayerFullNeighborSampler,
+    train/mr_nc_train.py:42-51): E_b edges from global source nodes into n_dst local destinations.
+    Exposes what models/model.py:156-178 reads: ``edata['_ID']`` (dgl.EID: parent edge ids),
+    ``edata['_TYPE']`` (dgl.ETYPE) and ``dstdata['_ID']`` (dgl.NID: global ids of the destinations)."""
+
+    @classmethod
+    def build(cls, parent_eid, etype, dst_local, dst_nid, device="cuda"):
+        b = cls(int(dst_nid.numel()), device)
+        dst_local = torch.as_tensor(dst_local)
+        b._finalize(torch.zeros_like(dst_local), dst_local, torch.zeros_like(dst_local), 1, with_norm=False,
+                    dst_only=True)
+        b.edata['_ID'] = torch.as_tensor(parent_eid).to(device).long()
+        b.edata['_TYPE'] = torch.as_tensor(etype).to(device).long()
+        b.dstdata = {'_ID': torch.as_tensor(dst_nid).to(device).long()}
+        return b
+
+
+def full_neighbor_blocks(src, dst, etype, seeds, num_layers, device="cuda"):
+    """All in-edges of the seeds, then of their sources, ... (MultiLayerFullNeighborSampler with
+    return_eids=True).  Returns blocks ordered input-side first, like DGL.  Host-side glue (numpy)."""
+    src, dst, etype = (np.asarray(a) for a in (src, dst, etype))
+    order = np.argsort(dst, kind="stable")
+    ptr = np.zeros(int(max(src.max(initial=0), dst.max(initial=0))) + 2, dtype=np.int64)
+    np.add.at(ptr, dst + 1, 1)
+    ptr = np.cumsum(ptr)
+    blocks = []
+    frontier = np.asarray(seeds, dtype=np.int64)
+    for _ in range(num_layers):
+        eids = np.concatenate([order[ptr[n]:ptr[n + 1]] for n in frontier]) if len(frontier) else np.zeros(0, np.int64)
+        eids = np.sort(eids)  # ascending parent edge id == DGL block edge order
+        local = np.searchsorted(frontier, dst[eids]) if np.all(np.diff(frontier) > 0) else \
+            np.array([int(np.nonzero(frontier == d)[0][0]) for d in dst[eids]], dtype=np.int64)
+        blocks.append(MRBlock.build(eids, etype[eids], local, torch.from_numpy(frontier), device))
+        # next (outer) layer: destinations = seeds of this layer followed by their new sources
+        nxt = np.unique(np.concatenate([frontier, src[eids]]))
+        frontier = nxt
+    return blocks[::-1]

@@ -292,6 +292,78 @@ def gen_compgcn():
     torch.save({"graph": gd, "Din": Din, "Dout": Dout, "cases": cases}, os.path.join(OUT, "compgcn.pt"))
 
 
+NC_GENOTYPE = ("[Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_dense', 2, 1), ('f_sparse', 3, 2), ('f_identity', 4, 3), "
+               "('a_sum', 5, 2), ('a_sum', 6, 3), ('a_mean', 7, 4), ('f_dense_last', 8, 7), ('f_sparse_last', 9, 7), "
+               "('f_sparse_last', 10, 5)], concat_node=[5, 6, 7, 8, 9, 10]), Genotype(alpha_cell=[('pre_sub', 1, 0), "
+               "('f_sparse', 2, 1), ('f_identity', 3, 2), ('f_identity', 4, 1), ('a_max', 5, 2), ('a_mean', 6, 3), "
+               "('a_mean', 7, 4), ('f_sparse_last', 8, 7), ('f_sparse_last', 9, 8), ('f_identity', 10, 9)], "
+               "concat_node=[5, 6, 7, 8, 9, 10])]")  # train/mr_nc_train.py:220 default
+
+
+def _nc_blocks(src, dst, etype, seeds, layers):
+    """Full-neighbour blocks as DGL's MultiLayerFullNeighborSampler(return_eids=True) yields them: block edges in
+    ascending parent edge id, destinations = the layer's frontier, outermost block first."""
+    blocks, frontier = [], np.asarray(seeds)
+    for _ in range(layers):
+        eids = np.nonzero(np.isin(dst, frontier))[0]
+        pos = {int(n): i for i, n in enumerate(frontier)}
+        local = np.array([pos[int(d)] for d in dst[eids]], dtype=np.int64)
+        b = dgl_stub.StubGraph(len(frontier), src[eids], local)
+        b.edata['_ID'] = torch.from_numpy(eids).long()
+        b.edata['_TYPE'] = torch.from_numpy(etype[eids]).long()
+        b.ndata['_ID'] = torch.from_numpy(frontier).long()
+        blocks.append((b, eids, local, frontier.copy()))
+        frontier = np.unique(np.concatenate([frontier, src[eids]]))
+    return blocks[::-1]
+
+
+def gen_network_nc():
+    import models.model as ref_model_nc
+    import models.model_search as ref_search_nc
+    from collections import namedtuple
+    G2 = namedtuple('Genotype', 'alpha_cell concat_node score_func', defaults=(None,))
+    N, ET, E, D, D0, C, NB = 70, 6, 400, 16, 8, 3, 5
+    rng = np.random.RandomState(23)
+    src, dst = rng.randint(0, N, E), rng.randint(0, N - 5, E)
+    etype = rng.randint(0, ET, E)
+    seeds = np.sort(rng.choice(N - 5, 7, replace=False))
+    blocks = _nc_blocks(src, dst, etype, seeds, 2)
+    trip_index = torch.from_numpy(np.stack([np.arange(E), src, dst], 1)).long()
+    labels = torch.from_numpy(rng.randint(0, C, len(seeds))).long()
+    block_dump = [{"eids": torch.from_numpy(e), "local": torch.from_numpy(l), "dst_nid": torch.from_numpy(f)}
+                  for (_, e, l, f) in blocks]
+    out = {"N": N, "ET": ET, "D": D, "D0": D0, "C": C, "NB": NB, "src": torch.from_numpy(src), "dst": torch.from_numpy(dst),
+           "etype": torch.from_numpy(etype), "seeds": torch.from_numpy(seeds), "blocks": block_dump,
+           "trip_index": trip_index, "labels": labels, "genotype": NC_GENOTYPE}
+    for op_norm in (True, False):
+        torch.manual_seed(8)
+        args = types.SimpleNamespace(feature_dim=D, op_norm=op_norm)
+        geno = eval(NC_GENOTYPE, {"Genotype": G2})
+        model = ref_model_nc.Network('cpu', geno, N, C, ET, 2, 1, 2, D, D0, NB, nn.CrossEntropyLoss(), args)
+        model.apply(weights_init)
+        model.train()
+        state0 = _sd(model)
+        logits = model(trip_index, [b for (b, _, _, _) in blocks])
+        loss = nn.CrossEntropyLoss()(logits, labels)
+        loss.backward()
+        out["derived_norm%d" % int(op_norm)] = {"state0": state0, "logits": logits.detach(), "loss": loss.detach(),
+                                                 "grads": _grads(model), "state_keys": list(state0.keys())}
+    torch.manual_seed(9)
+    sm = ref_search_nc.Network('cpu', N, C, ET, 2, 1, 2, D, D0, NB, 0.0)
+    sm.apply(weights_init)
+    sm.train()
+    state0 = _sd(sm)
+    alphas0 = [a.detach().clone() for a in sm.arch_parameters()]
+    logits = sm(trip_index, [b for (b, _, _, _) in blocks])
+    loss = nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    import configs.genotypes as cg
+    out["search"] = {"state0": state0, "alphas0": alphas0, "logits": logits.detach(), "loss": loss.detach(),
+                     "grads": _grads(sm), "dalphas": [a.grad.clone() for a in sm.arch_parameters()],
+                     "genotypes": str(sm.show_genotypes()), "state_keys": list(state0.keys())}
+    torch.save(out, os.path.join(OUT, "network_nc.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_ops_lp()
@@ -300,5 +372,6 @@ if __name__ == "__main__":
     gen_mixed_op()
     gen_search_lp()
     gen_compgcn()
+    gen_network_nc()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

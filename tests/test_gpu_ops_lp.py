@@ -196,6 +196,8 @@ def _amax_expected_grads(x, W, b, arg, E, cot):
     return xo.grad, Wo.grad, bo.grad
 
 
+@pytest.mark.parametrize("D", [8, 64, 128, 200, 256])
+@pytest.mark.parametrize("shape", ["zipf", "hub", "tiny"])
 def test_amax_tensor_core_vs_simt_and_oracle(dev, D, shape):
     """Fused tcgen05 a_max (3xTF32) against (a) the oracle in fp32/fp64 and (b) the SIMT/cuBLAS path of
     this library; argmax bit-exact against an exact recomputation on the kernel's own fp32 messages is

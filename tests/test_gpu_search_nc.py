@@ -1,0 +1,233 @@
+"""GPU parity for the remaining hot-path rows: DARTS MixedOp / LP supernet (cell_lp.py, model_search_lp.py),
+NC operators / derived net / supernet (operations.py, model.py, cell.py, model_search.py) and CompGraphConv
+(compgcn.py) -- all against golden vectors produced by the real reference code."""
+import os
+import types
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+Genotype = namedtuple("Genotype", "alpha_cell concat_node score_func", defaults=(None,))
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+def _check(name, a, b, tol=REL):
+    assert tuple(a.shape) == tuple(b.shape), f"{name}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    e = _err(a, b)
+    assert e <= tol, f"{name}: rel err {e:.3e} > {tol:.1e}"
+
+
+DEV = "cuda:0"
+
+
+def _lp_graph(gd):
+    from mr_gnas_b200.graph import MRGraph
+    return MRGraph.from_triples(gd["num_ent"], gd["triples"].numpy(), gd["num_rels"], device=DEV)
+
+
+# ------------------------------------------------------------------------------ MixedOp (K9)
+@pytest.mark.parametrize("tag", ["pre", "first", "middle", "last"])
+def test_mixed_op_golden(golden_dir, tag):
+    from mr_gnas_b200.cell_lp import MixedOp
+    G = _load(golden_dir, "mixed_op.pt")
+    g = _lp_graph(G["graph"])
+    c = G["cases"][tag]
+    mo = MixedOp(G["D"], 0.0, c["names"]).to(DEV)
+    mo.load_state_dict(c["state"])
+    mo.train()
+    alpha = c["alpha"].to(DEV).requires_grad_(True)
+    x = c["x"].to(DEV).requires_grad_(True)
+    xin = c["xin"].to(DEV).requires_grad_(True)
+    out = mo(torch.softmax(alpha, 0), g, x, xin)
+    _check("out", out, c["out"])
+    out.backward(c["cot"].to(DEV))
+    _check("dalpha", alpha.grad, c["dalpha"])
+    _check("dx", x.grad, c["dx"])
+    if c["dxin"] is not None:
+        _check("dxin", xin.grad if xin.grad is not None else torch.zeros_like(xin), c["dxin"])
+    for k, p in mo.named_parameters():
+        if c["dparams"][k] is not None:
+            _check("d" + k, p.grad, c["dparams"][k])
+    # running statistics of every candidate's BN were updated exactly once
+    for k, v in mo.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(c["state"][k]) + 1
+
+
+# ------------------------------------------------------------------------------ LP supernet
+def test_search_lp_golden(golden_dir):
+    from mr_gnas_b200.graph import MRGraph
+    from mr_gnas_b200.model_search_lp import Network
+    from mr_gnas_b200.utils import weights_init
+    G = _load(golden_dir, "search_lp.pt")
+    N, R, D, D0 = G["num_ent"], G["num_rels"], G["D"], G["D0"]
+    # seeded construction reproduces the reference init (parameters AND alphas)
+    torch.manual_seed(5)
+    np.random.seed(5)
+    from oracle.mrg_oracle import synth_kg
+    synth_kg(N, R, 60, seed=13)  # (numpy RandomState is local; kept for symmetry with the generator)
+    model = Network('cpu', N, R, 2, 1, 2, 2, D, D0, 2 * R + 1, 40, 0.0, 0.0)
+    model.apply(weights_init)
+    assert list(model.state_dict().keys()) == G["state_keys"]
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, G["state0"][k]), k
+    for a, b in zip(model.arch_parameters(), G["alphas0"]):
+        assert torch.equal(a.detach(), b)
+    assert str(model.show_genotypes()) == G["genotypes"]
+    # forward / loss / grads on the device
+    model = model.to(DEV)
+    model._device = DEV
+    alphas = [a.detach().to(DEV).requires_grad_(True) for a in G["alphas0"]]
+    (model.alphas_zero_cell, model.alphas_first_cell, model.alphas_middle_cell, model.alphas_last_cell,
+     model.alphas_final_cell) = alphas
+    model._arch_parameters = alphas
+    model.train()
+    g = MRGraph.from_edges(G["src"], G["dst"], G["etype"], N, 2 * R + 1, device=DEV)
+    assert np.array_equal(g.edge_norm.cpu().numpy(), G["norm"].view(-1).numpy())
+    loss = model._loss(g, G["node_id"].to(DEV), G["src"].to(DEV), G["etype"].to(DEV), G["samples"].to(DEV),
+                       G["labels"].to(DEV))
+    _check("loss", loss.view(1), G["loss"].view(1))
+    loss.backward()
+    worst = max((_err(p.grad, G["grads"][k]), k) for k, p in model.named_parameters() if G["grads"][k] is not None)
+    assert worst[0] <= REL, worst
+    for a, ref in zip(alphas, G["dalphas"]):
+        if ref is not None:
+            _check("dalpha", a.grad, ref)
+
+
+# ------------------------------------------------------------------------------ NC operators
+@pytest.mark.parametrize("name", ['a_max', 'a_mean', 'a_sum', 'a_std', 'f_dense', 'f_sparse', 'f_dense_last',
+                                  'f_sparse_last'])
+@pytest.mark.parametrize("tc", [True, False])
+def test_nc_op_golden(golden_dir, name, tc):
+    from mr_gnas_b200 import operations as ops
+    from mr_gnas_b200 import operations_lp
+    from mr_gnas_b200.graph import MRGraph
+    if not tc and name != 'a_max':
+        pytest.skip("tensor-core switch only affects a_max")
+    G = _load(golden_dir, "ops_nc.pt")
+    c = G["cases"][name]
+    g = MRGraph.from_block(G["dst"], G["n_dst"], device=DEV)
+    op = ops.MIXED_OPS[name]({'feature_dim': G["D"]}).to(DEV)
+    op.load_state_dict(c["state"])
+    x = c["x"].to(DEV).requires_grad_(True)
+    xin = c["xin"].to(DEV).requires_grad_(True)
+    operations_lp.USE_TENSOR_CORES = tc
+    try:
+        out = op(g, x, xin)
+        _check("out", out, c["out"])
+        out.backward(c["cot"].to(DEV))
+    finally:
+        operations_lp.USE_TENSOR_CORES = True
+    _check("dx", x.grad, c["dx"])
+    if c["dxin"] is not None:
+        _check("dxin", xin.grad if xin.grad is not None else torch.zeros_like(xin), c["dxin"])
+    for k, p in op.named_parameters():
+        if c["dparams"][k] is not None:
+            _check("d" + k, p.grad, c["dparams"][k])
+
+
+# ------------------------------------------------------------------------------ NC networks
+def _nc_blocks(G):
+    from mr_gnas_b200.graph import MRBlock
+    return [MRBlock.build(b["eids"], G["etype"][b["eids"]], b["local"], b["dst_nid"], device=DEV) for b in G["blocks"]]
+
+
+def test_block_sampler_matches_golden_blocks(golden_dir):
+    from mr_gnas_b200.graph import full_neighbor_blocks
+    G = _load(golden_dir, "network_nc.pt")
+    blocks = full_neighbor_blocks(G["src"].numpy(), G["dst"].numpy(), G["etype"].numpy(), G["seeds"].numpy(), 2,
+                                  device=DEV)
+    for b, ref in zip(blocks, G["blocks"]):
+        assert torch.equal(b.edata['_ID'].cpu(), ref["eids"])
+        assert torch.equal(b.dst.cpu().long(), ref["local"])
+        assert torch.equal(b.dstdata['_ID'].cpu(), ref["dst_nid"])
+
+
+@pytest.mark.parametrize("op_norm", [True, False])
+def test_network_nc_golden(golden_dir, op_norm):
+    from mr_gnas_b200.model import Network
+    G = _load(golden_dir, "network_nc.pt")
+    ref = G["derived_norm%d" % int(op_norm)]
+    args = types.SimpleNamespace(feature_dim=G["D"], op_norm=op_norm)
+    model = Network(DEV, eval(G["genotype"]), G["N"], G["C"], G["ET"], 2, 1, 2, G["D"], G["D0"], G["NB"],
+                    nn.CrossEntropyLoss(), args)
+    assert list(model.state_dict().keys()) == ref["state_keys"]
+    model.load_state_dict(ref["state0"])
+    model = model.to(DEV).train()
+    logits = model(G["trip_index"].to(DEV), _nc_blocks(G))
+    _check("logits", logits, ref["logits"])
+    loss = nn.CrossEntropyLoss()(logits, G["labels"].to(DEV))
+    _check("loss", loss.view(1), ref["loss"].view(1))
+    loss.backward()
+    worst = max((_err(p.grad, ref["grads"][k]), k) for k, p in model.named_parameters() if ref["grads"][k] is not None)
+    assert worst[0] <= REL, worst
+
+
+def test_search_nc_golden(golden_dir):
+    from mr_gnas_b200.model_search import Network
+    from mr_gnas_b200.utils import weights_init
+    G = _load(golden_dir, "network_nc.pt")
+    ref = G["search"]
+    torch.manual_seed(9)
+    model = Network('cpu', G["N"], G["C"], G["ET"], 2, 1, 2, G["D"], G["D0"], G["NB"], 0.0)
+    model.apply(weights_init)
+    assert list(model.state_dict().keys()) == ref["state_keys"]
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, ref["state0"][k]), k
+    for a, b in zip(model.arch_parameters(), ref["alphas0"]):
+        assert torch.equal(a.detach(), b)
+    assert str(model.show_genotypes()) == ref["genotypes"]
+    model = model.to(DEV)
+    alphas = [a.detach().to(DEV).requires_grad_(True) for a in ref["alphas0"]]
+    model.alphas_zero_cell, model.alphas_first_cell, model.alphas_middle_cell, model.alphas_last_cell = alphas
+    model._arch_parameters = alphas
+    model.train()
+    logits = model(G["trip_index"].to(DEV), _nc_blocks(G))
+    _check("logits", logits, ref["logits"])
+    loss = nn.CrossEntropyLoss()(logits, G["labels"].to(DEV))
+    loss.backward()
+    worst = max((_err(p.grad, ref["grads"][k]), k) for k, p in model.named_parameters() if ref["grads"][k] is not None)
+    assert worst[0] <= REL, worst
+    for a, r in zip(alphas, ref["dalphas"]):
+        _check("dalpha", a.grad, r)
+
+
+# ------------------------------------------------------------------------------ CompGraphConv (K10)
+@pytest.mark.parametrize("comp", ["sub", "mul", "ccorr"])
+def test_compgcn_golden(golden_dir, comp):
+    from mr_gnas_b200.compgcn import CompGraphConv
+    G = _load(golden_dir, "compgcn.pt")
+    gd, c = G["graph"], G["cases"][comp]
+    g = _lp_graph(gd)
+    E = g.E
+    g.edata['etype'] = g.edata['e_type']
+    g.edata['in_edges_mask'] = torch.arange(E, device=DEV) < E // 2
+    g.edata['out_edges_mask'] = torch.arange(E, device=DEV) >= E // 2
+    layer = CompGraphConv(G["Din"], G["Dout"], comp_fn=comp, batchnorm=True, dropout=0.0).to(DEV)
+    layer.load_state_dict(c["state"])
+    layer.train()
+    h = c["h"].to(DEV).requires_grad_(True)
+    r = c["r"].to(DEV).requires_grad_(True)
+    n_out, r_out = layer(g, h, r)
+    _check("n_out", n_out, c["n_out"])
+    _check("r_out", r_out, c["r_out"])
+    ((n_out * c["c1"].to(DEV)).sum() + (r_out * c["c2"].to(DEV)).sum()).backward()
+    _check("dh", h.grad, c["dh"])
+    _check("dr", r.grad, c["dr"])
+    for k, p in layer.named_parameters():
+        if c["dparams"][k] is not None:
+            _check("d" + k, p.grad, c["dparams"][k])

@@ -75,3 +75,50 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", ""), f"{f} references oracle/"
+
+
+def test_supernet_construction_matches_reference(golden_dir):
+    """LP and NC supernets: identical state_dict keys, seeded init (parameters and alpha tables) and decoded
+    genotype strings (model_search_lp.py:215-311) -- all host-side logic."""
+    from mr_gnas_b200.model_search import Network as SearchNC
+    from mr_gnas_b200.model_search_lp import Network as SearchLP
+    from mr_gnas_b200.utils import weights_init
+    G = torch.load(os.path.join(golden_dir, "search_lp.pt"), weights_only=False)
+    torch.manual_seed(5)
+    m = SearchLP('cpu', G['num_ent'], G['num_rels'], 2, 1, 2, 2, G['D'], G['D0'], 2 * G['num_rels'] + 1, 40, 0.0, 0.0)
+    m.apply(weights_init)
+    assert list(m.state_dict().keys()) == G['state_keys']
+    assert all(torch.equal(v, G['state0'][k]) for k, v in m.state_dict().items())
+    assert all(torch.equal(a.detach(), b) for a, b in zip(m.arch_parameters(), G['alphas0']))
+    assert str(m.show_genotypes()) == G['genotypes']
+    G = torch.load(os.path.join(golden_dir, "network_nc.pt"), weights_only=False)
+    r = G['search']
+    torch.manual_seed(9)
+    m = SearchNC('cpu', G['N'], G['C'], G['ET'], 2, 1, 2, G['D'], G['D0'], G['NB'], 0.0)
+    m.apply(weights_init)
+    assert list(m.state_dict().keys()) == r['state_keys']
+    assert all(torch.equal(v, r['state0'][k]) for k, v in m.state_dict().items())
+    assert str(m.show_genotypes()) == r['genotypes']
+
+
+def test_nc_derived_network_keys_and_default_genotype(golden_dir):
+    from mr_gnas_b200.genotypes import Genotype
+    from mr_gnas_b200.model import Network
+    G = torch.load(os.path.join(golden_dir, "network_nc.pt"), weights_only=False)
+    geno = eval(G['genotype'])          # the NC default string has no score_func: must still parse
+    assert geno[0].score_func is None
+    m = Network('cpu', geno, G['N'], G['C'], G['ET'], 2, 1, 2, G['D'], G['D0'], G['NB'], nn.CrossEntropyLoss(),
+                types.SimpleNamespace(feature_dim=G['D'], op_norm=True))
+    assert list(m.state_dict().keys()) == G['derived_norm1']['state_keys']
+
+
+def test_process_matches_reference_items(golden_dir):
+    from mr_gnas_b200.process_data import make_batch, process
+    G = torch.load(os.path.join(golden_dir, "network_lp.pt"), weights_only=False)
+    gd = G["graph"]
+    trip = gd["triples"].numpy()
+    items = process({'train': trip, 'valid': trip[:5], 'test': trip[:5]}, gd["num_rels"])['train'][: G["dims"]["B"]]
+    for it, (tr, lab) in zip(items, G["train_items"]):
+        assert list(it["triple"]) == tr and sorted(it["label"]) == sorted(lab)
+    t, y = make_batch(items, gd["num_ent"], lbl_smooth=0.1)
+    assert torch.equal(y, G["labels"]) and torch.equal(t[:, 0], G["subj"]) and torch.equal(t[:, 1], G["rel"])
