@@ -155,7 +155,7 @@ int mrg_compose_bwd_rows(const float* dy, const float* x, const float* r, int64_
  * where v = a.weight @ W.weight (split into the x / xin halves) and c = a.weight . W.bias
  * (no non-linearity sits between W and a in the reference).  xin.data == NULL drops the
  * second term; xin.data == x.data reads the row once.  `gate` [rows] is saved for backward.
- * Backward returns dx/dxin w.r.t. the activated inputs (accumulate!=0: +=) and per-block
+ * Backward returns dx/dxin w.r.t. the activated inputs (accumulate bit 0: dx +=, bit 1: dxin +=) and per-block
  * partials of dv1, dv2, dc in `dparam` ([nparts][2*D+1] doubles... see mrg_gate_dparam_count).
  * ---------------------------------------------------------------------------------- */
 int mrg_sparse_gate_fwd(mrg_act x, mrg_act xin, int64_t rows, int32_t D, const float* v1, const float* v2,

@@ -441,14 +441,14 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
           o.x += oi.x; o.y += oi.y; o.z += oi.z; o.w += oi.w;
         }
         if (dx) {
-          if (accumulate) {
+          if (accumulate & 1) {
             float4 p = *reinterpret_cast<const float4*>(dx + off);
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
           }
           st4(dx + off, o);
         }
         if (HAS_IN && !SAME && dxin) {
-          if (accumulate) {
+          if (accumulate & 2) {
             float4 p = *reinterpret_cast<const float4*>(dxin + off);
             oi.x += p.x; oi.y += p.y; oi.z += p.z; oi.w += p.w;
           }

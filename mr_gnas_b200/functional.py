@@ -360,18 +360,32 @@ class AMaxTC(torch.autograd.Function):
         g = ctx.g
         x, weight, arg = ctx.saved_tensors
         gout = _f32c(gout)
-        D = gout.shape[1]
-        E = g.E
-        dm = torch.empty(E, D, dtype=torch.float32, device=gout.device)
-        call("mrg_seg_reduce_bwd", 2, ptr(gout), ptr(arg), None, act(None), ptr(g.dst), ptr(g.csr.ptr), E, 0, D,
-             ptr(dm), 0, stream())
-        dx = torch.empty_like(x)
-        torch.mm(dm, weight, out=dx[:E])          # edge-tile GEMM (library) -- tcgen05 backward: see DESIGN.md
-        if ctx.has_residual:
-            dx[E:].copy_(gout)
-        dw = dm.t().mm(x[:E])
-        db = dm.sum(0)
+        dx, dw, db = amax_backward(g, gout, arg, act(x), weight, x.shape[0], ctx.has_residual, ctx.needs_input_grad[0])
         return dx, dw, db, None, None
+
+
+_bwd_ws = {}
+
+
+def amax_backward(g, gout, arg, x_act, weight, rows, has_residual, need_dx=True, dx=None):
+    """Sparse backward of a_max (mrg_amax_bwd): dX over the E edge rows (+ residual rows = gout), dW, db."""
+    D = gout.shape[1]
+    dev = gout.device
+    E = g.E
+    key = (D, str(dev))
+    if key not in _bwd_ws:
+        _bwd_ws[key] = torch.empty(int(_lib.load().mrg_amax_bwd_workspace_bytes(D)), dtype=torch.uint8, device=dev)
+    ws = _bwd_ws[key]
+    if need_dx and dx is None:
+        dx = torch.empty(rows, D, dtype=torch.float32, device=dev)
+    dw = torch.empty(D, D, dtype=torch.float32, device=dev)
+    db = torch.empty(D, dtype=torch.float32, device=dev)
+    call("mrg_amax_bwd", ptr(gout), ptr(arg), x_act, ptr(weight), ptr(g.csr.ptr), ptr(g.csr.idx),
+         ptr(g.csr.chunk_first), ptr(g.csr.chunk_seg), g.N, E, g.csr.max_chunks, D, ptr(dx) if need_dx else None,
+         ptr(dw), ptr(db), ptr(ws), ws.numel(), stream())
+    if need_dx and has_residual:
+        dx[E:].copy_(gout)
+    return (dx if need_dx else None), dw, db
 
 
 class AggSumLP(torch.autograd.Function):

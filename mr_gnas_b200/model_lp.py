@@ -13,7 +13,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as K
+from . import fused_cell
 from .operations_lp import MIXED_OPS, MIXED_OPS_sf
+
+USE_FUSED_CELL = True  # one autograd node for the edge-level chain of a cell (fused_cell.py) when the genotype allows
 
 
 class OpModule(nn.Module):
@@ -90,11 +93,33 @@ class Cell(nn.Module):
     def forward_fused(self, g, ent, rel):
         """Same result as forward(g, ent[src_final], rel[et_final]) without materialising either."""
         first = self._ops[0][0][0]
+        plan = fused_cell.plan_for(self) if USE_FUSED_CELL else None
+        if plan is not None:
+            return self._forward_plan(g, ent, rel, plan)
         if not hasattr(first.op, 'comp') or self.uses_state0():
             src = ent[g.src_final.long()]
             return self.forward(g, src, rel[g.et_final.long()])
         zero_out = first.forward_gathered(g, ent, rel)
         return self._rest(g, [None, zero_out], zero_out)
+
+    def _forward_plan(self, g, ent, rel, plan):
+        """Edge-level chain in one fused autograd node; node-level ops through their modules."""
+        _, gates, aggs = plan
+        agg_out = fused_cell.run(self, g, ent, rel, plan)
+        agg_mod = {node: om for node, om, _ in aggs}
+        edge_nodes = {1} | {node for node, _, _ in gates}
+        states = {}
+        for n in range(1, self._nb_nodes):
+            node = n + 1
+            if node in edge_nodes:
+                continue
+            if node in agg_out:
+                states[node] = agg_mod[node]._post(agg_out[node])
+                continue
+            hs = [self._ops[n][i][0](g, states[i], None) for i in range(n + 1) if len(self._ops[n][i]) > 0]
+            states[node] = hs[0] if len(hs) == 1 else sum(hs)
+        h = self.concat(torch.cat([states[idx] for idx in self._concat_node], dim=1))
+        return K.bn_act(h, self.batchnorm_h, relu=True)
 
 
 class Network(nn.Module):

@@ -33,7 +33,16 @@ def _build(dev, genos, N, R, D, D0):
     return Network(dev, genos, N, R, D, D0, 2 * R + 1, nn.BCELoss(), 0.0, _args(D)).to(dev)
 
 
-def test_network_lp_golden(golden_dir):
+@pytest.fixture(params=[True, False], ids=["fused", "modular"])
+def fused(request):
+    from mr_gnas_b200 import model_lp
+    old = model_lp.USE_FUSED_CELL
+    model_lp.USE_FUSED_CELL = request.param
+    yield request.param
+    model_lp.USE_FUSED_CELL = old
+
+
+def test_network_lp_golden(golden_dir, fused):
     dev = torch.device("cuda:0")
     G = torch.load(os.path.join(golden_dir, "network_lp.pt"), weights_only=False)
     gd, d = G["graph"], G["dims"]
@@ -82,15 +91,21 @@ def test_network_lp_golden(golden_dir):
     assert _err(pe, G["pred_eval"]) <= 1e-5
 
 
-@pytest.mark.parametrize("D", [64, 200])
-def test_network_lp_oracle_seeded(D):
+OTHER = ("[Genotype(alpha_cell=[('pre_mult', 1, 0), ('f_sparse_comp', 2, 1), ('a_sum', 3, 2), ('a_max', 4, 1), "
+         "('f_sparse_comp', 5, 2), ('a_max', 6, 5), ('f_sparse_last', 7, 3), ('f_dense_last', 8, 4)], "
+         "concat_node=[3, 4, 6, 7, 8], score_func='sf_DisMult')]")
+
+
+@pytest.mark.parametrize("D,geno", [(64, README), (200, README), (64, OTHER), (128, OTHER)], ids=["readme64", "readme200", "other64", "other128"])
+def test_network_lp_oracle_seeded(D, geno, fused):
+    README = geno  # noqa: F841 (shadows the module constant on purpose)
     dev = torch.device("cuda:0")
     from mr_gnas_b200.graph import MRGraph
     from mr_gnas_b200.utils import weights_init
     N, R, T, D0, B = 2500, 12, 15000, 48, 32
     trip = O.synth_kg(N, R, T, seed=21)
     graph = O.build_graph(N, trip, R)
-    genos = eval(README)
+    genos = eval(geno)
     torch.manual_seed(3)
     model = _build('cpu', genos, N, R, D, D0)
     model.apply(weights_init)
