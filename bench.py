@@ -60,8 +60,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (samples are filtered by their
+    timestamps to the [t0, t1] window the caller reports)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -70,13 +71,15 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -85,16 +88,24 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, sm_all = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk = float(r[1])
+                sm_all.append(clk)
+                if t0 is not None and not (t0 - 0.02 <= ts <= t1 + 0.02):
+                    continue
+                sm.append(clk)
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[4:8]):
                     if v.strip().lower() == "active":
                         reasons.add(nm)
             except Exception:
                 pass
+        if not sm and sm_all:   # clock-domain skew between nvidia-smi's timestamps and time.time(): keep the tail
+            sm = sm_all[-max(1, len(sm_all) // 3):]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -177,7 +188,7 @@ def algo_bytes(key, M, E, N, D):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1_fb15k237")
@@ -264,20 +275,29 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, sample_clocks=False):
-        barrier()
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:                      # let nvidia-smi start up while the GPU stays under load
+            t_end = time.time() + 0.4
+            j = 0
+            while time.time() < t_end:
+                fn(j)
+                j += 1
+                torch.cuda.synchronize()
+        barrier()
+        t0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             out = fn(i)
         e1.record()
         barrier()
+        t1 = time.time()
         ms = e0.elapsed_time(e1) / steps
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, (sampler.stop() if sampler else None), out
+        return ms, (sampler.stop(t0, t1) if sampler else None), out
 
     for i in range(args.warmup):
         step_resident(i)
@@ -299,10 +319,10 @@ def main():
         for i in range(3):
             step_resident(i)
         prof = _lib.stop_profile()
-        tot = sum(t for _, t in prof.values()) / 3
+        tot = sum(v[1] for v in prof.values()) / 3
         hbm, how = peaks()
-        for key, (cnt, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-            ab = algo_bytes(key, M, E, N, D)
+        for key, (cnt, t, nb) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            ab = (nb / cnt) if nb else algo_bytes(key, M, E, N, D)
             avg_ms = t / cnt
             prof_rows.append({"call": key, "launches_per_step": cnt / 3, "avg_ms": avg_ms, "ms_per_step": t / 3,
                               "share_of_lib_time": t / 3 / tot if tot else None,

@@ -138,7 +138,9 @@ def act(data, scale=None, shift=None, relu=False):
                   shift.data_ptr() if shift is not None else None, 1 if relu else 0)
 
 
-def call(name, *args):
+def call(name, *args, nbytes=None):
+    """Enqueue one C-ABI call.  `nbytes` (optional) = compulsory HBM bytes of this call (inputs read once +
+    outputs written once); only used by the profiler for roofline accounting."""
     global launch_count
     lib = load()
     if _profile is not None:
@@ -150,7 +152,7 @@ def call(name, *args):
     if _profile is not None:
         e1.record()
         ints = tuple(a for a in args if type(a) is int)[:3]
-        _profile.append((name + str(ints), e0, e1))
+        _profile.append((name + str(ints), e0, e1, nbytes))
     launch_count += KERNELS_PER_CALL.get(name, 1)
     return rc
 
@@ -161,12 +163,12 @@ def start_profile():
 
 
 def stop_profile():
-    """-> {call name: (count, total ms)} measured with CUDA events around each C-ABI call."""
+    """-> {call name: (count, total ms, total compulsory bytes or None)} from CUDA events around each call."""
     global _profile
     torch.cuda.synchronize()
     out = {}
-    for name, e0, e1 in _profile or []:
-        c, t = out.get(name, (0, 0.0))
-        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    for name, e0, e1, nb in _profile or []:
+        c, t, b = out.get(name, (0, 0.0, 0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1), (b + nb) if (nb is not None and b is not None) else None)
     _profile = None
     return out

@@ -13,9 +13,9 @@ namespace mrg {
 constexpr int kThreads = 256;            // 8 warps per CTA
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kNumSMs = 148;             // B200
-constexpr int kStatsBlocksPerSM = 4;
+constexpr int kStatsBlocksPerSM = 6;
 constexpr int kMaxParts = kNumSMs * kStatsBlocksPerSM;  // 592 persistent CTAs
-constexpr int kFoldRows = 16;            // fold fp32 partial sums into double every 16 rows
+constexpr int kFoldRows = 32;            // fold fp32 partial sums into (shared-memory) doubles every 32 rows
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
@@ -111,20 +111,29 @@ struct ActRegs {
   }
 };
 
-// Column (sum, sum of squares) accumulation: fp32 per lane, folded into double every
-// kFoldRows rows, reduced over the CTA's warps in a fixed order, written as this CTA's partial.
+// Column (sum, sum of squares) accumulation: fp32 per lane, folded every kFoldRows rows into
+// this warp's DOUBLE accumulators in shared memory (lane-owned columns: no conflicts, no atomics,
+// and no double registers in the streaming loop), reduced over the CTA's warps in a fixed order
+// and written as this CTA's partial.  smem need: stats_smem_doubles(D) doubles.
+__host__ __device__ inline int stats_smem_doubles(int D) { return kWarpsPerBlock * 2 * D; }
+
 template <int NV>
 struct ColStats {
   float4 fs[NV], fq[NV];
-  double ds[NV][4], dq[NV][4];
   int pending;
-  __device__ __forceinline__ void init() {
+  double* ws;  // this warp's [2][D] doubles
+  __device__ __forceinline__ void init(double* smem, int D, int D4) {
     pending = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ws = smem + (size_t)warp * 2 * D;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       fs[v] = fq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c4 = lane + 32 * v;
+      if (c4 < D4) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) ds[v][k] = dq[v][k] = 0.0;
+        for (int k = 0; k < 4; ++k) ws[4 * c4 + k] = ws[D + 4 * c4 + k] = 0.0;
+      }
     }
   }
   __device__ __forceinline__ void add(float4 a, float4 b, int v) {  // sum += a ; sq += b
@@ -134,41 +143,67 @@ struct ColStats {
   __device__ __forceinline__ void add_sq(float4 a, int v) {
     add(a, make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w), v);
   }
-  __device__ __forceinline__ void fold() {
+  __device__ __forceinline__ void fold(int D, int D4) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      ds[v][0] += fs[v].x; ds[v][1] += fs[v].y; ds[v][2] += fs[v].z; ds[v][3] += fs[v].w;
-      dq[v][0] += fq[v].x; dq[v][1] += fq[v].y; dq[v][2] += fq[v].z; dq[v][3] += fq[v].w;
+      const int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        double* s = ws + 4 * c4;
+        double* q = ws + D + 4 * c4;
+        s[0] += fs[v].x; s[1] += fs[v].y; s[2] += fs[v].z; s[3] += fs[v].w;
+        q[0] += fq[v].x; q[1] += fq[v].y; q[2] += fq[v].z; q[3] += fq[v].w;
+      }
       fs[v] = fq[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     pending = 0;
   }
-  __device__ __forceinline__ void row_done() {
-    if (++pending == kFoldRows) fold();
+  __device__ __forceinline__ void row_done(int D, int D4) {
+    if (++pending == kFoldRows) fold(D, D4);
   }
-  // part: this CTA's [2][D] doubles.  smem: kWarpsPerBlock*D doubles of scratch.
-  __device__ __forceinline__ void write_block(double* part, int D, int D4, double* smem) {
-    fold();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // part: this CTA's [2][D] doubles; smem: the base passed to init()
+  __device__ __forceinline__ void write_block(double* part, double* smem, int D, int D4) {
+    fold(D, D4);
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+      double t = 0.0;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      __syncthreads();
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        int c4 = lane + 32 * v;
-        if (c4 < D4) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) smem[warp * D + 4 * c4 + k] = pass == 0 ? ds[v][k] : dq[v][k];
-        }
-      }
-      __syncthreads();
-      for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; ++w) t += smem[w * D + c];
-        part[pass * D + c] = t;
-      }
+      for (int w = 0; w < kWarpsPerBlock; ++w) t += smem[(size_t)w * 2 * D + c];
+      part[c] = t;
     }
+  }
+};
+
+// Per-column constants (gate vectors, BN affine of an mrg_act) staged once per CTA in shared memory and
+// read back with conflict-free 128-bit loads, instead of pinning 8*NV registers each for the whole kernel.
+struct ActSmem {
+  const float* sc;  // smem, or nullptr if identity
+  const float* sh;
+  bool relu;
+  __device__ __forceinline__ void init(const mrg_act& a, float* smem_sc, float* smem_sh, int D) {
+    relu = a.relu != 0;
+    if (a.scale) {
+      for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        smem_sc[c] = a.scale[c];
+        smem_sh[c] = a.shift[c];
+      }
+      sc = smem_sc;
+      sh = smem_sh;
+    } else {
+      sc = sh = nullptr;
+    }
+  }
+  __device__ __forceinline__ float4 apply(float4 x, int c4) const {
+    if (sc) {
+      const float4 a = *reinterpret_cast<const float4*>(sc + 4 * c4);
+      const float4 b = *reinterpret_cast<const float4*>(sh + 4 * c4);
+      x.x = fmaf(a.x, x.x, b.x); x.y = fmaf(a.y, x.y, b.y); x.z = fmaf(a.z, x.z, b.z); x.w = fmaf(a.w, x.w, b.w);
+    }
+    if (relu) {
+      x.x = x.x > 0.f ? x.x : 0.f; x.y = x.y > 0.f ? x.y : 0.f;
+      x.z = x.z > 0.f ? x.z : 0.f; x.w = x.w > 0.f ? x.w : 0.f;
+    }
+    return x;
   }
 };
 

@@ -16,11 +16,13 @@
 // lo = rna_tf32(x - hi)) and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM
 // ("3xTF32"), giving ~2^-21 relative operand error, i.e. SGEMM-class results.
 //
-// Pipeline per CTA (persistent over tiles, one CTA per SM):
-//   warps 0-3  producers : X rows gathered by CSR edge id -> (BN affine + ReLU) -> hi/lo split ->
-//                          128B-swizzled K-major smem; W hi/lo K-chunk via cp.async
-//   warp  8    MMA issuer: one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
-//   warps 4-7  epilogue  : tcgen05.ld -> +bias, ReLU -> segmented max scan -> atomicMax
+// Pipeline per CTA (persistent over tiles, one CTA per SM, 14 warps):
+//   warps 0-7   X producers: 2 threads per tile row gather X by CSR edge id with a 3-chunk-deep register
+//                            prefetch ring -> (BN affine + ReLU) -> hi/lo split -> 128B-swizzled K-major smem
+//   warp  13    W loader   : one thread, cp.async.bulk (UBLKCP) of the pre-swizzled hi/lo K-chunk image,
+//                            completion by mbarrier expect_tx
+//   warp  12    MMA issuer : one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
+//   warps 8-11  epilogue   : tcgen05.ld -> +bias, ReLU -> segmented max scan -> atomicMax
 #include "common.cuh"
 
 namespace mrg {
@@ -29,9 +31,13 @@ namespace tc {
 constexpr int TILE_E = 128;   // edges per tile  (UMMA N)
 constexpr int KCH = 32;       // fp32 elements per K chunk = one 128-byte swizzled row
 constexpr int STAGES = 2;
-constexpr int PROD_THREADS = 128;
+constexpr int PROD_THREADS = 256;
 constexpr int EPI_THREADS = 128;
-constexpr int THREADS = PROD_THREADS + EPI_THREADS + 32;
+constexpr int THREADS = PROD_THREADS + EPI_THREADS + 64;
+constexpr int PD = 3;         // X prefetch depth (K chunks in flight per producer thread)
+constexpr int EPI_WARP0 = PROD_THREADS / 32;   // 8  (8 % 4 == 0 -> TMEM lane quadrants 0..3)
+constexpr int MMA_WARP = EPI_WARP0 + 4;        // 12
+constexpr int WLD_WARP = MMA_WARP + 1;         // 13
 constexpr uint32_t TILE_BYTES = 128 * 128;  // 128 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -42,8 +48,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_cpasync_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -111,16 +122,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// W [Dout, Din] fp32 -> hi/lo TF32 pair, zero padded to [MH*128, Kp]:  out[0]=hi, out[1]=lo
-__global__ void tf32_split_kernel(const float* __restrict__ W, int Dout, int Din, int rows_pad, int Kp,
-                                  float* __restrict__ out) {
-  const int64_t n = (int64_t)rows_pad * Kp;
+// W [Dout, Din] fp32 -> hi/lo TF32 pair in the exact shared-memory image of the pipeline: per K chunk
+// [hi half0..MH-1 | lo half0..MH-1], each half a 128-row x 128-byte tile, K-major, 128B-swizzled
+// (16-byte unit j of row r stored at unit j ^ (r & 7)), zero padded.  One bulk copy per chunk then lands it.
+__global__ void tf32_split_kernel(const float* __restrict__ W, int Dout, int Din, int MH, int nchunks,
+                                  float* __restrict__ img) {
+  const int64_t per_chunk = (int64_t)2 * MH * 128 * KCH;  // floats
+  const int64_t n = (int64_t)nchunks * MH * 128 * KCH;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / Kp), k = (int)(i % Kp);
-    const float x = (r < Dout && k < Din) ? W[(size_t)r * Din + k] : 0.f;
+    const int kk = (int)(i % KCH);
+    const int row = (int)((i / KCH) % (MH * 128));
+    const int c = (int)(i / ((int64_t)KCH * MH * 128));
+    const int k = c * KCH + kk;
+    const float x = (row < Dout && k < Din) ? W[(size_t)row * Din + k] : 0.f;
     const float hi = tf32_rna(x);
-    out[i] = hi;
-    out[n + i] = tf32_rna(x - hi);
+    const int h = row >> 7, rr = row & 127, j = kk >> 2, e = kk & 3;
+    const int64_t off = (int64_t)(rr >> 3) * 256 + (rr & 7) * 32 + ((j ^ (rr & 7)) << 2) + e;  // floats within a tile
+    img[c * per_chunk + (int64_t)h * 4096 + off] = hi;
+    img[c * per_chunk + (int64_t)(MH + h) * 4096 + off] = tf32_rna(x - hi);
   }
 }
 
@@ -128,7 +147,7 @@ struct AmaxParams {
   mrg_act x;                 // [rows, D] message source rows, read through act
   const int32_t* csr_eid;    // [E] row id per CSR position
   const int32_t* dst;        // [E] destination per edge id
-  const float* wsplit;       // [2][MH*128][Kp]
+  const float* wimg;         // [nchunks][2*MH tiles of 128x128B] pre-swizzled hi/lo image of W
   const float* bias;         // [D] or null
   unsigned long long* packed;  // [N, D] zero-initialised
   int64_t E;
@@ -142,9 +161,10 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   constexpr uint32_t STAGE_BYTES = (2 * MH + 2) * TILE_BYTES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* tail = smem + STAGES * STAGE_BYTES;
-  uint64_t* full_bar = (uint64_t*)tail;               // [STAGES]
-  uint64_t* empty_bar = full_bar + STAGES;            // [STAGES]
-  uint64_t* tfull_bar = empty_bar + STAGES;           // [2]
+  uint64_t* full_bar = (uint64_t*)tail;               // [STAGES]  X tile written (256 producer arrivals)
+  uint64_t* empty_bar = full_bar + STAGES;            // [STAGES]  MMAs that read the stage retired
+  uint64_t* wfull_bar = empty_bar + STAGES;           // [STAGES]  W chunk landed (expect_tx)
+  uint64_t* tfull_bar = wfull_bar + STAGES;           // [2]
   uint64_t* tempty_bar = tfull_bar + 2;               // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);  // [1] (+pad)
   float* s_scale = (float*)(tmem_slot + 4);           // [256]
@@ -166,6 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], PROD_THREADS);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&wfull_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -173,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TMEM_COLS)
                  : "memory");
@@ -184,81 +205,96 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ================================ PRODUCERS ================================
-    const int r = threadIdx.x;  // tile row owned by this thread
+  const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_tiles * p.nchunks;   // K chunks this CTA streams, in order
+  if (warp < EPI_WARP0) {
+    // ================================ X PRODUCERS ================================
+    const int r = (warp << 4) | (lane & 15);   // tile row
+    const int half = lane >> 4;                // which 16-byte units of a 128-byte chunk: 2j + half
     const bool affine = p.x.scale != nullptr, relu = p.x.relu != 0;
-    uint32_t it = 0;            // global chunk counter -> stage / phase
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int64_t pos = (int64_t)tile * TILE_E + r;
-      const bool valid = pos < p.E;
-      const float* xrow = valid ? p.x.data + (size_t)__ldg(p.csr_eid + pos) * D : nullptr;
-      float4 nxt[8];
-      auto load_chunk = [&](int c) {
+    const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+    const float* xrow = nullptr;   // load cursor's row
+    float4 buf[PD][4];
+    int lq = 0;
+    auto load = [&](float4(&b)[4], int q) {
+      const int tl = q / p.nchunks, c = q - tl * p.nchunks;
+      if (c == 0) {
+        const int64_t pos = (int64_t)(blockIdx.x + tl * gridDim.x) * TILE_E + r;
+        xrow = pos < p.E ? p.x.data + (size_t)__ldg(p.csr_eid + pos) * D : nullptr;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = c * KCH + 4 * j;
-          nxt[j] = (valid && col < D) ? ld_stream4(xrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      load_chunk(0);
-      for (int c = 0; c < p.nchunks; ++c, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        // W hi/lo chunk -> smem (async): 2*MH*128 rows x 8 x 16B, swizzled
-        {
-          const int rows_pad = MH * 128;
-          const int total = 2 * rows_pad * 8;
-          const uint32_t wbase = smem_u32(st);
-          for (int q = threadIdx.x; q < total; q += PROD_THREADS) {
-            const int j = q & 7, row = (q >> 3) % rows_pad, hl = (q >> 3) / rows_pad;
-            const float* src = p.wsplit + ((size_t)hl * rows_pad + row) * p.Kp + c * KCH + 4 * j;
-            const uint32_t dst = wbase + (uint32_t)hl * MH * TILE_BYTES + (uint32_t)(row >> 3) * 1024 +
-                                 (uint32_t)(row & 7) * 128 + (uint32_t)((j ^ (row & 7)) << 4);
-            cp_async16(dst, src);
+      for (int j = 0; j < 4; ++j) {
+        const int col = c * KCH + 4 * (2 * j + half);
+        b[j] = (xrow && col < D) ? ld_stream4(xrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto consume = [&](float4(&b)[4], int q) {
+      const int tl = q / p.nchunks, c = q - tl * p.nchunks;
+      const bool valid = (int64_t)(blockIdx.x + tl * gridDim.x) * TILE_E + r < p.E;
+      const int s = q % STAGES;
+      const uint32_t ph = (q / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* xhi = smem + (size_t)s * STAGE_BYTES + 2 * MH * TILE_BYTES;
+      uint8_t* xlo = xhi + TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = 2 * j + half;
+        const int col = c * KCH + 4 * u;
+        float4 v = b[j];
+        if (valid && col < D) {
+          if (affine) {
+            v.x = fmaf(s_scale[col], v.x, s_shift[col]);
+            v.y = fmaf(s_scale[col + 1], v.y, s_shift[col + 1]);
+            v.z = fmaf(s_scale[col + 2], v.z, s_shift[col + 2]);
+            v.w = fmaf(s_scale[col + 3], v.w, s_shift[col + 3]);
           }
-          mbar_cpasync_arrive(&full_bar[s]);
-        }
-        // X chunk: registers -> affine/ReLU -> hi/lo -> swizzled smem
-        float4 cur[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-        if (c + 1 < p.nchunks) load_chunk(c + 1);
-        uint8_t* xhi = st + 2 * MH * TILE_BYTES;
-        uint8_t* xlo = xhi + TILE_BYTES;
-        const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = c * KCH + 4 * j;
-          float4 v = cur[j];
-          if (valid && col < D) {
-            if (affine) {
-              v.x = fmaf(s_scale[col], v.x, s_shift[col]);
-              v.y = fmaf(s_scale[col + 1], v.y, s_shift[col + 1]);
-              v.z = fmaf(s_scale[col + 2], v.z, s_shift[col + 2]);
-              v.w = fmaf(s_scale[col + 3], v.w, s_shift[col + 3]);
-            }
-            if (relu) {
-              v.x = v.x > 0.f ? v.x : 0.f;
-              v.y = v.y > 0.f ? v.y : 0.f;
-              v.z = v.z > 0.f ? v.z : 0.f;
-              v.w = v.w > 0.f ? v.w : 0.f;
-            }
+          if (relu) {
+            v.x = v.x > 0.f ? v.x : 0.f;
+            v.y = v.y > 0.f ? v.y : 0.f;
+            v.z = v.z > 0.f ? v.z : 0.f;
+            v.w = v.w > 0.f ? v.w : 0.f;
           }
-          float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-          float4 lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z),
-                                  tf32_rna(v.w - hi.w));
-          const uint32_t off = roff + (uint32_t)((j ^ (r & 7)) << 4);
-          *reinterpret_cast<float4*>(xhi + off) = hi;
-          *reinterpret_cast<float4*>(xlo + off) = lo;
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);  // exact; MMA truncates to tf32
+        const uint32_t off = roff + (uint32_t)((u ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(xhi + off) = hi;
+        *reinterpret_cast<float4*>(xlo + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full_bar[s]);
+    };
+#pragma unroll
+    for (int u = 0; u < PD; ++u) {
+      if (lq < total) load(buf[u], lq);
+      ++lq;
+    }
+    for (int q = 0; q < total; q += PD) {
+#pragma unroll
+      for (int u = 0; u < PD; ++u) {
+        if (q + u < total) {
+          consume(buf[u], q + u);
+          if (lq < total) load(buf[u], lq);
+          ++lq;
+        }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == WLD_WARP) {
+    // ================================ W LOADER ================================
+    if (lane == 0) {
+      const uint32_t wbytes = 2 * MH * TILE_BYTES;
+      for (int q = 0; q < total; ++q) {
+        const int s = q % STAGES;
+        const uint32_t ph = (q / STAGES) & 1;
+        const int c = q % p.nchunks;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&wfull_bar[s], wbytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)c * wbytes;
+        const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        for (uint32_t o = 0; o < wbytes; o += TILE_BYTES) bulk_g2s(dst + o, src + o, TILE_BYTES, &wfull_bar[s]);
+      }
+    }
+  } else if (warp == MMA_WARP) {
     // ================================ MMA ISSUER ================================
     const uint32_t idesc = umma_idesc(128, TILE_E);
     uint32_t it = 0, tcount = 0;
@@ -270,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
-        fence_proxy_async();
+        mbar_wait(&wfull_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sbase = smem_u32(smem + (size_t)s * STAGE_BYTES);
@@ -282,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
             for (int k = 0; k < ksteps; ++k) {
               const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the swizzled 128B row
               const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-              umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);   // small terms first
+              umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);  // small terms first
               umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
               umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
             }
@@ -296,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   } else {
     // ================================ EPILOGUE ================================
     const int et = threadIdx.x - PROD_THREADS;       // 0..127 == TMEM lane
-    const int quad = warp & 3;                       // warps 4..7 -> lane quadrants 0..3
+    const int quad = warp & 3;                       // warps 8..11 -> lane quadrants 0..3
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1;
@@ -364,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
@@ -401,7 +437,7 @@ using namespace mrg;
 extern "C" size_t mrg_amax_tc_workspace_bytes(int64_t N, int32_t D) {
   const int MH = D <= 128 ? 1 : 2;
   const int Kp = (D + tc::KCH - 1) / tc::KCH * tc::KCH;
-  return (size_t)N * D * sizeof(unsigned long long) + (size_t)2 * MH * 128 * Kp * sizeof(float) + 512;
+  return (size_t)N * D * sizeof(unsigned long long) + (size_t)2 * MH * 128 * Kp * sizeof(float) + 1024;
 }
 
 extern "C" int mrg_amax_tc_supported(int32_t D) { return (D % 8 == 0 && D >= 8 && D <= 256) ? 1 : 0; }
@@ -424,12 +460,12 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   float* wsplit = (float*)((char*)workspace + packed_bytes);
   cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)N * D * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd memset");
-  tc::tf32_split_kernel<<<64, 256, 0, st>>>(W, D, D, MH * 128, Kp, wsplit);
+  tc::tf32_split_kernel<<<64, 256, 0, st>>>(W, D, D, MH, Kp / tc::KCH, wsplit);
   tc::AmaxParams p;
   p.x = x;
   p.csr_eid = csr_eid;
   p.dst = dst;
-  p.wsplit = wsplit;
+  p.wimg = wsplit;
   p.bias = bias;
   p.packed = packed;
   p.E = E;

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const float* __re
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   ColStats<NV> cs;
-  if (STATS) cs.init();
+  if (STATS) cs.init(smem_d, D, D4);
   for (int64_t row = warp0; row < rows; row += nwarps) {
     const int64_t hi = h_idx ? (int64_t)__ldg(h_idx + row) : row;
     const int64_t ri = r_idx ? (int64_t)__ldg(r_idx + row) : row;
@@ -62,9 +62,9 @@ __global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const float* __re
         if (STATS) cs.add_sq(o, v);
       }
     }
-    if (STATS) cs.row_done();
+    if (STATS) cs.row_done(D, D4);
   }
-  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, smem_d, D, D4);
 }
 
 template <int NV, int COMP>
@@ -113,16 +113,16 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(mrg_act x, int64_t r
   ActRegs<NV> ax;
   ax.init(x, lane, D4);
   ColStats<NV> cs;
-  cs.init();
+  cs.init(smem_d, D, D4);
   for (int64_t row = warp0; row < rows; row += nwarps) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       int c4 = lane + 32 * v;
       if (c4 < D4) cs.add_sq(ax.apply(ld_stream4(x.data + (size_t)row * D + 4 * c4), v), v);
     }
-    cs.row_done();
+    cs.row_done(D, D4);
   }
-  cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+  cs.write_block(stats + (size_t)blockIdx.x * 2 * D, smem_d, D, D4);
 }
 
 
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
   ActRegs<NV> ay;
   ay.init(y, lane, D4);
   ColStats<NV> cs;
-  cs.init();
+  cs.init(smem_d, D, D4);
   for (int64_t row = warp0; row < rows; row += nwarps) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
         cs.add(g, make_float4(g.x * yv.x, g.y * yv.y, g.z * yv.z, g.w * yv.w), v);
       }
     }
-    cs.row_done();
+    cs.row_done(D, D4);
   }
-  cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+  cs.write_block(stats + (size_t)blockIdx.x * 2 * D, smem_d, D, D4);
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int nparts, int64_t rows, int D,
@@ -315,26 +315,24 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_fwd_kernel(mrg_act x, mr
                                                                    float* __restrict__ gate,
                                                                    double* __restrict__ stats) {
   extern __shared__ double smem_d[];
+  float* sf = reinterpret_cast<float*>(smem_d + stats_smem_doubles(D));  // w1 | w2 | xsc | xsh | isc | ish
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  ActRegs<NV> ax, ai;
-  ax.init(x, lane, D4);
-  if (HAS_IN) ai.init(xin, lane, D4);
-  float4 w1[NV], w2[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    int c4 = lane + 32 * v;
-    w1[v] = w2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c4 < D4) {
-      w1[v] = ldg4(v1 + 4 * c4);
-      if (HAS_IN) w2[v] = ldg4(v2 + 4 * c4);
-    }
+  float* w1 = sf;
+  float* w2 = sf + D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    w1[c] = v1[c];
+    w2[c] = HAS_IN ? v2[c] : 0.f;
   }
+  ActSmem ax, ai;
+  ax.init(x, sf + 2 * D, sf + 3 * D, D);
+  if (HAS_IN) ai.init(xin, sf + 4 * D, sf + 5 * D, D);
   const float c = __ldg(cptr);
   ColStats<NV> cs;
-  if (STATS) cs.init();
+  if (STATS) cs.init(smem_d, D, D4);
+  __syncthreads();
   for (int64_t row = warp0; row < rows; row += nwarps) {
     float4 xv[NV];
     float dot = 0.f;
@@ -344,12 +342,16 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_fwd_kernel(mrg_act x, mr
       xv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c4 < D4) {
         const size_t off = (size_t)row * D + 4 * c4;
-        float4 raw = ld_stream4(x.data + off);
-        xv[v] = ax.apply(raw, v);
-        dot += xv[v].x * w1[v].x + xv[v].y * w1[v].y + xv[v].z * w1[v].z + xv[v].w * w1[v].w;
+        const float4 raw = ld_stream4(x.data + off);
+        float4 rin;
+        if (HAS_IN && !SAME) rin = ld_stream4(xin.data + off);
+        xv[v] = ax.apply(raw, c4);
+        const float4 a = *reinterpret_cast<const float4*>(w1 + 4 * c4);
+        dot += xv[v].x * a.x + xv[v].y * a.y + xv[v].z * a.z + xv[v].w * a.w;
         if (HAS_IN) {
-          float4 iv = SAME ? ai.apply(raw, v) : ai.apply(ld_stream4(xin.data + off), v);
-          dot += iv.x * w2[v].x + iv.y * w2[v].y + iv.z * w2[v].z + iv.w * w2[v].w;
+          const float4 iv = ai.apply(SAME ? raw : rin, c4);
+          const float4 b = *reinterpret_cast<const float4*>(w2 + 4 * c4);
+          dot += iv.x * b.x + iv.y * b.y + iv.z * b.z + iv.w * b.w;
         }
       }
     }
@@ -366,9 +368,9 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_fwd_kernel(mrg_act x, mr
         if (STATS) cs.add_sq(o, v);
       }
     }
-    if (STATS) cs.row_done();
+    if (STATS) cs.row_done(D, D4);
   }
-  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, smem_d, D, D4);
 }
 
 // dparam partial per CTA: [dv1[D] | dv2[D] | dc] doubles
@@ -381,29 +383,27 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
                                                                    float base_scale, float* dx, float* dxin,
                                                                    int accumulate, double* __restrict__ dparam) {
   extern __shared__ double smem_d[];
+  float* sf = reinterpret_cast<float*>(smem_d + stats_smem_doubles(D));
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int D4 = D >> 2;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  ActRegs<NV> ax, ai;
-  ax.init(x, lane, D4);
-  if (HAS_IN) ai.init(xin, lane, D4);
-  float4 w1[NV], w2[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    int c4 = lane + 32 * v;
-    w1[v] = w2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c4 < D4) {
-      w1[v] = ldg4(v1 + 4 * c4);
-      if (HAS_IN) w2[v] = ldg4(v2 + 4 * c4);
-    }
+  float* w1 = sf;
+  float* w2 = sf + D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    w1[c] = v1[c];
+    w2[c] = HAS_IN ? v2[c] : 0.f;
   }
+  ActSmem ax, ai;
+  ax.init(x, sf + 2 * D, sf + 3 * D, D);
+  if (HAS_IN) ai.init(xin, sf + 4 * D, sf + 5 * D, D);
   // ColStats reused: "sum" slot accumulates dt*x (dv1), "sq" slot accumulates dt*xin (dv2)
   ColStats<NV> cs;
-  cs.init();
+  cs.init(smem_d, D, D4);
   float dc_f = 0.f;
   double dc_d = 0.0;
+  __syncthreads();
   for (int64_t row = warp0; row < rows; row += nwarps) {
     float4 xv[NV], iv[NV], gv[NV];
     float dot = 0.f;
@@ -413,10 +413,12 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
       xv[v] = iv[v] = gv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c4 < D4) {
         const size_t off = (size_t)row * D + 4 * c4;
-        float4 raw = ld_stream4(x.data + off);
-        xv[v] = ax.apply(raw, v);
-        if (HAS_IN) iv[v] = SAME ? ai.apply(raw, v) : ai.apply(ld_stream4(xin.data + off), v);
+        const float4 raw = ld_stream4(x.data + off);
+        float4 rin;
+        if (HAS_IN && !SAME) rin = ld_stream4(xin.data + off);
         gv[v] = ld_stream4(dy + off);
+        xv[v] = ax.apply(raw, c4);
+        if (HAS_IN) iv[v] = ai.apply(SAME ? raw : rin, c4);
         dot += gv[v].x * xv[v].x + gv[v].y * xv[v].y + gv[v].z * xv[v].z + gv[v].w * xv[v].w;
       }
     }
@@ -431,12 +433,14 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
       int c4 = lane + 32 * v;
       if (c4 < D4) {
         const size_t off = (size_t)row * D + 4 * c4;
+        const float4 a = *reinterpret_cast<const float4*>(w1 + 4 * c4);
+        const float4 b = *reinterpret_cast<const float4*>(w2 + 4 * c4);
         float4 o;
-        o.x = fmaf(sg, gv[v].x, dt * w1[v].x);
-        o.y = fmaf(sg, gv[v].y, dt * w1[v].y);
-        o.z = fmaf(sg, gv[v].z, dt * w1[v].z);
-        o.w = fmaf(sg, gv[v].w, dt * w1[v].w);
-        float4 oi = make_float4(dt * w2[v].x, dt * w2[v].y, dt * w2[v].z, dt * w2[v].w);
+        o.x = fmaf(sg, gv[v].x, dt * a.x);
+        o.y = fmaf(sg, gv[v].y, dt * a.y);
+        o.z = fmaf(sg, gv[v].z, dt * a.z);
+        o.w = fmaf(sg, gv[v].w, dt * a.w);
+        float4 oi = make_float4(dt * b.x, dt * b.y, dt * b.z, dt * b.w);
         if (HAS_IN && SAME) {  // dx and dxin are the same buffer: one combined write
           o.x += oi.x; o.y += oi.y; o.z += oi.z; o.w += oi.w;
         }
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
                make_float4(dt * iv[v].x, dt * iv[v].y, dt * iv[v].z, dt * iv[v].w), v);
       }
     }
-    cs.row_done();
+    cs.row_done(D, D4);
     if (cs.pending == 0) {
       dc_d += dc_f;
       dc_f = 0.f;
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_bwd_kernel(const float* 
   }
   dc_d += dc_f;
   double* part = dparam + (size_t)blockIdx.x * (2 * D + 1);
-  cs.write_block(part, D, D4, smem_d);
+  cs.write_block(part, smem_d, D, D4);
   __syncthreads();
   if (lane == 0) smem_d[warp] = dc_d;
   __syncthreads();
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kThreads) dense_gate_fwd_kernel(const float* _
   ActRegs<NV> ax;
   if (use_sigmoid) ax.init(x, lane, D4);
   ColStats<NV> cs;
-  if (STATS) cs.init();
+  if (STATS) cs.init(smem_d, D, D4);
   for (int64_t row = warp0; row < rows; row += nwarps) {
     const float sc = base_scale * (row_scale ? __ldg(row_scale + row) : 1.f);
 #pragma unroll
@@ -531,9 +535,9 @@ __global__ void __launch_bounds__(kThreads) dense_gate_fwd_kernel(const float* _
         if (STATS) cs.add_sq(o, v);
       }
     }
-    if (STATS) cs.row_done();
+    if (STATS) cs.row_done(D, D4);
   }
-  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, D, D4, smem_d);
+  if (STATS) cs.write_block(stats + (size_t)blockIdx.x * 2 * D, smem_d, D, D4);
 }
 
 template <int NV>
@@ -714,7 +718,13 @@ extern "C" const char* mrg_last_error(void) { return g_err; }
 extern "C" int32_t mrg_stats_nparts(int64_t rows) { return stats_grid(rows); }
 extern "C" int32_t mrg_stats_max_parts(void) { return kMaxParts; }
 
-static inline size_t stats_smem(int D) { return (size_t)kWarpsPerBlock * D * sizeof(double); }
+static inline size_t stats_smem(int D) { return (size_t)stats_smem_doubles(D) * sizeof(double); }
+static inline size_t gate_smem(int D) { return stats_smem(D) + 6 * (size_t)D * sizeof(float); }
+// kernels whose dynamic smem may exceed the 48 KB default (D > 256): opt in before launching
+#define MRG_SMEM_OPTIN(kernel, bytes)                                                                  \
+  do {                                                                                                 \
+    if ((bytes) > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+  } while (0)
 
 extern "C" int mrg_compose_fwd(const float* h, const int32_t* h_idx, const float* r, const int32_t* r_idx,
                                int64_t rows, int32_t D, int32_t comp, float* y, double* stats, void* stream) {
@@ -822,8 +832,8 @@ extern "C" int mrg_sparse_gate_fwd(mrg_act x, mrg_act xin, int64_t rows, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stats_grid(rows);
   const bool has_in = xin.data != nullptr, same = has_in && xin.data == x.data;
-#define L(HI, SM_, ST_) sparse_gate_fwd_kernel<NV, HI, SM_, ST_><<<grid, kThreads, ST_ ? stats_smem(D) : 0, st>>>( \
-      x, xin, rows, D, v1, v2, c, row_scale, base_scale, y, gate, stats)
+#define L(HI, SM_, ST_) do { MRG_SMEM_OPTIN((sparse_gate_fwd_kernel<NV, HI, SM_, ST_>), gate_smem(D)); sparse_gate_fwd_kernel<NV, HI, SM_, ST_><<<grid, kThreads, gate_smem(D), st>>>( \
+      x, xin, rows, D, v1, v2, c, row_scale, base_scale, y, gate, stats); } while (0)
   MRG_DISPATCH_NV(D, if (stats) { if (!has_in) L(false, false, true); else if (same) L(true, true, true); else L(true, false, true); }
                      else { if (!has_in) L(false, false, false); else if (same) L(true, true, false); else L(true, false, false); });
 #undef L
@@ -843,8 +853,8 @@ extern "C" int mrg_sparse_gate_bwd(const float* dy, mrg_act x, mrg_act xin, cons
   const int grid = stats_grid(rows);
   const bool has_in = xin.data != nullptr;
   const bool same = has_in && xin.data == x.data && dxin == dx;
-#define L(HI, SM_) sparse_gate_bwd_kernel<NV, HI, SM_><<<grid, kThreads, stats_smem(D), st>>>( \
-      dy, x, xin, gate, rows, D, v1, v2, row_scale, base_scale, dx, dxin, accumulate, dparam)
+#define L(HI, SM_) do { MRG_SMEM_OPTIN((sparse_gate_bwd_kernel<NV, HI, SM_>), gate_smem(D)); sparse_gate_bwd_kernel<NV, HI, SM_><<<grid, kThreads, gate_smem(D), st>>>( \
+      dy, x, xin, gate, rows, D, v1, v2, row_scale, base_scale, dx, dxin, accumulate, dparam); } while (0)
   MRG_DISPATCH_NV(D, if (!has_in) L(false, false); else if (same) L(true, true); else L(true, false));
 #undef L
   MRG_LAUNCH_CHECK("sparse_gate_bwd");

@@ -56,7 +56,7 @@ def seg_reduce_raw(seg, kind, m_act, D, out, arg=None, mul=None, mul_idx=None, a
     res = residual if residual is not None else act(None)
     call("mrg_seg_reduce_fwd", kind, m_act, ptr(seg.ptr), ptr(seg.idx), ptr(seg.chunk_first), ptr(seg.chunk_seg),
          seg.nseg, seg.max_chunks, D, ptr(mul), ptr(mul_idx), float(alpha), res, 1 if accumulate else 0, ptr(out),
-         ptr(arg), ptr(ws), ws.numel(), stream())
+         ptr(arg), ptr(ws), ws.numel(), stream(), nbytes=seg.total * (4 * D + 4) + seg.nseg * 4 * D)
     return out
 
 
@@ -382,7 +382,7 @@ def amax_backward(g, gout, arg, x_act, weight, rows, has_residual, need_dx=True,
     db = torch.empty(D, dtype=torch.float32, device=dev)
     call("mrg_amax_bwd", ptr(gout), ptr(arg), x_act, ptr(weight), ptr(g.csr.ptr), ptr(g.csr.idx),
          ptr(g.csr.chunk_first), ptr(g.csr.chunk_seg), g.N, E, g.csr.max_chunks, D, ptr(dx) if need_dx else None,
-         ptr(dw), ptr(db), ptr(ws), ws.numel(), stream())
+         ptr(dw), ptr(db), ptr(ws), ws.numel(), stream(), nbytes=2 * E * 4 * D + 2 * g.N * 4 * D)
     if need_dx and has_residual:
         dx[E:].copy_(gout)
     return (dx if need_dx else None), dw, db

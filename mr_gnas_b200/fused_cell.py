@@ -93,8 +93,9 @@ class EdgeChain(torch.autograd.Function):
         # node 1: gather + compose (+ column statistics)
         y1 = torch.empty(M, D, dtype=torch.float32, device=dev)
         st = K._stats_buf(K.stats_nparts(M), D, dev)
+        b = 4 * D
         call("mrg_compose_fwd", ptr(ent), ptr(g.src_final), ptr(rel), ptr(g.et_final), M, D, first.op.comp, ptr(y1),
-             ptr(st), stream())
+             ptr(st), stream(), nbytes=M * (b + 8))
         Y[1] = y1
         BN[1] = bn_affine(first, st, M)
 
@@ -117,7 +118,8 @@ class EdgeChain(torch.autograd.Function):
             for s_, (lo, hi) in enumerate(bounds):
                 rs = norm[lo:] if lo < E else None
                 call("mrg_sparse_gate_fwd", view(i, lo, hi), view(1, lo, hi), hi - lo, D, ptr(v1[s_]), ptr(v2[s_]),
-                     ptr(c[s_:s_ + 1]), ptr(rs), 1.0 / 3.0, ptr(y[lo:hi]), ptr(gt[lo:hi]), ptr(st[off * 2 * D:]), stream())
+                     ptr(c[s_:s_ + 1]), ptr(rs), 1.0 / 3.0, ptr(y[lo:hi]), ptr(gt[lo:hi]), ptr(st[off * 2 * D:]), stream(),
+                     nbytes=(hi - lo) * ((2 if i == 1 else 3) * b + 8))
                 off += nparts[s_]
             Y[node], GATE[node] = y, gt
             BN[node] = bn_affine(om, st, M)
@@ -130,7 +132,7 @@ class EdgeChain(torch.autograd.Function):
                 arg = torch.empty(N, D, dtype=torch.int32, device=dev)
                 ws = K._tc_workspace(N, D, dev)
                 call("mrg_amax_tc_fwd", view(i), ptr(W), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, view(i, E, M),
-                     ptr(out), ptr(arg), ptr(ws), ws.numel(), stream())
+                     ptr(out), ptr(arg), ptr(ws), ws.numel(), stream(), nbytes=E * (b + 8) + 3 * N * b)
                 ARG[node] = arg
                 g.last_arg = arg
             else:
@@ -189,7 +191,7 @@ class EdgeChain(torch.autograd.Function):
             yv = act(Y[k], a, b, True)
             nparts = K.stats_nparts(M)
             bst = K._stats_buf(nparts, D, dev)
-            call("mrg_bn_bwd_reduce", ptr(ds), yv, M, D, ptr(bst), stream())
+            call("mrg_bn_bwd_reduce", ptr(ds), yv, M, D, ptr(bst), stream(), nbytes=2 * M * 4 * D)
             dgamma = torch.empty(D, dtype=torch.float32, device=dev)
             dbeta = torch.empty_like(dgamma)
             coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
@@ -197,7 +199,7 @@ class EdgeChain(torch.autograd.Function):
                  ptr(dbeta), ptr(coef), stream())
             if not training:
                 coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
-            call("mrg_bn_bwd_apply", ptr(ds), yv, ptr(coef), M, D, ptr(ds), 0, stream())
+            call("mrg_bn_bwd_apply", ptr(ds), yv, ptr(coef), M, D, ptr(ds), 0, stream(), nbytes=3 * M * 4 * D)
             return dgamma, dbeta
 
         # ---- gates in reverse order
@@ -222,7 +224,8 @@ class EdgeChain(torch.autograd.Function):
                 dparam = torch.empty(int(lib.mrg_gate_dparam_count(n, D)), dtype=torch.float64, device=dev)
                 call("mrg_sparse_gate_bwd", ptr(dy[lo:hi]), view(i, lo, hi), view(1, lo, hi), ptr(GATE[node][lo:hi]), n, D,
                      ptr(v1[s_]), ptr(v2[s_]), ptr(rs), 1.0 / 3.0, ptr(DS[i][lo:hi]), ptr(DS[1][lo:hi]), accum,
-                     ptr(dparam), stream())
+                     ptr(dparam), stream(),
+                     nbytes=n * (4 * D * ((2 if same else 3) + (1 if same else 2) + bin(accum).count("1")) + 8))
                 call("mrg_sparse_gate_bwd_finalize", ptr(dparam), n, D, ptr(dv1[s_]), ptr(dv2[s_]), ptr(dc[s_:s_ + 1]),
                      stream())
             grads[('gate', node)] = (dv1, dv2, dc)
