@@ -238,17 +238,10 @@ def main():
     dev_batches = [(t.to(dev), y.to(dev)) for t, y in host_batches]
     h2d = host_batches[0][0].numel() * 8 + host_batches[0][1].numel() * 4
 
+    from mr_gnas_b200.dist import allreduce_grads as _allreduce
+
     def allreduce_grads():
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params:
-                if p.grad is not None:
-                    n = p.grad.numel()
-                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                    off += n
+        _allreduce(params, world)
 
     def step_resident(i):
         trip_d, y_d = dev_batches[i % len(dev_batches)]

@@ -89,77 +89,77 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
 // f = w, w+8, ...), walking destinations n = cta, cta+stride, ...; x rows are gathered through
 // the lazy BatchNorm+ReLU view.  Partials: part[cta][D][KW] (+ db in part_b[cta][D]).
 // ---------------------------------------------------------------------------------------
-template <int NT>
+template <int NT>   // NT = float4 groups per lane covering the CTA's KW-wide column slice
 __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dw_kernel(const float* __restrict__ g,
-                                                               const int32_t* __restrict__ arg, mrg_act x, int64_t N,
-                                                               int D, int KW, int kslices, float* __restrict__ part,
-                                                               float* __restrict__ part_b) {
-  extern __shared__ float smem[];  // dW_s [D][KW] | g_s [D] | arg_s [D] | db_s [D]
+                                                                     const int32_t* __restrict__ arg, mrg_act x,
+                                                                     int64_t N, int D, int KW, int kslices,
+                                                                     float* __restrict__ part,
+                                                                     float* __restrict__ part_b) {
+  extern __shared__ float smem[];  // dW_s [D][KW] | db_s [D]
   float* dW_s = smem;
-  float* g_s = dW_s + (size_t)D * KW;
-  int32_t* a_s = reinterpret_cast<int32_t*>(g_s + D);
-  float* db_s = reinterpret_cast<float*>(a_s + D);
+  float* db_s = dW_s + (size_t)D * KW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x % kslices;
   const int k0 = slice * KW;
-  const int kw = min(KW, D - k0);
+  const int kw4 = min(KW, D - k0) >> 2;   // float4 groups in this slice (KW % 4 == 0)
   for (int i = threadIdx.x; i < D * KW; i += blockDim.x) dW_s[i] = 0.f;
   for (int i = threadIdx.x; i < D; i += blockDim.x) db_s[i] = 0.f;
+  __syncthreads();
   const bool affine = x.scale != nullptr, relu = x.relu != 0;
-  float sc[NT], sh[NT];
+  float4 sc[NT], sh[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
-    const int k = k0 + lane + 32 * t;
-    sc[t] = (affine && lane + 32 * t < kw) ? __ldg(x.scale + k) : 1.f;
-    sh[t] = (affine && lane + 32 * t < kw) ? __ldg(x.shift + k) : 0.f;
+    const int c4 = lane + 32 * t;
+    sc[t] = (affine && c4 < kw4) ? ldg4(x.scale + k0 + 4 * c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+    sh[t] = (affine && c4 < kw4) ? ldg4(x.shift + k0 + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  // Warp w owns the dW rows f = w + 32 j: no other warp ever touches them, so there is no block-level
+  // synchronisation in the node loop and every warp keeps a batch of gathered x rows in flight.
+  constexpr int FB = 4;                       // features (gathered rows) in flight per batch
+  const int nf = (D - warp + kBwdWarps - 1) / kBwdWarps;   // features owned by this warp (<= 32)
   const int64_t stride = gridDim.x / kslices;
   for (int64_t n = blockIdx.x / kslices; n < N; n += stride) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      g_s[i] = __ldg(g + (size_t)n * D + i);
-      a_s[i] = __ldg(arg + (size_t)n * D + i);
-    }
-    __syncthreads();
-    // two features per iteration: both gathered x rows are in flight before the shared-memory RMW
-    for (int f0 = warp; f0 < D; f0 += 2 * kBwdWarps) {
-      const int f1 = f0 + kBwdWarps;
-      const int32_t e0 = a_s[f0];
-      const int32_t e1 = f1 < D ? a_s[f1] : -1;
-      float xv0[NT], xv1[NT];
+    // lane j holds (arg, g) of the warp's j-th feature
+    const int fl = warp + kBwdWarps * lane;
+    const int32_t a_l = (lane < nf) ? __ldg(arg + (size_t)n * D + fl) : -1;
+    const float g_l = (lane < nf) ? __ldg(g + (size_t)n * D + fl) : 0.f;
+    for (int j0 = 0; j0 < nf; j0 += FB) {
+      float4 xv[FB][NT];
+      int32_t ev[FB];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int k = lane + 32 * t;
-        xv0[t] = (e0 >= 0 && k < kw) ? __ldg(x.data + (size_t)e0 * D + k0 + k) : 0.f;
-        xv1[t] = (e1 >= 0 && k < kw) ? __ldg(x.data + (size_t)e1 * D + k0 + k) : 0.f;
-      }
-      if (e0 >= 0) {
-        const float gv = g_s[f0];
-        if (lane == 0 && slice == 0) db_s[f0] += gv;
-        float* wr = dW_s + (size_t)f0 * KW;
+      for (int u = 0; u < FB; ++u) {
+        ev[u] = (j0 + u < nf) ? __shfl_sync(0xffffffffu, a_l, (j0 + u) & 31) : -1;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const int k = lane + 32 * t;
-          if (k < kw) {
-            float xv = xv0[t];
-            if (affine) xv = fmaf(sc[t], xv, sh[t]);
-            if (relu) xv = xv > 0.f ? xv : 0.f;
-            wr[k] = fmaf(gv, xv, wr[k]);
-          }
+          const int c4 = lane + 32 * t;
+          xv[u][t] = (ev[u] >= 0 && c4 < kw4) ? ldg4(x.data + (size_t)ev[u] * D + k0 + 4 * c4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      if (e1 >= 0) {
-        const float gv = g_s[f1];
-        if (lane == 0 && slice == 0) db_s[f1] += gv;
-        float* wr = dW_s + (size_t)f1 * KW;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int k = lane + 32 * t;
-          if (k < kw) {
-            float xv = xv1[t];
-            if (affine) xv = fmaf(sc[t], xv, sh[t]);
-            if (relu) xv = xv > 0.f ? xv : 0.f;
-            wr[k] = fmaf(gv, xv, wr[k]);
+      for (int u = 0; u < FB; ++u) {
+        const float gv = __shfl_sync(0xffffffffu, g_l, (j0 + u) & 31);
+        if (ev[u] >= 0) {   // warp-uniform
+          const int f = warp + kBwdWarps * (j0 + u);
+          if (lane == 0 && slice == 0) db_s[f] += gv;
+          float* wr = dW_s + (size_t)f * KW;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const int c4 = lane + 32 * t;
+            if (c4 < kw4) {
+              float4 v = xv[u][t];
+              if (affine) {
+                v.x = fmaf(sc[t].x, v.x, sh[t].x); v.y = fmaf(sc[t].y, v.y, sh[t].y);
+                v.z = fmaf(sc[t].z, v.z, sh[t].z); v.w = fmaf(sc[t].w, v.w, sh[t].w);
+              }
+              if (relu) {
+                v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+                v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+              }
+              float4 a = *reinterpret_cast<float4*>(wr + 4 * c4);
+              a.x = fmaf(gv, v.x, a.x); a.y = fmaf(gv, v.y, a.y); a.z = fmaf(gv, v.z, a.z); a.w = fmaf(gv, v.w, a.w);
+              *reinterpret_cast<float4*>(wr + 4 * c4) = a;
+            }
           }
         }
       }
@@ -195,9 +195,10 @@ __global__ void amax_bwd_dw_fold_kernel(const float* __restrict__ part, const fl
 
 using namespace mrg;
 
+static inline int dw_kw(int D, int ks) { return ((D + ks - 1) / ks + 3) / 4 * 4; }
 static inline int dw_kslices(int D) {
   int ks = 1;
-  while ((size_t)D * ((D + ks - 1) / ks) * 4 > 190 * 1024) ++ks;
+  while ((size_t)D * dw_kw(D, ks) * 4 > 190 * 1024) ++ks;
   return ks;
 }
 static inline int dw_grid(int D) {
@@ -206,7 +207,7 @@ static inline int dw_grid(int D) {
 }
 
 extern "C" size_t mrg_amax_bwd_workspace_bytes(int32_t D) {
-  const int ks = dw_kslices(D), KW = (D + ks - 1) / ks;
+  const int ks = dw_kslices(D), KW = dw_kw(D, ks);
   return (size_t)dw_grid(D) * D * KW * sizeof(float) + (size_t)dw_grid(D) * D * sizeof(float) + 256;
 }
 
@@ -244,11 +245,11 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
 #undef LDX
   }
   if (dW) {
-    const int ks = dw_kslices(D), KW = (D + ks - 1) / ks, grid = dw_grid(D);
+    const int ks = dw_kslices(D), KW = dw_kw(D, ks), grid = dw_grid(D);
     float* part = (float*)workspace;
     float* part_b = part + (size_t)grid * D * KW;
-    const size_t smem = ((size_t)D * KW + 3 * (size_t)D) * 4;
-    const int nt = (KW + 31) / 32;
+    const size_t smem = ((size_t)D * KW + (size_t)D) * 4;
+    const int nt = (KW / 4 + 31) / 32;
 #define LDW(NT)                                                                                               \
   do {                                                                                                        \
     if (smem > 48 * 1024) {                                                                                   \
@@ -257,10 +258,8 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
     }                                                                                                         \
     amax_bwd_dw_kernel<NT><<<grid, kBwdThreads, smem, st>>>(g, arg, x, N, D, KW, ks, part, part_b);               \
   } while (0)
-    if (nt <= 2) LDW(2);
-    else if (nt <= 4) LDW(4);
-    else if (nt <= 7) LDW(7);
-    else LDW(8);
+    if (nt <= 1) LDW(1);
+    else LDW(2);
 #undef LDW
     const int n = D * D + D;
     amax_bwd_dw_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, part_b, grid, ks, D, KW, dW, db);

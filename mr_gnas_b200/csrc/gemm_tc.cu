@@ -16,13 +16,15 @@
 // lo = rna_tf32(x - hi)) and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM
 // ("3xTF32"), giving ~2^-21 relative operand error, i.e. SGEMM-class results.
 //
-// Pipeline per CTA (persistent over tiles, one CTA per SM, 14 warps):
+// Pipeline per CTA (persistent, one CTA per SM, 18 warps; tiles are walked in PAIRS -- TMEM slots 0/1 -- with
+// their K chunks interleaved so each W chunk streamed from L2 feeds two tiles):
 //   warps 0-7   X producers: 2 threads per tile row gather X by CSR edge id with a 3-chunk-deep register
 //                            prefetch ring -> (BN affine + ReLU) -> hi/lo split -> 128B-swizzled K-major smem
-//   warp  13    W loader   : one thread, cp.async.bulk (UBLKCP) of the pre-swizzled hi/lo K-chunk image,
+//   warp  17    W loader   : one thread, cp.async.bulk (UBLKCP) of the pre-swizzled hi/lo K-chunk image,
 //                            completion by mbarrier expect_tx
-//   warp  12    MMA issuer : one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
-//   warps 8-11  epilogue   : tcgen05.ld -> +bias, ReLU -> segmented max scan -> atomicMax
+//   warp  16    MMA issuer : one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
+//   warps 8-15  epilogue   : one 4-warp set per TMEM slot: tcgen05.ld -> +bias, ReLU -> segmented max scan
+//                            -> atomicMax
 #include "common.cuh"
 
 namespace mrg {
@@ -33,11 +35,11 @@ constexpr int KCH = 32;       // fp32 elements per K chunk = one 128-byte swizzl
 constexpr int STAGES = 2;
 constexpr int PROD_THREADS = 256;
 constexpr int EPI_THREADS = 128;
-constexpr int THREADS = PROD_THREADS + EPI_THREADS + 64;
-constexpr int PD = 3;         // X prefetch depth (K chunks in flight per producer thread)
-constexpr int EPI_WARP0 = PROD_THREADS / 32;   // 8  (8 % 4 == 0 -> TMEM lane quadrants 0..3)
-constexpr int MMA_WARP = EPI_WARP0 + 4;        // 12
-constexpr int WLD_WARP = MMA_WARP + 1;         // 13
+constexpr int THREADS = PROD_THREADS + 2 * EPI_THREADS + 64;   // 18 warps
+constexpr int PD = 3;         // X prefetch depth (items in flight per producer thread)
+constexpr int EPI_WARP0 = PROD_THREADS / 32;   // 8  (8 % 4 == 0 -> TMEM lane quadrants 0..3 for both warp sets)
+constexpr int MMA_WARP = EPI_WARP0 + 8;        // 16
+constexpr int WLD_WARP = MMA_WARP + 1;         // 17
 constexpr uint32_t TILE_BYTES = 128 * 128;  // 128 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,24 +156,54 @@ struct AmaxParams {
   int D, MH, Kp, nchunks, num_tiles;
 };
 
-// dynamic smem: [stage][ Whi MH tiles | Wlo MH tiles | Xhi | Xlo ] (1024-B aligned) then small arrays
+// One work ITEM = (tile, K chunk).  A CTA walks its tiles in PAIRS (TMEM slots 0/1) with the chunks of the
+// two tiles interleaved, so every W chunk fetched from L2 feeds two tiles (W re-streaming is the dominant
+// L2->SM traffic of this kernel):  items of pair p:  (A,c0) (B,c0) (A,c1) (B,c1) ...
+struct Item {
+  int pair, c, slot;
+};
+__device__ __forceinline__ Item item_of(int q, int nchunks, int full_pairs) {
+  Item it;
+  const int per_pair = 2 * nchunks;
+  if (q < full_pairs * per_pair) {
+    it.pair = q / per_pair;
+    const int rem = q - it.pair * per_pair;
+    it.c = rem >> 1;
+    it.slot = rem & 1;
+  } else {  // trailing single tile
+    it.pair = full_pairs;
+    it.c = q - full_pairs * per_pair;
+    it.slot = 0;
+  }
+  return it;
+}
+
+// dynamic smem (1024-B aligned): W ring [WS][Whi MH tiles | Wlo MH tiles], X ring [XS][Xhi | Xlo], small arrays
 template <int MH>
 __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t STAGE_BYTES = (2 * MH + 2) * TILE_BYTES;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* tail = smem + STAGES * STAGE_BYTES;
-  uint64_t* full_bar = (uint64_t*)tail;               // [STAGES]  X tile written (256 producer arrivals)
-  uint64_t* empty_bar = full_bar + STAGES;            // [STAGES]  MMAs that read the stage retired
-  uint64_t* wfull_bar = empty_bar + STAGES;           // [STAGES]  W chunk landed (expect_tx)
-  uint64_t* tfull_bar = wfull_bar + STAGES;           // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;               // [2]
+  constexpr uint32_t WSTAGE = 2 * MH * TILE_BYTES;
+  constexpr uint32_t XSTAGE = 2 * TILE_BYTES;
+  constexpr int XS = MH == 1 ? 4 : 2;
+  // align with pointer arithmetic on the __shared__ symbol (an integer round-trip would demote every access
+  // below to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + STAGES * WSTAGE;
+  uint8_t* tail = smem_x + XS * XSTAGE;
+  uint64_t* xfull_bar = (uint64_t*)tail;              // [XS]      X item written (256 producer arrivals)
+  uint64_t* xempty_bar = xfull_bar + XS;              // [XS]      MMAs that read the X stage retired
+  uint64_t* wfull_bar = xempty_bar + XS;              // [STAGES]  W chunk landed (expect_tx)
+  uint64_t* wempty_bar = wfull_bar + STAGES;          // [STAGES]  MMAs of both slots on this chunk retired
+  uint64_t* tfull_bar = wempty_bar + STAGES;          // [2]       accumulator of slot complete
+  uint64_t* tempty_bar = tfull_bar + 2;               // [2]       epilogue drained the slot
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);  // [1] (+pad)
   float* s_scale = (float*)(tmem_slot + 4);           // [256]
   float* s_shift = s_scale + 256;                     // [256]
   float* s_bias = s_shift + 256;                      // [256]
-  int32_t* s_dst = (int32_t*)(s_bias + 256);          // [2][128]
-  int32_t* s_eid = s_dst + 2 * TILE_E;                // [2][128]
+  int32_t* s_dst = (int32_t*)(s_bias + 256);          // [2 slots][128]
+  int32_t* s_eid = s_dst + 2 * TILE_E;                // [2 slots][128]
+  uint32_t* s_flag = (uint32_t*)(s_eid + 2 * TILE_E); // [2 slots][4] segment-start bitmask of the tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = p.D;
@@ -183,10 +215,13 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     s_bias[c] = (p.bias && c < D) ? p.bias[c] : 0.f;
   }
   if (threadIdx.x == 0) {
+    for (int s = 0; s < XS; ++s) {
+      mbar_init(&xfull_bar[s], PROD_THREADS);
+      mbar_init(&xempty_bar[s], 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], PROD_THREADS);
-      mbar_init(&empty_bar[s], 1);
       mbar_init(&wfull_bar[s], 1);
+      mbar_init(&wempty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -206,40 +241,48 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   const uint32_t tmem_base = *tmem_slot;
 
   const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int total = my_tiles * p.nchunks;   // K chunks this CTA streams, in order
+  const int full_pairs = my_tiles >> 1;
+  const int npairs = (my_tiles + 1) >> 1;
+  const int total = my_tiles * p.nchunks;   // items this CTA streams, in order
+  auto tile_of = [&](int pair, int slot) { return (int64_t)blockIdx.x + (int64_t)(2 * pair + slot) * gridDim.x; };
+
   if (warp < EPI_WARP0) {
     // ================================ X PRODUCERS ================================
     const int r = (warp << 4) | (lane & 15);   // tile row
     const int half = lane >> 4;                // which 16-byte units of a 128-byte chunk: 2j + half
     const bool affine = p.x.scale != nullptr, relu = p.x.relu != 0;
     const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
-    const float* xrow = nullptr;   // load cursor's row
+    const float* xrow0 = nullptr;   // load cursor's row, slot 0 / slot 1
+    const float* xrow1 = nullptr;
     float4 buf[PD][4];
     int lq = 0;
     auto load = [&](float4(&b)[4], int q) {
-      const int tl = q / p.nchunks, c = q - tl * p.nchunks;
-      if (c == 0) {
-        const int64_t pos = (int64_t)(blockIdx.x + tl * gridDim.x) * TILE_E + r;
-        xrow = pos < p.E ? p.x.data + (size_t)__ldg(p.csr_eid + pos) * D : nullptr;
+      const Item it = item_of(q, p.nchunks, full_pairs);
+      if (it.c == 0) {
+        const int64_t pos = tile_of(it.pair, it.slot) * TILE_E + r;
+        const float* v = pos < p.E ? p.x.data + (size_t)__ldg(p.csr_eid + pos) * D : nullptr;
+        if (it.slot) xrow1 = v;
+        else xrow0 = v;
       }
+      const float* xr = it.slot ? xrow1 : xrow0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int col = c * KCH + 4 * (2 * j + half);
-        b[j] = (xrow && col < D) ? ld_stream4(xrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int col = it.c * KCH + 4 * (2 * j + half);
+        b[j] = (xr && col < D) ? ld_stream4(xr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     auto consume = [&](float4(&b)[4], int q) {
-      const int tl = q / p.nchunks, c = q - tl * p.nchunks;
-      const bool valid = (int64_t)(blockIdx.x + tl * gridDim.x) * TILE_E + r < p.E;
-      const int s = q % STAGES;
-      const uint32_t ph = (q / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* xhi = smem + (size_t)s * STAGE_BYTES + 2 * MH * TILE_BYTES;
+      const Item it = item_of(q, p.nchunks, full_pairs);
+      const bool valid = tile_of(it.pair, it.slot) * TILE_E + r < p.E;
+      const int s = q % XS;
+      const uint32_t ph = (q / XS) & 1;
+      mbar_wait(&xempty_bar[s], ph ^ 1);
+      uint8_t* xhi = smem_x + (size_t)s * XSTAGE;
       uint8_t* xlo = xhi + TILE_BYTES;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int u = 2 * j + half;
-        const int col = c * KCH + 4 * u;
+        const int col = it.c * KCH + 4 * u;
         float4 v = b[j];
         if (valid && col < D) {
           if (affine) {
@@ -262,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         *reinterpret_cast<float4*>(xlo + off) = lo;
       }
       fence_proxy_async();
-      mbar_arrive(&full_bar[s]);
+      mbar_arrive(&xfull_bar[s]);
     };
 #pragma unroll
     for (int u = 0; u < PD; ++u) {
@@ -282,119 +325,146 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   } else if (warp == WLD_WARP) {
     // ================================ W LOADER ================================
     if (lane == 0) {
-      const uint32_t wbytes = 2 * MH * TILE_BYTES;
-      for (int q = 0; q < total; ++q) {
-        const int s = q % STAGES;
-        const uint32_t ph = (q / STAGES) & 1;
-        const int c = q % p.nchunks;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&wfull_bar[s], wbytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)c * wbytes;
-        const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        for (uint32_t o = 0; o < wbytes; o += TILE_BYTES) bulk_g2s(dst + o, src + o, TILE_BYTES, &wfull_bar[s]);
+      const int wtotal = npairs * p.nchunks;
+      for (int wq = 0; wq < wtotal; ++wq) {
+        const int s = wq % STAGES;
+        const uint32_t ph = (wq / STAGES) & 1;
+        const int c = wq % p.nchunks;
+        mbar_wait(&wempty_bar[s], ph ^ 1);
+        mbar_expect_tx(&wfull_bar[s], WSTAGE);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)c * WSTAGE;
+        const uint32_t dst = smem_u32(smem_w + (size_t)s * WSTAGE);
+        for (uint32_t o = 0; o < WSTAGE; o += TILE_BYTES) bulk_g2s(dst + o, src + o, TILE_BYTES, &wfull_bar[s]);
       }
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA ISSUER ================================
     const uint32_t idesc = umma_idesc(128, TILE_E);
-    uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1;
-      mbar_wait(&tempty_bar[buf], ((tcount >> 1) & 1) ^ 1);
+    int q = 0, wq = 0;
+    for (int pr = 0; pr < npairs; ++pr) {
+      const int ntp = min(2, my_tiles - 2 * pr);
+      for (int ts = 0; ts < ntp; ++ts) mbar_wait(&tempty_bar[ts], (pr & 1) ^ 1);
       tc_fence_after();
-      for (int c = 0; c < p.nchunks; ++c, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        mbar_wait(&wfull_bar[s], ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sbase = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t xhi = sbase + 2 * MH * TILE_BYTES, xlo = xhi + TILE_BYTES;
-          const int ksteps = min(KCH, D - c * KCH) / 8;
-          for (int h = 0; h < MH; ++h) {
-            const uint32_t whi = sbase + h * TILE_BYTES, wlo = sbase + (MH + h) * TILE_BYTES;
-            const uint32_t d_tmem = tmem_base + buf * (MH * TILE_E) + h * TILE_E;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the swizzled 128B row
-              const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-              umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);  // small terms first
-              umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
-              umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+      for (int c = 0; c < p.nchunks; ++c, ++wq) {
+        const int ws = wq % STAGES;
+        mbar_wait(&wfull_bar[ws], (wq / STAGES) & 1);
+        const uint32_t wbase = smem_u32(smem_w + (size_t)ws * WSTAGE);
+        const int ksteps = min(KCH, D - c * KCH) / 8;
+        for (int ts = 0; ts < ntp; ++ts, ++q) {
+          const int xs = q % XS;
+          mbar_wait(&xfull_bar[xs], (q / XS) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t xhi = smem_u32(smem_x + (size_t)xs * XSTAGE), xlo = xhi + TILE_BYTES;
+            for (int h = 0; h < MH; ++h) {
+              const uint32_t whi = wbase + h * TILE_BYTES, wlo = wbase + (MH + h) * TILE_BYTES;
+              const uint32_t d_tmem = tmem_base + ts * (MH * TILE_E) + h * TILE_E;
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the swizzled 128B row
+                const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+                umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);  // small terms first
+                umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
+                umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+              }
             }
+            umma_commit(&xempty_bar[xs]);                          // X stage free when these MMAs retire
+            if (c == p.nchunks - 1) umma_commit(&tfull_bar[ts]);   // accumulator of this slot complete
           }
-          umma_commit(&empty_bar[s]);                       // frees the smem stage when the MMAs retire
-          if (c == p.nchunks - 1) umma_commit(&tfull_bar[buf]);  // accumulator complete
+          __syncwarp();
         }
+        if (lane == 0) umma_commit(&wempty_bar[ws]);               // W stage free (both slots done with it)
         __syncwarp();
       }
     }
   } else {
-    // ================================ EPILOGUE ================================
-    const int et = threadIdx.x - PROD_THREADS;       // 0..127 == TMEM lane
-    const int quad = warp & 3;                       // warps 8..11 -> lane quadrants 0..3
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1;
-      const int64_t pos0 = (int64_t)tile * TILE_E;
+    // ================================ EPILOGUE (2 warp sets, one per TMEM slot) ================================
+    const int ts = (warp - EPI_WARP0) >> 2;           // slot served by this warp set
+    const int et = (threadIdx.x - PROD_THREADS) & 127;  // 0..127 == TMEM lane
+    const int quad = warp & 3;                        // TMEM lane quadrant of this warp
+    int32_t* sd = s_dst + ts * TILE_E;
+    int32_t* se = s_eid + ts * TILE_E;
+    for (int pr = 0; pr < npairs; ++pr) {
+      if (2 * pr + ts >= my_tiles) break;
+      const int64_t pos0 = tile_of(pr, ts) * TILE_E;
       const int cnt = (int)min((int64_t)TILE_E, p.E - pos0);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");   // previous tile's readers are done with sd/se
       {
         int32_t e = -1, d = -1;
         if (et < cnt) {
           e = __ldg(p.csr_eid + pos0 + et);
           d = __ldg(p.dst + e);
         }
-        s_eid[buf * TILE_E + et] = e;
-        s_dst[buf * TILE_E + et] = d;
+        se[et] = e;
+        sd[et] = d;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+      {
+        // bit j of word w: a new destination starts at column 32 w + j (column 0 never flags)
+        const bool starts = et > 0 && et < cnt && sd[et] != sd[et - 1];
+        const uint32_t word = __ballot_sync(0xffffffffu, starts);
+        if (lane == 0) s_flag[ts * 4 + quad] = word;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+      mbar_wait(&tfull_bar[ts], pr & 1);
       tc_fence_after();
-      const int32_t* sd = s_dst + buf * TILE_E;
-      const int32_t* se = s_eid + buf * TILE_E;
       for (int h = 0; h < MH; ++h) {
         const int f = h * 128 + et;
         const bool fvalid = f < D;
         const float bias = s_bias[f & 255];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MH * TILE_E) + h * TILE_E;
-        int32_t cur = sd[0];
-        float best = -1.f;
-        int32_t barg = -1;
-        for (int cb = 0; cb < TILE_E; cb += 32) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * (MH * TILE_E) + h * TILE_E;
+        // Register-only segmented max.  relu(v) >= 0, so starting every segment at (best = 0, bcol = first column)
+        // and updating on a strict v > best IS max(relu(v)) with the lowest-column tie-break -- 4 instructions per
+        // column (FADD, FSETP, FSEL, SEL); memory is touched only when a segment closes (a few times per tile).
+        float best = 0.f;
+        int bcol = 0;
+        auto close_seg = [&](int col) {   // columns [.., col) of the running destination are done
+          if (fvalid) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - (uint32_t)se[bcol]);
+            atomicMax(p.packed + (size_t)sd[col - 1] * D + f, key);
+          }
+        };
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+          const int cb = 32 * w;
+          if (cb >= cnt) break;   // warp-uniform
           uint32_t v[32];
           tmem_ld32(taddr + cb, v);
+          const uint32_t fl = s_flag[ts * 4 + w];
+          if (cb + 32 <= cnt) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = cb + j;
-            if (col < cnt) {
-              const int32_t d = sd[col];
-              if (d != cur) {
-                if (fvalid) {
-                  const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) |
-                                                 (unsigned long long)(0xFFFFFFFFu - (uint32_t)barg);
-                  atomicMax(p.packed + (size_t)cur * D + f, key);
-                }
-                cur = d;
-                best = -1.f;
-                barg = -1;
+            for (int j = 0; j < 32; ++j) {
+              if (fl & (1u << j)) {   // warp-uniform, rare
+                close_seg(cb + j);
+                best = 0.f;
+                bcol = cb + j;
               }
-              float val = __uint_as_float(v[j]) + bias;
-              val = val > 0.f ? val : 0.f;
-              if (val > best) {
-                best = val;
-                barg = se[col];
+              const float val = __uint_as_float(v[j]) + bias;
+              const bool gt = val > best;
+              best = gt ? val : best;
+              bcol = gt ? cb + j : bcol;
+            }
+          } else {   // ragged last tile
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (cb + j < cnt) {
+                if (fl & (1u << j)) {
+                  close_seg(cb + j);
+                  best = 0.f;
+                  bcol = cb + j;
+                }
+                const float val = __uint_as_float(v[j]) + bias;
+                const bool gt = val > best;
+                best = gt ? val : best;
+                bcol = gt ? cb + j : bcol;
               }
             }
           }
         }
-        if (fvalid && cnt > 0) {
-          const unsigned long long key =
-              ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)barg);
-          atomicMax(p.packed + (size_t)cur * D + f, key);
-        }
+        if (cnt > 0) close_seg(cnt);
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      mbar_arrive(&tempty_bar[ts]);
     }
   }
 
@@ -475,7 +545,8 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   p.nchunks = Kp / tc::KCH;
   p.num_tiles = (int)((E + tc::TILE_E - 1) / tc::TILE_E);
   if (p.num_tiles > 0) {
-    const size_t smem = (size_t)tc::STAGES * (2 * MH + 2) * tc::TILE_BYTES + 1024 /*align*/ + 8192 /*tail*/;
+    const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
+                        1024 /*align*/ + 8192 /*tail*/;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     if (MH == 1) {
       e = cudaFuncSetAttribute(tc::amax_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
