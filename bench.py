@@ -269,15 +269,13 @@ def main():
 
     def timed(fn, steps, sample_clocks=False):
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
-        if sampler:                      # let nvidia-smi start up while the GPU stays under load
-            t_end = time.time() + 0.4
-            j = 0
-            while time.time() < t_end:
+        if sample_clocks:                # let nvidia-smi start up while the GPU stays under load; EVERY rank runs the
+            for j in range(40):          # same number of steps (each step holds a collective when world > 1)
                 fn(j)
-                j += 1
-                torch.cuda.synchronize()
+            torch.cuda.synchronize()
         barrier()
         t0 = time.time()
+        k_before = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -285,6 +283,7 @@ def main():
         e1.record()
         barrier()
         t1 = time.time()
+        timed.launches = _lib.launch_count - k_before
         ms = e0.elapsed_time(e1) / steps
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -294,9 +293,8 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
-    k0 = _lib.launch_count
     ms, clocks, last_loss = timed(step_resident, args.steps, sample_clocks=True)
-    launches = (_lib.launch_count - k0)
+    launches = timed.launches   # libmrgnas kernels enqueued inside the timed region
     for i in range(2):
         step_e2e(i)
     ms_e2e, _, last_e2e = timed(step_e2e, args.steps)
@@ -309,8 +307,10 @@ def main():
     roofline, prof_rows = None, []
     if rank == 0:
         _lib.start_profile()
-        for i in range(3):
-            step_resident(i)
+    for i in range(3):                   # all ranks step together (gradient all-reduce inside); rank 0 records
+        step_resident(i)
+    barrier()
+    if rank == 0:
         prof = _lib.stop_profile()
         tot = sum(v[1] for v in prof.values()) / 3
         hbm, how = peaks()
@@ -329,7 +329,7 @@ def main():
             json.dump(prof_rows, open(args.profile_json, "w"), indent=1)
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import mrg_oracle as O  # cpu_baseline leg only
         torch.set_num_threads(os.cpu_count())
         out = time_cpu_oracle(O, N, R, trip, D, B, steps=1, warmup=0)
