@@ -169,6 +169,29 @@ int mrg_sparse_gate_bwd(const float* dy, mrg_act x, mrg_act xin, const float* ga
 int mrg_sparse_gate_bwd_finalize(const double* dparam, int64_t rows, int32_t D, float* dv1, float* dv2, float* dc,
                                  void* stream);
 
+/* A gradient read through the lazy BatchNorm1d(+ReLU) backward of the state it belongs to
+ * (model_lp.py:31-33 backward; torch native_batch_norm_backward + threshold_backward):
+ *   dz(i,c)    = ds[i,c] * [ y.relu ? y.scale[c]*y.data[i,c] + y.shift[c] > 0 : 1 ]
+ *   value(i,c) = coef ? coef[2D+c]*dz + coef[c] + coef[D+c]*y.data[i,c] : ds[i,c]
+ * coef is the [3][D] output of mrg_bn_bwd_finalize; with coef == NULL it is a plain gradient matrix. */
+typedef struct {
+  const float* ds;
+  mrg_act y;
+  const float* coef;
+} mrg_grad;
+
+/* mrg_sparse_gate_bwd with the BatchNorm backward of the neighbouring states folded in (TMA-staged row
+ * pipeline, D <= 256): the incoming gradient is an mrg_grad view, so no separate mrg_bn_bwd_apply pass runs, and, when
+ * x_bwd_stats != NULL, the kernel also writes the per-CTA partial column sums
+ *   sum_i dz_x(i,c), sum_i dz_x(i,c) * x.data[i,c],   dz_x = (final dx row) * [x.relu ? x(i,c) > 0 : 1]
+ * in the layout mrg_bn_bwd_finalize consumes ([mrg_stats_nparts(rows)][2][D] doubles) -- valid as the BN
+ * backward statistics of x's own state when this call contributes the LAST term of dx (no separate
+ * mrg_bn_bwd_reduce pass).  Everything else as mrg_sparse_gate_bwd. */
+int mrg_sparse_gate_bwd_fused_supported(int32_t D);
+int mrg_sparse_gate_bwd_fused(mrg_grad dy, mrg_act x, mrg_act xin, const float* gate, int64_t rows, int32_t D,
+                              const float* v1, const float* v2, const float* row_scale, float base_scale, float* dx,
+                              float* dxin, int32_t accumulate, double* dparam, double* x_bwd_stats, void* stream);
+
 /* dense gate epilogue: y = scale_i * sigmoid?(z) * x  (f_dense_op_comp / f_comp_op /
  * f_dense_op(_last), operations_lp.py:266-288,356-401) after the edge-tile GEMM z. */
 int mrg_dense_gate_fwd(const float* z, mrg_act x, int64_t rows, int32_t D, int32_t use_sigmoid,

@@ -21,6 +21,10 @@ class MrgAct(Structure):
     _fields_ = [("data", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("relu", c_int32)]
 
 
+class MrgGrad(Structure):
+    _fields_ = [("ds", c_void_p), ("y", MrgAct), ("coef", c_void_p)]
+
+
 class MrgActList(Structure):
     _fields_ = [("acts", MrgAct * 8), ("n", c_int32)]
 
@@ -50,6 +54,8 @@ _SIGNATURES = {
     "mrg_gate_dparam_count": (I64, [I64, I32]),
     "mrg_sparse_gate_bwd": (I32, [P, MrgAct, MrgAct, P, I64, I32, P, P, P, F32, P, P, I32, P, P]),
     "mrg_sparse_gate_bwd_finalize": (I32, [P, I64, I32, P, P, P, P]),
+    "mrg_sparse_gate_bwd_fused_supported": (I32, [I32]),
+    "mrg_sparse_gate_bwd_fused": (I32, [MrgGrad, MrgAct, MrgAct, P, I64, I32, P, P, P, F32, P, P, I32, P, P, P]),
     "mrg_dense_gate_fwd": (I32, [P, MrgAct, I64, I32, I32, P, F32, P, P, P]),
     "mrg_dense_gate_bwd": (I32, [P, P, MrgAct, I64, I32, I32, P, F32, P, P, I32, P]),
     "mrg_mixed_sum_fwd": (I32, [MrgActList, P, I64, I32, P, P]),
@@ -136,6 +142,13 @@ def act(data, scale=None, shift=None, relu=False):
     check_f32(data, scale, shift)
     return MrgAct(data.data_ptr(), scale.data_ptr() if scale is not None else None,
                   shift.data_ptr() if shift is not None else None, 1 if relu else 0)
+
+
+def grad(ds, y_act=None, coef=None):
+    """mrg_grad view: `ds` read through the lazy BN(+ReLU) backward of its state (coef from mrg_bn_bwd_finalize)."""
+    check_f32(ds, coef)
+    return MrgGrad(ds.data_ptr(), y_act if y_act is not None else MrgAct(None, None, None, 0),
+                   coef.data_ptr() if coef is not None else None)
 
 
 def call(name, *args, nbytes=None):

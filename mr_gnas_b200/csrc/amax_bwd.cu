@@ -85,91 +85,184 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
-// dW / db: every CTA accumulates a private [D][KW] slice in shared memory (warp w owns rows
-// f = w, w+8, ...), walking destinations n = cta, cta+stride, ...; x rows are gathered through
-// the lazy BatchNorm+ReLU view.  Partials: part[cta][D][KW] (+ db in part_b[cta][D]).
+// dW / db.  Every (destination, feature) pair routes g[n,f] to ONE edge row, so dW^T is a sum of
+// N*D rank-1 contributions g[n,f] * x(arg[n,f],:).  Gathering an 800-byte x row per pair would move
+// N*D*b bytes (5x the edge tensor at C1); instead each CTA owns a contiguous range of dst-CSR
+// positions, streams the x rows of that range ONCE into shared memory (cp.async, 3-stage ring of
+// kDwCap-row windows, lazy BatchNorm+ReLU applied in place when a window lands) and resolves every
+// pair against the staged window by a binary search of its edge id in the window's (ascending) edge
+// list.  Warp w owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS
+// (acc[u][t]: feature w*NF+u, column k0 + lane + 32 t): no shared-memory read-modify-write, no atomics,
+// a fixed accumulation order -> deterministic.  Destinations that straddle windows / CTAs are simply
+// seen by both; each pair is counted where its edge position falls.
+// Partials: part[cta][D][KW] (+ db in part_b[group][D]), folded in CTA order.
 // ---------------------------------------------------------------------------------------
-template <int NT>   // NT = float4 groups per lane covering the CTA's KW-wide column slice
-__global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dw_kernel(const float* __restrict__ g,
-                                                                     const int32_t* __restrict__ arg, mrg_act x,
-                                                                     int64_t N, int D, int KW, int kslices,
-                                                                     float* __restrict__ part,
-                                                                     float* __restrict__ part_b) {
-  extern __shared__ float smem[];  // dW_s [D][KW] | db_s [D]
-  float* dW_s = smem;
-  float* db_s = dW_s + (size_t)D * KW;
+constexpr int kDwThreads = 512;
+constexpr int kDwWarps = kDwThreads / 32;
+constexpr int kDwCap = 64;      // edge rows per staged window
+constexpr int kDwStages = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NF, int NT>
+__global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
+    const float* __restrict__ g, const int32_t* __restrict__ arg, mrg_act x, const int32_t* __restrict__ ptr,
+    const int32_t* __restrict__ eid, int64_t N, int64_t E, int D, int KW, int kslices, float* __restrict__ part,
+    float* __restrict__ part_b) {
+  extern __shared__ float smem[];
+  // layout: xs[kDwStages][kDwCap][KW] | pad[32] | eids[kDwStages][kDwCap] | sc[KW] | sh[KW]
+  float* xs = smem;
+  int32_t* eids = reinterpret_cast<int32_t*>(xs + (size_t)kDwStages * kDwCap * KW + 32);
+  float* sc_s = reinterpret_cast<float*>(eids + kDwStages * kDwCap);
+  float* sh_s = sc_s + KW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slice = blockIdx.x % kslices;
+  const int slice = blockIdx.x % kslices, group = blockIdx.x / kslices, ngroups = gridDim.x / kslices;
   const int k0 = slice * KW;
-  const int kw4 = min(KW, D - k0) >> 2;   // float4 groups in this slice (KW % 4 == 0)
-  for (int i = threadIdx.x; i < D * KW; i += blockDim.x) dW_s[i] = 0.f;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) db_s[i] = 0.f;
-  __syncthreads();
+  const int kw = min(KW, D - k0);   // valid columns of this slice (multiple of 4)
+  const int kw4 = kw >> 2;
   const bool affine = x.scale != nullptr, relu = x.relu != 0;
-  float4 sc[NT], sh[NT];
+  if (affine)
+    for (int c = threadIdx.x; c < kw; c += blockDim.x) {
+      sc_s[c] = x.scale[k0 + c];
+      sh_s[c] = x.shift[k0 + c];
+    }
+  const int64_t P0 = E * group / ngroups, P1 = E * (group + 1) / ngroups;
+  const int nb = (int)((P1 - P0 + kDwCap - 1) / kDwCap);
+
+  float acc[NF][NT];
 #pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const int c4 = lane + 32 * t;
-    sc[t] = (affine && c4 < kw4) ? ldg4(x.scale + k0 + 4 * c4) : make_float4(1.f, 1.f, 1.f, 1.f);
-    sh[t] = (affine && c4 < kw4) ? ldg4(x.shift + k0 + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = 0; u < NF; ++u)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[u][t] = 0.f;
+  float db_acc = 0.f;
+  const int f_l = warp * NF + lane;                 // the feature whose (arg, g) this lane fetches
+  const bool f_ok = lane < NF && f_l < D;
+
+  auto issue = [&](int b) {   // warp w copies rows w, w+16, ... of window b
+    const int64_t w_lo = P0 + (int64_t)b * kDwCap;
+    const int nrows = (int)min((int64_t)kDwCap, P1 - w_lo);
+    float* st = xs + (size_t)(b % kDwStages) * kDwCap * KW;
+    for (int r = warp; r < nrows; r += kDwWarps) {
+      const int32_t e = __ldg(eid + w_lo + r);
+      const float* src = x.data + (size_t)e * D + k0;
+      for (int c4 = lane; c4 < kw4; c4 += 32) cp_async16(st + (size_t)r * KW + 4 * c4, src + 4 * c4);
+    }
+    if (threadIdx.x < nrows) eids[(b % kDwStages) * kDwCap + threadIdx.x] = __ldg(eid + w_lo + threadIdx.x);
+  };
+
+  if (nb > 0) issue(0);
+  cp_async_commit();
+  if (nb > 1) issue(1);
+  cp_async_commit();
+
+  // first destination whose CSR row reaches past P0: largest n with ptr[n] <= P0 (empty rows skipped below)
+  int64_t n_cur = 0;
+  {
+    int64_t lo = 0, hi = N;   // invariant: ptr[lo] <= P0, answer in [lo, hi)
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(ptr + mid) <= P0) lo = mid; else hi = mid;
+    }
+    n_cur = lo;
   }
-  // Warp w owns the dW rows f = w + 32 j: no other warp ever touches them, so there is no block-level
-  // synchronisation in the node loop and every warp keeps a batch of gathered x rows in flight.
-  constexpr int FB = 4;                       // features (gathered rows) in flight per batch
-  const int nf = (D - warp + kBwdWarps - 1) / kBwdWarps;   // features owned by this warp (<= 32)
-  const int64_t stride = gridDim.x / kslices;
-  for (int64_t n = blockIdx.x / kslices; n < N; n += stride) {
-    // lane j holds (arg, g) of the warp's j-th feature
-    const int fl = warp + kBwdWarps * lane;
-    const int32_t a_l = (lane < nf) ? __ldg(arg + (size_t)n * D + fl) : -1;
-    const float g_l = (lane < nf) ? __ldg(g + (size_t)n * D + fl) : 0.f;
-    for (int j0 = 0; j0 < nf; j0 += FB) {
-      float4 xv[FB][NT];
-      int32_t ev[FB];
-#pragma unroll
-      for (int u = 0; u < FB; ++u) {
-        ev[u] = (j0 + u < nf) ? __shfl_sync(0xffffffffu, a_l, (j0 + u) & 31) : -1;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int c4 = lane + 32 * t;
-          xv[u][t] = (ev[u] >= 0 && c4 < kw4) ? ldg4(x.data + (size_t)ev[u] * D + k0 + 4 * c4)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t n_pf = -1;          // destination whose (arg, g) were prefetched into a_pf / g_pf
+  int32_t a_pf = -1;
+  float g_pf = 0.f;
+
+  for (int b = 0; b < nb; ++b) {
+    cp_async_wait<1>();
+    const int64_t w_lo = P0 + (int64_t)b * kDwCap;
+    const int64_t w_hi = min(w_lo + kDwCap, P1);
+    const int nrows = (int)(w_hi - w_lo);
+    float* st = xs + (size_t)(b % kDwStages) * kDwCap * KW;
+    if (affine || relu) {     // each thread post-processes exactly the 16-byte pieces it copied
+      for (int r = warp; r < nrows; r += kDwWarps)
+        for (int c4 = lane; c4 < kw4; c4 += 32) {
+          float4 v = *reinterpret_cast<float4*>(st + (size_t)r * KW + 4 * c4);
+          if (affine) {
+            const float4 a = *reinterpret_cast<const float4*>(sc_s + 4 * c4);
+            const float4 s = *reinterpret_cast<const float4*>(sh_s + 4 * c4);
+            v.x = fmaf(a.x, v.x, s.x); v.y = fmaf(a.y, v.y, s.y); v.z = fmaf(a.z, v.z, s.z); v.w = fmaf(a.w, v.w, s.w);
+          }
+          if (relu) {
+            v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+            v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+          }
+          *reinterpret_cast<float4*>(st + (size_t)r * KW + 4 * c4) = v;
         }
-      }
+    }
+    __syncthreads();          // window b complete for everyone; everyone finished computing window b-1
+    if (b + 2 < nb) issue(b + 2);
+    cp_async_commit();
+    const int32_t* el = eids + (b % kDwStages) * kDwCap;
+
+    int64_t n = n_cur;
+    while (n < N) {
+      const int32_t p0 = __ldg(ptr + n), p1 = __ldg(ptr + n + 1);
+      if (p0 >= w_hi) break;
+      if (p1 > w_lo && p1 > p0) {
+        const int lo = (int)(max((int64_t)p0, w_lo) - w_lo), hi = (int)(min((int64_t)p1, w_hi) - w_lo);
+        int32_t a;
+        float gv;
+        if (n == n_pf) {
+          a = a_pf; gv = g_pf;
+        } else {
+          a = f_ok ? __ldg(arg + (size_t)n * D + f_l) : -1;
+          gv = f_ok ? __ldg(g + (size_t)n * D + f_l) : 0.f;
+        }
+        if (n + 1 < N) {      // prefetch the next destination's routing while this one is processed
+          n_pf = n + 1;
+          a_pf = f_ok ? __ldg(arg + (size_t)(n + 1) * D + f_l) : -1;
+          g_pf = f_ok ? __ldg(g + (size_t)(n + 1) * D + f_l) : 0.f;
+        }
+        int r = -1;
+        if (a >= 0) {
+          int l = lo, h = hi;
+          while (l < h) {
+            const int mid = (l + h) >> 1;
+            if (el[mid] < a) l = mid + 1; else h = mid;
+          }
+          if (l < hi && el[l] == a) r = l;
+        }
+        if (r >= 0) db_acc += gv;
+        if (__any_sync(0xffffffffu, r >= 0)) {
 #pragma unroll
-      for (int u = 0; u < FB; ++u) {
-        const float gv = __shfl_sync(0xffffffffu, g_l, (j0 + u) & 31);
-        if (ev[u] >= 0) {   // warp-uniform
-          const int f = warp + kBwdWarps * (j0 + u);
-          if (lane == 0 && slice == 0) db_s[f] += gv;
-          float* wr = dW_s + (size_t)f * KW;
+          for (int u = 0; u < NF; ++u) {
+            const int ru = __shfl_sync(0xffffffffu, r, u);
+            const float gu = __shfl_sync(0xffffffffu, gv, u);
+            if (ru >= 0) {      // warp-uniform
+              const float* row = st + (size_t)ru * KW + lane;
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            const int c4 = lane + 32 * t;
-            if (c4 < kw4) {
-              float4 v = xv[u][t];
-              if (affine) {
-                v.x = fmaf(sc[t].x, v.x, sh[t].x); v.y = fmaf(sc[t].y, v.y, sh[t].y);
-                v.z = fmaf(sc[t].z, v.z, sh[t].z); v.w = fmaf(sc[t].w, v.w, sh[t].w);
-              }
-              if (relu) {
-                v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
-                v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
-              }
-              float4 a = *reinterpret_cast<float4*>(wr + 4 * c4);
-              a.x = fmaf(gv, v.x, a.x); a.y = fmaf(gv, v.y, a.y); a.z = fmaf(gv, v.z, a.z); a.w = fmaf(gv, v.w, a.w);
-              *reinterpret_cast<float4*>(wr + 4 * c4) = a;
+              for (int t = 0; t < NT; ++t) acc[u][t] = fmaf(gu, row[32 * t], acc[u][t]);
             }
           }
         }
       }
+      if (p1 > w_hi) break;     // this destination continues in the next window
+      ++n;
+    }
+    n_cur = n;
+  }
+  cp_async_wait<0>();
+  float* p = part + (size_t)blockIdx.x * D * KW;
+#pragma unroll
+  for (int u = 0; u < NF; ++u) {
+    const int f = warp * NF + u;
+    if (f < D) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int k = lane + 32 * t;
+        if (k < KW) p[(size_t)f * KW + k] = k < kw ? acc[u][t] : 0.f;
+      }
     }
   }
-  __syncthreads();
-  float* p = part + (size_t)blockIdx.x * D * KW;
-  for (int i = threadIdx.x; i < D * KW; i += blockDim.x) p[i] = dW_s[i];
-  if (slice == 0)
-    for (int i = threadIdx.x; i < D; i += blockDim.x) part_b[(size_t)(blockIdx.x / kslices) * D + i] = db_s[i];
+  if (slice == 0 && f_ok) part_b[(size_t)group * D + f_l] = db_acc;
 }
 
 // fold the per-CTA partials in CTA order: dW[f][k0+k] = sum_c part[c*kslices+slice][f][k]
@@ -195,15 +288,14 @@ __global__ void amax_bwd_dw_fold_kernel(const float* __restrict__ part, const fl
 
 using namespace mrg;
 
+static inline int dw_kslices(int D) { return D > 208 ? 2 : 1; }
 static inline int dw_kw(int D, int ks) { return ((D + ks - 1) / ks + 3) / 4 * 4; }
-static inline int dw_kslices(int D) {
-  int ks = 1;
-  while ((size_t)D * dw_kw(D, ks) * 4 > 190 * 1024) ++ks;
-  return ks;
-}
 static inline int dw_grid(int D) {
   const int ks = dw_kslices(D);
   return kNumSMs / ks * ks;
+}
+static inline size_t dw_smem(int KW) {
+  return ((size_t)kDwStages * kDwCap * KW + 32) * 4 + (size_t)kDwStages * kDwCap * 4 + 2 * (size_t)KW * 4;
 }
 
 extern "C" size_t mrg_amax_bwd_workspace_bytes(int32_t D) {
@@ -248,18 +340,19 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
     const int ks = dw_kslices(D), KW = dw_kw(D, ks), grid = dw_grid(D);
     float* part = (float*)workspace;
     float* part_b = part + (size_t)grid * D * KW;
-    const size_t smem = ((size_t)D * KW + (size_t)D) * 4;
-    const int nt = (KW / 4 + 31) / 32;
-#define LDW(NT)                                                                                               \
-  do {                                                                                                        \
-    if (smem > 48 * 1024) {                                                                                   \
-      e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw smem attr");                                     \
-    }                                                                                                         \
-    amax_bwd_dw_kernel<NT><<<grid, kBwdThreads, smem, st>>>(g, arg, x, N, D, KW, ks, part, part_b);               \
+    const size_t smem = dw_smem(KW);
+    const int nf = (D + kDwWarps - 1) / kDwWarps, nt = (KW + 31) / 32;
+#define LDW(NF, NT)                                                                                               \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw smem attr");                                           \
+    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, arg, x, csr_ptr, csr_eid, N, E, D, KW, ks, part, \
+                                                               part_b);                                           \
   } while (0)
-    if (nt <= 1) LDW(1);
-    else LDW(2);
+    if (nf <= 4 && nt <= 2) LDW(4, 2);
+    else if (nf <= 8 && nt <= 4) LDW(8, 4);
+    else if (nf <= 13 && nt <= 7) LDW(13, 7);
+    else LDW(16, 4);
 #undef LDW
     const int n = D * D + D;
     amax_bwd_dw_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, part_b, grid, ks, D, KW, dW, db);

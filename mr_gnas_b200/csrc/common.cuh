@@ -42,6 +42,25 @@ inline int stats_grid(int64_t rows) {
   return (int)(need < kMaxParts ? need : kMaxParts);
 }
 
+// Persistent row kernels walk rows with stride gridDim*warps and assume every CTA is resident: a grid larger
+// than (resident CTAs per SM) x SMs runs in waves and the last, partial wave costs a full pass (measured:
+// 592 CTAs at 3 resident/SM = 444 + 148 -> 1.5x the time).  Cap the grid at what is co-resident.
+template <typename K>
+inline int resident_grid(K kernel, size_t smem, int want, int threads = kThreads) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  const int g = occ * kNumSMs;
+  return want < g ? want : g;
+}
+// per-CTA partial buffers are sized for stats_grid(rows) parts: zero the slots a capped grid does not write
+inline void zero_unwritten_parts(double* parts, int grid, int nparts, size_t doubles_per_part, cudaStream_t st) {
+  if (parts && grid < nparts)
+    cudaMemsetAsync(parts + (size_t)grid * doubles_per_part, 0, (size_t)(nparts - grid) * doubles_per_part * sizeof(double), st);
+}
+
 // dispatch on NV (float4 groups per lane)
 #define MRG_DISPATCH_NV(D, ...)                      \
   do {                                               \
@@ -65,6 +84,21 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w));
 }
+
+// One row of a streamed [rows, D] matrix held in registers.  Persistent row kernels keep the NEXT row's loads in
+// flight while the current row is processed (ncu: with one row per warp in flight the gate kernels sat at
+// 2.6 TB/s on long-scoreboard stalls; bytes in flight per SM were ~19 KB against the ~40 KB HBM3e needs).
+template <int NV>
+struct RowBuf {
+  float4 v[NV];
+  __device__ __forceinline__ void load(const float* __restrict__ base, int64_t row, int D, int D4, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = lane + 32 * k;
+      if (c4 < D4) v[k] = ld_stream4(base + (size_t)row * D + 4 * c4);
+    }
+  }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -36,18 +36,43 @@ __global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const float* __re
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   ColStats<NV> cs;
   if (STATS) cs.init(smem_d, D, D4);
-  for (int64_t row = warp0; row < rows; row += nwarps) {
-    const int64_t hi = h_idx ? (int64_t)__ldg(h_idx + row) : row;
-    const int64_t ri = r_idx ? (int64_t)__ldg(r_idx + row) : row;
-    const float* hp = h + hi * D;
-    const float* rp = r + ri * D;
-    float4 a[NV], b[NV];
+  // software pipeline: indices two rows ahead, gathered rows one row ahead of the row being written
+  auto idx_of = [&](int64_t row, int64_t& hi, int64_t& ri) {
+    hi = row < rows ? (h_idx ? (int64_t)__ldg(h_idx + row) : row) : 0;
+    ri = row < rows ? (r_idx ? (int64_t)__ldg(r_idx + row) : row) : 0;
+  };
+  int64_t hi1, ri1, hi2, ri2;
+  idx_of(warp0, hi1, ri1);
+  idx_of(warp0 + nwarps, hi2, ri2);
+  float4 na[NV], nb[NV];
+  if (warp0 < rows) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       int c4 = lane + 32 * v;
       if (c4 < D4) {
-        a[v] = ldg4(hp + 4 * c4);
-        b[v] = ldg4(rp + 4 * c4);
+        na[v] = ldg4(h + hi1 * D + 4 * c4);
+        nb[v] = ldg4(r + ri1 * D + 4 * c4);
+      }
+    }
+  }
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    float4 a[NV], b[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      a[v] = na[v];
+      b[v] = nb[v];
+    }
+    hi1 = hi2;
+    ri1 = ri2;
+    idx_of(row + 2 * nwarps, hi2, ri2);
+    if (row + nwarps < rows) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        int c4 = lane + 32 * v;
+        if (c4 < D4) {
+          na[v] = ldg4(h + hi1 * D + 4 * c4);
+          nb[v] = ldg4(r + ri1 * D + 4 * c4);
+        }
       }
     }
 #pragma unroll
@@ -114,11 +139,15 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(mrg_act x, int64_t r
   ax.init(x, lane, D4);
   ColStats<NV> cs;
   cs.init(smem_d, D, D4);
+  RowBuf<NV> nx;
+  if (warp0 < rows) nx.load(x.data, warp0, D, D4, lane);
   for (int64_t row = warp0; row < rows; row += nwarps) {
+    const RowBuf<NV> cx = nx;
+    if (row + nwarps < rows) nx.load(x.data, row + nwarps, D, D4, lane);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       int c4 = lane + 32 * v;
-      if (c4 < D4) cs.add_sq(ax.apply(ld_stream4(x.data + (size_t)row * D + 4 * c4), v), v);
+      if (c4 < D4) cs.add_sq(ax.apply(cx.v[v], v), v);
     }
     cs.row_done(D, D4);
   }
@@ -208,14 +237,23 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
   ay.init(y, lane, D4);
   ColStats<NV> cs;
   cs.init(smem_d, D, D4);
+  RowBuf<NV> ny, ng;
+  if (warp0 < rows) {
+    ny.load(y.data, warp0, D, D4, lane);
+    ng.load(ds, warp0, D, D4, lane);
+  }
   for (int64_t row = warp0; row < rows; row += nwarps) {
+    const RowBuf<NV> cy = ny, cg = ng;
+    if (row + nwarps < rows) {
+      ny.load(y.data, row + nwarps, D, D4, lane);
+      ng.load(ds, row + nwarps, D, D4, lane);
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       int c4 = lane + 32 * v;
       if (c4 < D4) {
-        const size_t off = (size_t)row * D + 4 * c4;
-        float4 yv = ld_stream4(y.data + off);
-        float4 g = ld_stream4(ds + off);
+        float4 yv = cy.v[v];
+        float4 g = cg.v[v];
         if (ay.relu) {
           float4 s = ay.apply(yv, v);
           g.x = s.x > 0.f ? g.x : 0.f;
@@ -272,14 +310,35 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
       c2[v] = ldg4(coef + 2 * D + 4 * c4);
     }
   }
-  for (int64_t row = warp0; row < rows; row += nwarps) {
+  // ds may alias dy: a row is only ever touched by the warp that owns it, and it is read before it is written
+  float4 ny[NV], ng[NV];
+  auto fetch = [&](int64_t row) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       int c4 = lane + 32 * v;
       if (c4 < D4) {
         const size_t off = (size_t)row * D + 4 * c4;
-        float4 yv = ld_stream4(y.data + off);
-        float4 g = *reinterpret_cast<const float4*>(ds + off);  // may alias dy
+        ny[v] = ld_stream4(y.data + off);
+        ng[v] = *reinterpret_cast<const float4*>(ds + off);
+      }
+    }
+  };
+  if (warp0 < rows) fetch(warp0);
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    float4 cy[NV], cg[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      cy[v] = ny[v];
+      cg[v] = ng[v];
+    }
+    if (row + nwarps < rows) fetch(row + nwarps);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        const size_t off = (size_t)row * D + 4 * c4;
+        float4 yv = cy[v];
+        float4 g = cg[v];
         if (ay.relu) {
           float4 s = ay.apply(yv, v);
           g.x = s.x > 0.f ? g.x : 0.f;
@@ -333,7 +392,17 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_fwd_kernel(mrg_act x, mr
   ColStats<NV> cs;
   if (STATS) cs.init(smem_d, D, D4);
   __syncthreads();
+  RowBuf<NV> nx, ni;
+  if (warp0 < rows) {
+    nx.load(x.data, warp0, D, D4, lane);
+    if (HAS_IN && !SAME) ni.load(xin.data, warp0, D, D4, lane);
+  }
   for (int64_t row = warp0; row < rows; row += nwarps) {
+    const RowBuf<NV> cx = nx, ci = ni;
+    if (row + nwarps < rows) {
+      nx.load(x.data, row + nwarps, D, D4, lane);
+      if (HAS_IN && !SAME) ni.load(xin.data, row + nwarps, D, D4, lane);
+    }
     float4 xv[NV];
     float dot = 0.f;
 #pragma unroll
@@ -341,10 +410,9 @@ __global__ void __launch_bounds__(kThreads) sparse_gate_fwd_kernel(mrg_act x, mr
       int c4 = lane + 32 * v;
       xv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c4 < D4) {
-        const size_t off = (size_t)row * D + 4 * c4;
-        const float4 raw = ld_stream4(x.data + off);
+        const float4 raw = cx.v[v];
         float4 rin;
-        if (HAS_IN && !SAME) rin = ld_stream4(xin.data + off);
+        if (HAS_IN && !SAME) rin = ci.v[v];
         xv[v] = ax.apply(raw, c4);
         const float4 a = *reinterpret_cast<const float4*>(w1 + 4 * c4);
         dot += xv[v].x * a.x + xv[v].y * a.y + xv[v].z * a.z + xv[v].w * a.w;
@@ -733,11 +801,13 @@ extern "C" int mrg_compose_fwd(const float* h, const int32_t* h_idx, const float
   MRG_CHECK_ARG(comp >= 0 && comp <= 2, "compose_fwd: comp");
   if (rows <= 0 && !stats) return MRG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(rows);
+  const int want = stats_grid(rows);
   const size_t sm = stats ? stats_smem(D) : 0;
 #define L(COMP)                                                                                              \
-  MRG_DISPATCH_NV(D, if (stats) compose_fwd_kernel<NV, COMP, true><<<grid, kThreads, sm, st>>>(h, h_idx, r, r_idx, rows, D, y, stats); \
-                  else compose_fwd_kernel<NV, COMP, false><<<grid, kThreads, 0, st>>>(h, h_idx, r, r_idx, rows, D, y, stats))
+  MRG_DISPATCH_NV(D, if (stats) { const int grid = resident_grid(compose_fwd_kernel<NV, COMP, true>, sm, want); \
+                    compose_fwd_kernel<NV, COMP, true><<<grid, kThreads, sm, st>>>(h, h_idx, r, r_idx, rows, D, y, stats); \
+                    zero_unwritten_parts(stats, grid, want, 2 * (size_t)D, st); } \
+                  else compose_fwd_kernel<NV, COMP, false><<<resident_grid(compose_fwd_kernel<NV, COMP, false>, 0, want), kThreads, 0, st>>>(h, h_idx, r, r_idx, rows, D, y, stats))
   if (comp == MRG_COMP_SUB) L(MRG_COMP_SUB);
   else if (comp == MRG_COMP_MULT) L(MRG_COMP_MULT);
   else L(MRG_COMP_ADD);
@@ -753,10 +823,12 @@ extern "C" int mrg_compose_bwd_rows(const float* dy, const float* x, const float
   MRG_CHECK_ARG(comp != MRG_COMP_MULT || (x && r), "compose_bwd_rows: mult needs x and r");
   if (rows <= 0) return MRG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(rows);
-  if (comp == MRG_COMP_SUB) MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, MRG_COMP_SUB><<<grid, kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr));
-  else if (comp == MRG_COMP_MULT) MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, MRG_COMP_MULT><<<grid, kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr));
-  else MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, MRG_COMP_ADD><<<grid, kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr));
+  const int want = stats_grid(rows);
+#define L(COMP) MRG_DISPATCH_NV(D, compose_bwd_rows_kernel<NV, COMP><<<resident_grid(compose_bwd_rows_kernel<NV, COMP>, 0, want), kThreads, 0, st>>>(dy, x, r, rows, D, dx, dr))
+  if (comp == MRG_COMP_SUB) L(MRG_COMP_SUB);
+  else if (comp == MRG_COMP_MULT) L(MRG_COMP_MULT);
+  else L(MRG_COMP_ADD);
+#undef L
   MRG_LAUNCH_CHECK("compose_bwd_rows");
   return MRG_OK;
 }
@@ -765,8 +837,10 @@ extern "C" int mrg_colstats(mrg_act x, int64_t rows, int32_t D, double* stats, v
   MRG_CHECK_ARG(x.data && stats, "colstats: null pointer");
   MRG_CHECK_ARG(valid_D(D), "colstats: D");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(rows);
-  MRG_DISPATCH_NV(D, colstats_kernel<NV><<<grid, kThreads, stats_smem(D), st>>>(x, rows, D, stats));
+  const int want = stats_grid(rows);
+  MRG_DISPATCH_NV(D, { const int grid = resident_grid(colstats_kernel<NV>, stats_smem(D), want);
+                       colstats_kernel<NV><<<grid, kThreads, stats_smem(D), st>>>(x, rows, D, stats);
+                       zero_unwritten_parts(stats, grid, want, 2 * (size_t)D, st); });
   MRG_LAUNCH_CHECK("colstats");
   return MRG_OK;
 }
@@ -787,7 +861,7 @@ extern "C" int mrg_affine_act(mrg_act x, int64_t rows, int32_t D, float* out, vo
   MRG_CHECK_ARG(x.data && out, "affine_act: null pointer");
   MRG_CHECK_ARG(valid_D(D), "affine_act: D");
   if (rows <= 0) return MRG_OK;
-  MRG_DISPATCH_NV(D, affine_act_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(x, rows, D, out));
+  MRG_DISPATCH_NV(D, affine_act_kernel<NV><<<resident_grid(affine_act_kernel<NV>, 0, stats_grid(rows)), kThreads, 0, (cudaStream_t)stream>>>(x, rows, D, out));
   MRG_LAUNCH_CHECK("affine_act");
   return MRG_OK;
 }
@@ -796,8 +870,10 @@ extern "C" int mrg_bn_bwd_reduce(const float* ds, mrg_act y, int64_t rows, int32
                                  void* stream) {
   MRG_CHECK_ARG(ds && y.data && bwd_stats, "bn_bwd_reduce: null pointer");
   MRG_CHECK_ARG(valid_D(D), "bn_bwd_reduce: D");
-  MRG_DISPATCH_NV(D, bn_bwd_reduce_kernel<NV><<<stats_grid(rows), kThreads, stats_smem(D), (cudaStream_t)stream>>>(
-                         ds, y, rows, D, bwd_stats));
+  const int want = stats_grid(rows);
+  MRG_DISPATCH_NV(D, { const int grid = resident_grid(bn_bwd_reduce_kernel<NV>, stats_smem(D), want);
+                       bn_bwd_reduce_kernel<NV><<<grid, kThreads, stats_smem(D), (cudaStream_t)stream>>>(ds, y, rows, D, bwd_stats);
+                       zero_unwritten_parts(bwd_stats, grid, want, 2 * (size_t)D, (cudaStream_t)stream); });
   MRG_LAUNCH_CHECK("bn_bwd_reduce");
   return MRG_OK;
 }
@@ -817,7 +893,7 @@ extern "C" int mrg_bn_bwd_apply(const float* ds, mrg_act y, const float* coef, i
   MRG_CHECK_ARG(ds && y.data && coef && dy, "bn_bwd_apply: null pointer");
   MRG_CHECK_ARG(valid_D(D), "bn_bwd_apply: D");
   if (rows <= 0) return MRG_OK;
-  MRG_DISPATCH_NV(D, bn_bwd_apply_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(
+  MRG_DISPATCH_NV(D, bn_bwd_apply_kernel<NV><<<resident_grid(bn_bwd_apply_kernel<NV>, 0, stats_grid(rows)), kThreads, 0, (cudaStream_t)stream>>>(
                          ds, y, coef, rows, D, dy, accumulate));
   MRG_LAUNCH_CHECK("bn_bwd_apply");
   return MRG_OK;
@@ -830,10 +906,13 @@ extern "C" int mrg_sparse_gate_fwd(mrg_act x, mrg_act xin, int64_t rows, int32_t
   MRG_CHECK_ARG(valid_D(D), "sparse_gate_fwd: D");
   MRG_CHECK_ARG(!xin.data || v2, "sparse_gate_fwd: xin needs v2");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(rows);
+  const int want = stats_grid(rows);
   const bool has_in = xin.data != nullptr, same = has_in && xin.data == x.data;
-#define L(HI, SM_, ST_) do { MRG_SMEM_OPTIN((sparse_gate_fwd_kernel<NV, HI, SM_, ST_>), gate_smem(D)); sparse_gate_fwd_kernel<NV, HI, SM_, ST_><<<grid, kThreads, gate_smem(D), st>>>( \
-      x, xin, rows, D, v1, v2, c, row_scale, base_scale, y, gate, stats); } while (0)
+#define L(HI, SM_, ST_) do { MRG_SMEM_OPTIN((sparse_gate_fwd_kernel<NV, HI, SM_, ST_>), gate_smem(D)); \
+      const int grid = resident_grid(sparse_gate_fwd_kernel<NV, HI, SM_, ST_>, gate_smem(D), want); \
+      sparse_gate_fwd_kernel<NV, HI, SM_, ST_><<<grid, kThreads, gate_smem(D), st>>>( \
+      x, xin, rows, D, v1, v2, c, row_scale, base_scale, y, gate, stats); \
+      if (ST_) zero_unwritten_parts(stats, grid, want, 2 * (size_t)D, st); } while (0)
   MRG_DISPATCH_NV(D, if (stats) { if (!has_in) L(false, false, true); else if (same) L(true, true, true); else L(true, false, true); }
                      else { if (!has_in) L(false, false, false); else if (same) L(true, true, false); else L(true, false, false); });
 #undef L
@@ -850,11 +929,14 @@ extern "C" int mrg_sparse_gate_bwd(const float* dy, mrg_act x, mrg_act xin, cons
   MRG_CHECK_ARG(dy && x.data && gate && v1 && dparam, "sparse_gate_bwd: null pointer");
   MRG_CHECK_ARG(valid_D(D), "sparse_gate_bwd: D");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(rows);
+  const int want = stats_grid(rows);
   const bool has_in = xin.data != nullptr;
   const bool same = has_in && xin.data == x.data && dxin == dx;
-#define L(HI, SM_) do { MRG_SMEM_OPTIN((sparse_gate_bwd_kernel<NV, HI, SM_>), gate_smem(D)); sparse_gate_bwd_kernel<NV, HI, SM_><<<grid, kThreads, gate_smem(D), st>>>( \
-      dy, x, xin, gate, rows, D, v1, v2, row_scale, base_scale, dx, dxin, accumulate, dparam); } while (0)
+#define L(HI, SM_) do { MRG_SMEM_OPTIN((sparse_gate_bwd_kernel<NV, HI, SM_>), gate_smem(D)); \
+      const int grid = resident_grid(sparse_gate_bwd_kernel<NV, HI, SM_>, gate_smem(D), want); \
+      sparse_gate_bwd_kernel<NV, HI, SM_><<<grid, kThreads, gate_smem(D), st>>>( \
+      dy, x, xin, gate, rows, D, v1, v2, row_scale, base_scale, dx, dxin, accumulate, dparam); \
+      zero_unwritten_parts(dparam, grid, want, 2 * (size_t)D + 1, st); } while (0)
   MRG_DISPATCH_NV(D, if (!has_in) L(false, false); else if (same) L(true, true); else L(true, false));
 #undef L
   MRG_LAUNCH_CHECK("sparse_gate_bwd");
@@ -877,9 +959,11 @@ extern "C" int mrg_dense_gate_fwd(const float* z, mrg_act x, int64_t rows, int32
   MRG_CHECK_ARG(!use_sigmoid || x.data, "dense_gate_fwd: sigmoid form needs x");
   MRG_CHECK_ARG(valid_D(D), "dense_gate_fwd: D");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(rows);
-  MRG_DISPATCH_NV(D, if (stats) dense_gate_fwd_kernel<NV, true><<<grid, kThreads, stats_smem(D), st>>>(z, x, rows, D, use_sigmoid, row_scale, base_scale, y, stats);
-                     else dense_gate_fwd_kernel<NV, false><<<grid, kThreads, 0, st>>>(z, x, rows, D, use_sigmoid, row_scale, base_scale, y, stats));
+  const int want = stats_grid(rows);
+  MRG_DISPATCH_NV(D, if (stats) { const int grid = resident_grid(dense_gate_fwd_kernel<NV, true>, stats_smem(D), want);
+                       dense_gate_fwd_kernel<NV, true><<<grid, kThreads, stats_smem(D), st>>>(z, x, rows, D, use_sigmoid, row_scale, base_scale, y, stats);
+                       zero_unwritten_parts(stats, grid, want, 2 * (size_t)D, st); }
+                     else dense_gate_fwd_kernel<NV, false><<<resident_grid(dense_gate_fwd_kernel<NV, false>, 0, want), kThreads, 0, st>>>(z, x, rows, D, use_sigmoid, row_scale, base_scale, y, stats));
   MRG_LAUNCH_CHECK("dense_gate_fwd");
   return MRG_OK;
 }
@@ -891,7 +975,7 @@ extern "C" int mrg_dense_gate_bwd(const float* dy, const float* z, mrg_act x, in
   MRG_CHECK_ARG(!use_sigmoid || (x.data && z), "dense_gate_bwd: sigmoid form needs x and z");
   MRG_CHECK_ARG(valid_D(D), "dense_gate_bwd: D");
   if (rows <= 0) return MRG_OK;
-  MRG_DISPATCH_NV(D, dense_gate_bwd_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(
+  MRG_DISPATCH_NV(D, dense_gate_bwd_kernel<NV><<<resident_grid(dense_gate_bwd_kernel<NV>, 0, stats_grid(rows)), kThreads, 0, (cudaStream_t)stream>>>(
                          dy, z, x, rows, D, use_sigmoid, row_scale, base_scale, dz, dx, accumulate));
   MRG_LAUNCH_CHECK("dense_gate_bwd");
   return MRG_OK;
@@ -928,7 +1012,7 @@ extern "C" int mrg_mixed_sum_fwd(mrg_act_list ys, const float* w, int64_t rows, 
   MRG_CHECK_ARG(valid_D(D), "mixed_sum_fwd: D");
   for (int k = 0; k < ys.n; ++k) MRG_CHECK_ARG(ys.acts[k].data, "mixed_sum_fwd: null candidate");
   if (rows <= 0) return MRG_OK;
-  MRG_DISPATCH_NV(D, mixed_sum_kernel<NV><<<stats_grid(rows), kThreads, 0, (cudaStream_t)stream>>>(ys, w, rows, D, out));
+  MRG_DISPATCH_NV(D, mixed_sum_kernel<NV><<<resident_grid(mixed_sum_kernel<NV>, 0, stats_grid(rows)), kThreads, 0, (cudaStream_t)stream>>>(ys, w, rows, D, out));
   MRG_LAUNCH_CHECK("mixed_sum_fwd");
   return MRG_OK;
 }

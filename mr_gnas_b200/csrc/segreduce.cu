@@ -356,13 +356,13 @@ extern "C" int mrg_seg_reduce_fwd(int32_t kind, mrg_act m, const int32_t* ptr, c
   cudaStream_t st = (cudaStream_t)stream;
   float* pval = (float*)workspace;
   int32_t* parg = (int32_t*)(pval + (size_t)max_chunks * D);
-  const int grid_c = stats_grid(max_chunks);
+  const int want_c = stats_grid(max_chunks);
   const int grid_s = (int)(nseg < 4 * kMaxParts ? nseg : 4 * kMaxParts);
   const size_t comb_smem = (size_t)kWarpsPerBlock * D * 8;
 #define L(KIND)                                                                                                   \
   MRG_DISPATCH_NV(D, {                                                                                            \
-    if (mul) seg_reduce_chunk_kernel<NV, KIND, true><<<grid_c, kThreads, 0, st>>>(m, ptr, idx, chunk_first, chunk_seg, nseg, D, mul, mul_idx, alpha, residual, accumulate, out, arg, pval, parg); \
-    else seg_reduce_chunk_kernel<NV, KIND, false><<<grid_c, kThreads, 0, st>>>(m, ptr, idx, chunk_first, chunk_seg, nseg, D, mul, mul_idx, alpha, residual, accumulate, out, arg, pval, parg); \
+    if (mul) seg_reduce_chunk_kernel<NV, KIND, true><<<resident_grid(seg_reduce_chunk_kernel<NV, KIND, true>, 0, want_c), kThreads, 0, st>>>(m, ptr, idx, chunk_first, chunk_seg, nseg, D, mul, mul_idx, alpha, residual, accumulate, out, arg, pval, parg); \
+    else seg_reduce_chunk_kernel<NV, KIND, false><<<resident_grid(seg_reduce_chunk_kernel<NV, KIND, false>, 0, want_c), kThreads, 0, st>>>(m, ptr, idx, chunk_first, chunk_seg, nseg, D, mul, mul_idx, alpha, residual, accumulate, out, arg, pval, parg); \
     seg_reduce_combine_kernel<NV, KIND><<<grid_s, kThreads, comb_smem, st>>>(m, ptr, chunk_first, nseg, D, alpha, residual, accumulate, out, arg, pval, parg); \
   })
   if (kind == MRG_RED_SUM) L(MRG_RED_SUM);
@@ -384,10 +384,12 @@ extern "C" int mrg_seg_reduce_bwd(int32_t kind, const float* g, const int32_t* a
   MRG_CHECK_ARG(kind == MRG_RED_SUM || kind == MRG_RED_MEAN || kind == MRG_RED_MAX, "seg_reduce_bwd: kind");
   if (E + n_self <= 0) return MRG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stats_grid(E + n_self);
+  const int want = stats_grid(E + n_self);
+#define grid resident_grid(seg_reduce_bwd_kernel<NV, MRG_RED_SUM>, 0, want)
   if (kind == MRG_RED_SUM) MRG_DISPATCH_NV(D, seg_reduce_bwd_kernel<NV, MRG_RED_SUM><<<grid, kThreads, 0, st>>>(g, arg, m, dst, ptr, E, n_self, D, dm, accumulate));
   else if (kind == MRG_RED_MEAN) MRG_DISPATCH_NV(D, seg_reduce_bwd_kernel<NV, MRG_RED_MEAN><<<grid, kThreads, 0, st>>>(g, arg, m, dst, ptr, E, n_self, D, dm, accumulate));
   else MRG_DISPATCH_NV(D, seg_reduce_bwd_kernel<NV, MRG_RED_MAX><<<grid, kThreads, 0, st>>>(g, arg, m, dst, ptr, E, n_self, D, dm, accumulate));
+#undef grid
   MRG_LAUNCH_CHECK("seg_reduce_bwd");
   return MRG_OK;
 }

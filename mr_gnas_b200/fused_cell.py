@@ -180,18 +180,33 @@ class EdgeChain(torch.autograd.Function):
         bounds = [(0, E // 2), (E // 2, E), (E, M)]
         norm = g.norm()
         lib = _lib.load()
+        fused_bwd = bool(lib.mrg_sparse_gate_bwd_fused_supported(D))
+        # pending gradient contributions per edge-level state: when the LAST one is the dx of a fused gate
+        # backward, that kernel also emits the state's BN-backward column sums (BST) and no reduce pass runs
+        pending = {}
+        for node, om, i in aggs:
+            pending[i] = pending.get(i, 0) + 1
+        for node, om, i in gates:
+            pending[i] = pending.get(i, 0) + 1
+            if i != 1:
+                pending[1] = pending.get(1, 0) + 1
+        for node, om, i in aggs:
+            pending[i] -= 1
+        BST = {}
 
-        def bn_backward(k):
-            """ds_k -> dy_k in place; returns (dgamma, dbeta)."""
+        def bn_coef(k):
+            """BN backward statistics of state k -> (dgamma, dbeta), coef [3,D] (None: no BN after this op)."""
             aff, gamma, beta = BN[k]
-            ds = DS[k]
             if aff is None:
-                return torch.zeros_like(gamma), torch.zeros_like(beta)
+                return (torch.zeros_like(gamma), torch.zeros_like(beta)), None
             a, b, mean, invstd = aff
-            yv = act(Y[k], a, b, True)
-            nparts = K.stats_nparts(M)
-            bst = K._stats_buf(nparts, D, dev)
-            call("mrg_bn_bwd_reduce", ptr(ds), yv, M, D, ptr(bst), stream(), nbytes=2 * M * 4 * D)
+            if k in BST:
+                bst, nparts = BST.pop(k)
+            else:
+                nparts = K.stats_nparts(M)
+                bst = K._stats_buf(nparts, D, dev)
+                call("mrg_bn_bwd_reduce", ptr(DS[k]), act(Y[k], a, b, True), M, D, ptr(bst), stream(),
+                     nbytes=2 * M * 4 * D)
             dgamma = torch.empty(D, dtype=torch.float32, device=dev)
             dbeta = torch.empty_like(dgamma)
             coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
@@ -199,14 +214,23 @@ class EdgeChain(torch.autograd.Function):
                  ptr(dbeta), ptr(coef), stream())
             if not training:
                 coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
-            call("mrg_bn_bwd_apply", ptr(ds), yv, ptr(coef), M, D, ptr(ds), 0, stream(), nbytes=3 * M * 4 * D)
-            return dgamma, dbeta
+            return (dgamma, dbeta), coef
+
+        def bn_apply(k, coef):
+            """ds_k -> dy_k in place (only where no fused consumer reads the gradient lazily)."""
+            if coef is None:
+                return
+            aff = BN[k][0]
+            call("mrg_bn_bwd_apply", ptr(DS[k]), act(Y[k], aff[0], aff[1], True), ptr(coef), M, D, ptr(DS[k]), 0,
+                 stream(), nbytes=3 * M * 4 * D)
 
         # ---- gates in reverse order
         for node, om, i in reversed(gates):
             if node not in DS:       # state never consumed (dead branch): zero gradient
                 DS[node] = torch.zeros(M, D, dtype=torch.float32, device=dev)
-            grads[('bn', node)] = bn_backward(node)
+            grads[('bn', node)], coef = bn_coef(node)
+            if not fused_bwd:
+                bn_apply(node, coef)
             dy = DS.pop(node)
             v1, v2, c = gate_params[node]
             same = i == 1
@@ -218,22 +242,42 @@ class EdgeChain(torch.autograd.Function):
             accum = (0 if fresh_x else 1) | (0 if (fresh_in or same) else 2)
             dv1, dv2 = torch.empty_like(v1), torch.empty_like(v2)
             dc = torch.empty(3, dtype=torch.float32, device=dev)
+            last_for_x = fused_bwd and pending[i] == 1 and BN[i][0] is not None
+            if last_for_x:
+                nparts = [K.stats_nparts(hi - lo) for lo, hi in bounds]
+                xst = K._stats_buf(sum(nparts), D, dev)
+                BST[i] = (xst, sum(nparts))
+            off = 0
+            aff_k = BN[node][0]
             for s_, (lo, hi) in enumerate(bounds):
                 n = hi - lo
                 rs = norm[lo:] if lo < E else None
                 dparam = torch.empty(int(lib.mrg_gate_dparam_count(n, D)), dtype=torch.float64, device=dev)
-                call("mrg_sparse_gate_bwd", ptr(dy[lo:hi]), view(i, lo, hi), view(1, lo, hi), ptr(GATE[node][lo:hi]), n, D,
-                     ptr(v1[s_]), ptr(v2[s_]), ptr(rs), 1.0 / 3.0, ptr(DS[i][lo:hi]), ptr(DS[1][lo:hi]), accum,
-                     ptr(dparam), stream(),
-                     nbytes=n * (4 * D * ((2 if same else 3) + (1 if same else 2) + bin(accum).count("1")) + 8))
+                n_in = (2 if same else 3) + bin(accum).count("1")
+                if fused_bwd:
+                    yk = act(Y[node][lo:hi], aff_k[0], aff_k[1], True) if coef is not None else None
+                    call("mrg_sparse_gate_bwd_fused", _lib.grad(dy[lo:hi], yk, coef), view(i, lo, hi), view(1, lo, hi),
+                         ptr(GATE[node][lo:hi]), n, D, ptr(v1[s_]), ptr(v2[s_]), ptr(rs), 1.0 / 3.0, ptr(DS[i][lo:hi]),
+                         ptr(DS[1][lo:hi]), accum, ptr(dparam), ptr(xst[off * 2 * D:]) if last_for_x else None, stream(),
+                         nbytes=n * (4 * D * (n_in + (1 if coef is not None else 0) + (1 if same else 2)) + 8))
+                    if last_for_x:
+                        off += nparts[s_]
+                else:
+                    call("mrg_sparse_gate_bwd", ptr(dy[lo:hi]), view(i, lo, hi), view(1, lo, hi), ptr(GATE[node][lo:hi]),
+                         n, D, ptr(v1[s_]), ptr(v2[s_]), ptr(rs), 1.0 / 3.0, ptr(DS[i][lo:hi]), ptr(DS[1][lo:hi]),
+                         accum, ptr(dparam), stream(), nbytes=n * (4 * D * (n_in + (1 if same else 2)) + 8))
                 call("mrg_sparse_gate_bwd_finalize", ptr(dparam), n, D, ptr(dv1[s_]), ptr(dv2[s_]), ptr(dc[s_:s_ + 1]),
                      stream())
+            pending[i] -= 1
+            if not same:
+                pending[1] -= 1
             grads[('gate', node)] = (dv1, dv2, dc)
             del dy
         # ---- node 1: BN backward, then the gather/compose backward
         if 1 not in DS:
             DS[1] = torch.zeros(M, D, dtype=torch.float32, device=dev)
-        grads[('bn', 1)] = bn_backward(1)
+        grads[('bn', 1)], coef1 = bn_coef(1)
+        bn_apply(1, coef1)
         dy1 = DS.pop(1)
         comp = first.op.comp
         dent = drel = None
