@@ -110,16 +110,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// pos[n,f] = dst-CSR position of edge arg[n,f] (edge ids ascend inside a destination), -1 when no gradient flows
+__global__ void amax_pos_kernel(const int32_t* __restrict__ arg, const int32_t* __restrict__ ptr,
+                                const int32_t* __restrict__ eid, int64_t N, int D, int32_t* __restrict__ pos) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  const int64_t n = i / D;
+  const int32_t a = __ldg(arg + i);
+  int32_t r = -1;
+  if (a >= 0) {
+    int32_t l = __ldg(ptr + n), h = __ldg(ptr + n + 1);
+    const int32_t hi = h;
+    while (l < h) {
+      const int32_t mid = (l + h) >> 1;
+      if (__ldg(eid + mid) < a) l = mid + 1; else h = mid;
+    }
+    if (l < hi && __ldg(eid + l) == a) r = l;
+  }
+  pos[i] = r;
+}
+
 template <int NF, int NT>
 __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
-    const float* __restrict__ g, const int32_t* __restrict__ arg, mrg_act x, const int32_t* __restrict__ ptr,
+    const float* __restrict__ g, const int32_t* __restrict__ pos, mrg_act x, const int32_t* __restrict__ ptr,
     const int32_t* __restrict__ eid, int64_t N, int64_t E, int D, int KW, int kslices, float* __restrict__ part,
     float* __restrict__ part_b) {
   extern __shared__ float smem[];
-  // layout: xs[kDwStages][kDwCap][KW] | pad[32] | eids[kDwStages][kDwCap] | sc[KW] | sh[KW]
+  // layout: xs[kDwStages][kDwCap][KW] | pad[32] | sc[KW] | sh[KW]
   float* xs = smem;
-  int32_t* eids = reinterpret_cast<int32_t*>(xs + (size_t)kDwStages * kDwCap * KW + 32);
-  float* sc_s = reinterpret_cast<float*>(eids + kDwStages * kDwCap);
+  float* sc_s = xs + (size_t)kDwStages * kDwCap * KW + 32;
   float* sh_s = sc_s + KW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x % kslices, group = blockIdx.x / kslices, ngroups = gridDim.x / kslices;
@@ -141,8 +160,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[u][t] = 0.f;
   float db_acc = 0.f;
-  const int f_l = warp * NF + lane;                 // the feature whose (arg, g) this lane fetches
+  const int f_l = warp * NF + lane;                 // the feature whose (pos, g) this lane fetches
   const bool f_ok = lane < NF && f_l < D;
+  const float* xs_lane = xs + lane;
 
   auto issue = [&](int b) {   // warp w copies rows w, w+16, ... of window b
     const int64_t w_lo = P0 + (int64_t)b * kDwCap;
@@ -153,7 +173,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
       const float* src = x.data + (size_t)e * D + k0;
       for (int c4 = lane; c4 < kw4; c4 += 32) cp_async16(st + (size_t)r * KW + 4 * c4, src + 4 * c4);
     }
-    if (threadIdx.x < nrows) eids[(b % kDwStages) * kDwCap + threadIdx.x] = __ldg(eid + w_lo + threadIdx.x);
   };
 
   if (nb > 0) issue(0);
@@ -171,17 +190,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     }
     n_cur = lo;
   }
-  int64_t n_pf = -1;          // destination whose (arg, g) were prefetched into a_pf / g_pf
-  int32_t a_pf = -1;
-  float g_pf = 0.f;
+  // (pos, g) of destination n_pf, fetched one destination ahead of use
+  int64_t n_pf = n_cur;
+  int32_t p_pf = f_ok ? __ldg(pos + (size_t)n_pf * D + f_l) : -1;
+  float g_pf = f_ok ? __ldg(g + (size_t)n_pf * D + f_l) : 0.f;
 
   for (int b = 0; b < nb; ++b) {
     cp_async_wait<1>();
     const int64_t w_lo = P0 + (int64_t)b * kDwCap;
     const int64_t w_hi = min(w_lo + kDwCap, P1);
     const int nrows = (int)(w_hi - w_lo);
-    float* st = xs + (size_t)(b % kDwStages) * kDwCap * KW;
+    const int stage_off = (b % kDwStages) * kDwCap * KW;
     if (affine || relu) {     // each thread post-processes exactly the 16-byte pieces it copied
+      float* st = xs + stage_off;
       for (int r = warp; r < nrows; r += kDwWarps)
         for (int c4 = lane; c4 < kw4; c4 += 32) {
           float4 v = *reinterpret_cast<float4*>(st + (size_t)r * KW + 4 * c4);
@@ -200,44 +221,36 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     __syncthreads();          // window b complete for everyone; everyone finished computing window b-1
     if (b + 2 < nb) issue(b + 2);
     cp_async_commit();
-    const int32_t* el = eids + (b % kDwStages) * kDwCap;
+    const float* st_lane = xs_lane + stage_off;
 
     int64_t n = n_cur;
     while (n < N) {
       const int32_t p0 = __ldg(ptr + n), p1 = __ldg(ptr + n + 1);
       if (p0 >= w_hi) break;
       if (p1 > w_lo && p1 > p0) {
-        const int lo = (int)(max((int64_t)p0, w_lo) - w_lo), hi = (int)(min((int64_t)p1, w_hi) - w_lo);
-        int32_t a;
+        int32_t pp;
         float gv;
         if (n == n_pf) {
-          a = a_pf; gv = g_pf;
+          pp = p_pf; gv = g_pf;
         } else {
-          a = f_ok ? __ldg(arg + (size_t)n * D + f_l) : -1;
+          pp = f_ok ? __ldg(pos + (size_t)n * D + f_l) : -1;
           gv = f_ok ? __ldg(g + (size_t)n * D + f_l) : 0.f;
         }
-        if (n + 1 < N) {      // prefetch the next destination's routing while this one is processed
+        if (n + 1 < N && n_pf != n + 1) {   // next destination's routing, in flight while this one is processed
           n_pf = n + 1;
-          a_pf = f_ok ? __ldg(arg + (size_t)(n + 1) * D + f_l) : -1;
+          p_pf = f_ok ? __ldg(pos + (size_t)(n + 1) * D + f_l) : -1;
           g_pf = f_ok ? __ldg(g + (size_t)(n + 1) * D + f_l) : 0.f;
         }
-        int r = -1;
-        if (a >= 0) {
-          int l = lo, h = hi;
-          while (l < h) {
-            const int mid = (l + h) >> 1;
-            if (el[mid] < a) l = mid + 1; else h = mid;
-          }
-          if (l < hi && el[l] == a) r = l;
-        }
+        const int r = (pp >= w_lo && pp < w_hi) ? (int)(pp - w_lo) : -1;
         if (r >= 0) db_acc += gv;
-        if (__any_sync(0xffffffffu, r >= 0)) {
+        const unsigned mask = __ballot_sync(0xffffffffu, r >= 0);
+        if (mask) {
 #pragma unroll
           for (int u = 0; u < NF; ++u) {
-            const int ru = __shfl_sync(0xffffffffu, r, u);
-            const float gu = __shfl_sync(0xffffffffu, gv, u);
-            if (ru >= 0) {      // warp-uniform
-              const float* row = st + (size_t)ru * KW + lane;
+            if (mask & (1u << u)) {      // warp-uniform
+              const int ru = __shfl_sync(0xffffffffu, r, u);
+              const float gu = __shfl_sync(0xffffffffu, gv, u);
+              const float* row = st_lane + ru * KW;
 #pragma unroll
               for (int t = 0; t < NT; ++t) acc[u][t] = fmaf(gu, row[32 * t], acc[u][t]);
             }
@@ -294,13 +307,14 @@ static inline int dw_grid(int D) {
   const int ks = dw_kslices(D);
   return kNumSMs / ks * ks;
 }
-static inline size_t dw_smem(int KW) {
-  return ((size_t)kDwStages * kDwCap * KW + 32) * 4 + (size_t)kDwStages * kDwCap * 4 + 2 * (size_t)KW * 4;
+static inline size_t dw_smem(int KW) { return ((size_t)kDwStages * kDwCap * KW + 32) * 4 + 2 * (size_t)KW * 4; }
+static inline size_t dw_part_bytes(int D) {
+  const int ks = dw_kslices(D), KW = dw_kw(D, ks);
+  return ((size_t)dw_grid(D) * D * KW * sizeof(float) + (size_t)dw_grid(D) * D * sizeof(float) + 255) / 256 * 256;
 }
 
-extern "C" size_t mrg_amax_bwd_workspace_bytes(int32_t D) {
-  const int ks = dw_kslices(D), KW = dw_kw(D, ks);
-  return (size_t)dw_grid(D) * D * KW * sizeof(float) + (size_t)dw_grid(D) * D * sizeof(float) + 256;
+extern "C" size_t mrg_amax_bwd_workspace_bytes(int64_t N, int32_t D) {
+  return dw_part_bytes(D) + (size_t)N * D * sizeof(int32_t) + 256;   // per-CTA dW partials | pos[N,D]
 }
 
 extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,
@@ -310,7 +324,7 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
   MRG_CHECK_ARG(g && arg && x.data && W && csr_ptr && chunk_first && chunk_seg && workspace, "amax_bwd: null pointer");
   MRG_CHECK_ARG(E == 0 || csr_eid, "amax_bwd: null csr_eid");
   MRG_CHECK_ARG(valid_D(D) && D <= 256, "amax_bwd: D must be a multiple of 4 and <= 256");
-  if (workspace_bytes < mrg_amax_bwd_workspace_bytes(D)) {
+  if (workspace_bytes < mrg_amax_bwd_workspace_bytes(N, D)) {
     set_error("amax_bwd: workspace too small");
     return MRG_ERR_WORKSPACE;
   }
@@ -342,11 +356,13 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
     float* part_b = part + (size_t)grid * D * KW;
     const size_t smem = dw_smem(KW);
     const int nf = (D + kDwWarps - 1) / kDwWarps, nt = (KW + 31) / 32;
+    int32_t* pos = (int32_t*)((char*)workspace + dw_part_bytes(D));
+    if (N > 0) amax_pos_kernel<<<(unsigned)((N * D + 255) / 256), 256, 0, st>>>(arg, csr_ptr, csr_eid, N, D, pos);
 #define LDW(NF, NT)                                                                                               \
   do {                                                                                                            \
     e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw smem attr");                                           \
-    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, arg, x, csr_ptr, csr_eid, N, E, D, KW, ks, part, \
+    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, pos, x, csr_ptr, csr_eid, N, E, D, KW, ks, part, \
                                                                part_b);                                           \
   } while (0)
     if (nf <= 4 && nt <= 2) LDW(4, 2);

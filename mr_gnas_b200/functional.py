@@ -372,9 +372,9 @@ def amax_backward(g, gout, arg, x_act, weight, rows, has_residual, need_dx=True,
     D = gout.shape[1]
     dev = gout.device
     E = g.E
-    key = (D, str(dev))
+    key = (g.N, D, str(dev))
     if key not in _bwd_ws:
-        _bwd_ws[key] = torch.empty(int(_lib.load().mrg_amax_bwd_workspace_bytes(D)), dtype=torch.uint8, device=dev)
+        _bwd_ws[key] = torch.empty(int(_lib.load().mrg_amax_bwd_workspace_bytes(g.N, D)), dtype=torch.uint8, device=dev)
     ws = _bwd_ws[key]
     if need_dx and dx is None:
         dx = torch.empty(rows, D, dtype=torch.float32, device=dev)
