@@ -196,6 +196,11 @@ def main():
     ap.add_argument("--ref-downscale", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-call CUDA-event profile here")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying the CUDA graph")
+    ap.add_argument("--partition", action="store_true",
+                    help="N>1: destination-partitioned message passing (halo all-gather, global BatchNorm statistics, "
+                         "entity-sharded scoring) on ONE shared batch -- strong scaling -- instead of the default "
+                         "data parallelism over query batches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -219,31 +224,46 @@ def main():
 
     N, R, T, D, trip = workload(args.workload)
     E, M, B = 2 * T, 2 * T + N, args.batch
-    g = MRGraph.from_triples(N, trip, R, device=dev)
+    part_mode = args.partition and world > 1
+    if part_mode:
+        from mr_gnas_b200.dist import lp_partition
+        g = lp_partition(trip, N, R, rank, world, device=dev)
+    else:
+        g = MRGraph.from_triples(N, trip, R, device=dev)
     torch.manual_seed(0)
     model = Network(dev, README_GENOTYPE, N, R, D, D, 2 * R + 1, nn.BCELoss(), 0.0, model_args(D))
     model.apply(weights_init)
     model = model.to(dev).train()
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     # data-parallel over query batches for N>1: every rank runs full-graph MP on its own batch,
     # parameter gradients are all-reduced (NCCL) -- weak scaling, per-GPU work fixed.
     items = process({'train': trip.tolist(), 'valid': [], 'test': []}, R)['train']
     nb = args.steps + args.warmup
-    rng = np.random.RandomState(100 + rank)
+    rng = np.random.RandomState(100 + (0 if part_mode else rank))
     host_batches = []
     for i in range(min(nb, 8)):
         sel = rng.choice(len(items), size=B, replace=False)
-        host_batches.append(make_batch([items[j] for j in sel], N, lbl_smooth=0.1, pin=True))
+        t_h, y_h = make_batch([items[j] for j in sel], N, lbl_smooth=0.1, pin=True)
+        if part_mode:   # this rank scores its own entity range only: it needs its columns of the label matrix
+            y_h = y_h[:, g.part.lo:g.part.hi].contiguous().pin_memory()
+        host_batches.append((t_h, y_h))
     dev_batches = [(t.to(dev), y.to(dev)) for t, y in host_batches]
     h2d = host_batches[0][0].numel() * 8 + host_batches[0][1].numel() * 4
 
-    from mr_gnas_b200.dist import allreduce_grads as _allreduce
+    from mr_gnas_b200.dist import allreduce_grads as _allreduce, allreduce_grads_sum as _allreduce_sum
 
     def allreduce_grads():
-        _allreduce(params, world)
+        if part_mode:
+            _allreduce_sum(params, g.part)
+        else:
+            _allreduce(params, world)
 
-    def step_resident(i):
+    from mr_gnas_b200.train import GraphedTrainStep
+    label_cols = host_batches[0][1].shape[1]
+    runner = GraphedTrainStep(model, g, opt, B, label_cols, grad_sync=lambda ps: allreduce_grads())
+
+    def step_eager(i):                       # per-call profiling pass and --no-graph
         trip_d, y_d = dev_batches[i % len(dev_batches)]
         opt.zero_grad(set_to_none=True)
         loss = model._loss(g, trip_d[:, 0], trip_d[:, 1], y_d)
@@ -252,15 +272,13 @@ def main():
         opt.step()
         return loss
 
-    def step_e2e(i):
+    def step_resident(i):                    # inputs already in HBM
+        trip_d, y_d = dev_batches[i % len(dev_batches)]
+        return runner(trip_d[:, 0], trip_d[:, 1], y_d)
+
+    def step_e2e(i):                         # inputs in pinned host memory, loss read back
         t_h, y_h = host_batches[i % len(host_batches)]
-        trip_d, y_d = t_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True)
-        opt.zero_grad(set_to_none=True)
-        loss = model._loss(g, trip_d[:, 0], trip_d[:, 1], y_d)
-        loss.backward()
-        allreduce_grads()
-        opt.step()
-        return loss.item()  # device -> host read of the step's result
+        return runner(t_h[:, 0], t_h[:, 1], y_h).item()
 
     def barrier():
         if world > 1:
@@ -291,24 +309,32 @@ def main():
             ms = float(t.item())
         return ms, (sampler.stop(t0, t1) if sampler else None), out
 
+    k0 = _lib.launch_count
+    step_eager(0)
+    lib_launches_per_step = _lib.launch_count - k0
+    if not args.no_graph:
+        trip_d, y_d = dev_batches[0]
+        runner.load(trip_d[:, 0], trip_d[:, 1], y_d)
+        runner.capture()
     for i in range(args.warmup):
         step_resident(i)
     ms, clocks, last_loss = timed(step_resident, args.steps, sample_clocks=True)
-    launches = timed.launches   # libmrgnas kernels enqueued inside the timed region
+    launches = lib_launches_per_step * args.steps   # libmrgnas kernels executed inside the timed region
     for i in range(2):
         step_e2e(i)
     ms_e2e, _, last_e2e = timed(step_e2e, args.steps)
 
     cells = len(README_GENOTYPE)
-    value = world * E * cells / (ms / 1e3)
-    e2e_value = world * E * cells / (ms_e2e / 1e3)
+    units = 1 if part_mode else world      # partitioned: the ranks share ONE graph pass; data parallel: one each
+    value = units * E * cells / (ms / 1e3)
+    e2e_value = units * E * cells / (ms_e2e / 1e3)
 
     # per-call CUDA-event profile of one step (rank 0) -> dominant kernel + roofline
     roofline, prof_rows = None, []
     if rank == 0:
         _lib.start_profile()
     for i in range(3):                   # all ranks step together (gradient all-reduce inside); rank 0 records
-        step_resident(i)
+        step_eager(i)
     barrier()
     if rank == 0:
         prof = _lib.stop_profile()
@@ -339,15 +365,18 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong" if part_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: README genotype LP train step (fwd+bwd+Adam), "
                                        f"N={N} R={R} T={T} E={E} D={D} B={B}, 1 cell",
-                           "parallelism": f"dp{world} over query batches (full-graph MP per rank, NCCL grad all-reduce)",
-                           "l2": "edge tensors are 447 MB each (> 126 MB L2); no explicit flush"},
-                "triples_per_s": world * B / (ms / 1e3),
+                           "parallelism": (f"dst-partition x{world} (1-D destination ranges, NCCL halo all-gather, "
+                                           "global BatchNorm statistics, entity-sharded 1-N scoring)" if part_mode else
+                                           f"dp{world} over query batches (full-graph MP per rank, NCCL grad all-reduce)"),
+                           "l2": "edge tensors are 447 MB each (> 126 MB L2); no explicit flush",
+                           "launch": "eager" if args.no_graph else "whole step replayed from one CUDA graph"},
+                "triples_per_s": units * B / (ms / 1e3),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e, "triples_per_s": world * B / (ms_e2e / 1e3)},
+                        "ms_per_step": ms_e2e, "triples_per_s": units * B / (ms_e2e / 1e3)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "loss": float(last_loss)}
         print(json.dumps(line), flush=True)

@@ -89,6 +89,17 @@ int mrg_graph_build(const int32_t* src, const int32_t* dst, const int32_t* etype
                     int32_t* csr_eid, int32_t* csc_ptr, int32_t* csc_row, int32_t* rel_ptr, int32_t* rel_row,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Destination-partitioned form (the reference is single-device): this process owns the
+ * destinations [node_lo, node_lo + n_dst) of an n_src-node graph and the E edges that point at them
+ * (dst_local = dst - node_lo), in global edge-id order.  Rows are the M = E + n_dst local edge-expanded rows;
+ * self row E+j has source node_lo+j.  csr_ptr[n_dst+1]; csc_ptr[n_src+1] (gather tables keep n_src rows);
+ * workspace: mrg_graph_workspace_bytes(E, n_dst, n_rel_rows).  Degree norms come from the GLOBAL in-degrees
+ * (caller) through mrg_edge_norm. */
+int mrg_graph_build_part(const int32_t* src, const int32_t* dst_local, const int32_t* etype, int64_t E, int64_t n_src,
+                         int64_t n_dst, int64_t node_lo, int64_t n_rel_rows, int32_t* csr_ptr, int32_t* csr_eid,
+                         int32_t* csc_ptr, int32_t* csc_row, int32_t* rel_ptr, int32_t* rel_row, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* edge_norm[e] = n_norm[dst[e]] * n_norm[src[e]] (one IEEE fp32 multiply; the apply_edges UDF of
  * train/mr_lp_train.py:86 and search/mr_lp_search.py:30-36) for a caller-supplied node norm. */
 int mrg_edge_norm(const int32_t* src, const int32_t* dst, const float* n_norm, int64_t E, float* edge_norm,

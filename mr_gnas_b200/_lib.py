@@ -36,6 +36,7 @@ _SIGNATURES = {
     "mrg_last_error": (c_char_p, []),
     "mrg_graph_workspace_bytes": (SZ, [I64, I64, I64]),
     "mrg_graph_build": (I32, [P, P, P, I64, I64, I64, P, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "mrg_graph_build_part": (I32, [P, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, P, P, SZ, P]),
     "mrg_edge_norm": (I32, [P, P, P, I64, P, P]),
     "mrg_chunk_capacity": (I64, [I64, I64]),
     "mrg_chunk_workspace_bytes": (SZ, [I64]),
@@ -76,7 +77,7 @@ _OPTIONAL = {}
 
 _lib = None
 # kernels enqueued per C-ABI call (default 1); used for the gpu_launches count bench.py reports
-KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_amax_bwd": 4, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_chunk_build": 3}
+KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_amax_bwd": 4, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_graph_build": 12, "mrg_graph_build_part": 10, "mrg_chunk_build": 3}
 launch_count = 0   # libmrgnas kernels launched so far
 _profile = None    # when a list: (name, start_event, end_event) per call (bench.py per-kernel timing)
 

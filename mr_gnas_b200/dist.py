@@ -53,3 +53,175 @@ def allreduce_stats(stats, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(stats, group=group)
     return stats
+
+
+# ------------------------------------------------------------------------------------------
+# Destination-partitioned message passing
+# ------------------------------------------------------------------------------------------
+class Partition:
+    """This rank's share of a destination-partitioned graph: destinations [lo, hi) of n_global nodes and the
+    e_local of e_global directed edges that point at them.  `rows_global` maps a LOCAL BatchNorm row count to
+    the global one (edge-expanded rows M = E + N, node rows N) so every rank normalises with global statistics."""
+
+    def __init__(self, rank, world, lo, hi, n_global, e_local, e_global, bounds, group=None):
+        self.rank, self.world, self.lo, self.hi = int(rank), int(world), int(lo), int(hi)
+        self.n_global, self.e_local, self.e_global = int(n_global), int(e_local), int(e_global)
+        self.bounds = list(bounds)          # [(lo, hi)] of every rank
+        self.group = group
+        self.n_local = self.hi - self.lo
+
+    def rows_global(self, rows_local):
+        if rows_local == self.e_local + self.n_local:
+            return self.e_global + self.n_global
+        if rows_local == self.n_local:
+            return self.n_global
+        raise RuntimeError(f"partitioned BatchNorm over {rows_local} rows: neither the local edge-expanded rows "
+                           f"({self.e_local + self.n_local}) nor the local nodes ({self.n_local})")
+
+
+_current = None
+
+
+def current():
+    """The Partition whose collectives the running forward should use (None: single-GPU semantics)."""
+    return _current
+
+
+class use:
+    """with dist.use(g.part): ...   -- BatchNorm statistics inside are summed over the partition's ranks."""
+
+    def __init__(self, part):
+        self.part = part
+
+    def __enter__(self):
+        global _current
+        self.prev, _current = _current, self.part
+        return self.part
+
+    def __exit__(self, *exc):
+        global _current
+        _current = self.prev
+        return False
+
+
+def sync_stats(part, stats, nparts, width, rows):
+    """Per-CTA partial column sums ([nparts, width] doubles) of THIS rank -> ([1, width] global sums, 1,
+    global row count).  The local fold is a fixed-order sum; the cross-rank sum is one all-reduce."""
+    if part is None or part.world <= 1:
+        return stats, nparts, rows
+    folded = stats[:nparts * width].view(nparts, width).sum(0)
+    dist.all_reduce(folded, group=part.group)
+    return folded.contiguous(), 1, part.rows_global(rows)
+
+
+def unshare_param_grads(part, *grads):
+    """BatchNorm dgamma/dbeta come out of the GLOBAL statistics, i.e. complete and identical on every rank, while
+    every other parameter gradient of the partitioned step is a per-rank partial that allreduce_grads_sum adds up.
+    Scale the complete ones by 1/world so the same final sum restores them (exact for power-of-two worlds)."""
+    if part is None or part.world <= 1:
+        return grads
+    return tuple(g / part.world for g in grads)
+
+
+class AllGatherRows(torch.autograd.Function):
+    """[n_local, D] owned rows -> the full [n_global, D] table on every rank (the halo exchange before the edge
+    gather of the next cell / the entity table of the scorer).  Backward: every rank holds a partial gradient of
+    the whole table (from its own edges / score block); the owner's slice of their SUM comes back."""
+
+    @staticmethod
+    def forward(ctx, x, part):
+        ctx.part = part
+        sizes = [h - l for l, h in part.bounds]
+        pad = max(sizes)
+        buf = x.new_zeros(pad, x.shape[1])
+        buf[:x.shape[0]] = x
+        out = x.new_empty(part.world * pad, x.shape[1])
+        dist.all_gather_into_tensor(out, buf, group=part.group)
+        return torch.cat([out[r * pad:r * pad + sizes[r]] for r in range(part.world)], 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        part = ctx.part
+        g = g.contiguous()
+        dist.all_reduce(g, group=part.group)
+        return g[part.lo:part.hi].contiguous(), None
+
+
+class ShardedRowSelect(torch.autograd.Function):
+    """table_local[idx - lo] for the idx this rank owns, summed over ranks -> the selected rows of the global
+    table on every rank ([B, D], B small: the 1-N query block of sf_DisMult, model_lp.py:135)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, part):
+        own = (idx >= part.lo) & (idx < part.hi)
+        loc = (idx - part.lo).clamp(0, max(part.n_local - 1, 0))
+        out = table[loc] * own.unsqueeze(1).to(table.dtype)
+        dist.all_reduce(out, group=part.group)
+        ctx.part, ctx.rows = part, table.shape[0]
+        ctx.save_for_backward(own, loc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        own, loc = ctx.saved_tensors
+        g = g.contiguous()
+        dist.all_reduce(g, group=ctx.part.group)
+        d = g.new_zeros(ctx.rows, g.shape[1])
+        d.index_put_((loc[own],), g[own], accumulate=True)   # sort-based on CUDA: deterministic
+        return d, None, None
+
+
+class AllReduceSum(torch.autograd.Function):
+    """Sum of per-rank partial losses; every rank's partial receives the upstream gradient unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, part):
+        y = x.clone()
+        dist.all_reduce(y, group=part.group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def allreduce_grads_sum(params, part):
+    """Partial parameter gradients (each rank saw only its own destinations / score block) -> their sum."""
+    if part is None or part.world <= 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=part.group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def lp_partition(triples, num_ent, num_rels, rank, world, device="cuda", group=None):
+    """Destination-partitioned build_graph (train/mr_lp_train.py:77-89): edges [s->o | o->s], e_type [r | r+R];
+    this rank keeps the edges whose destination falls in its range (ranges balanced by in-edge count) and the
+    GLOBAL degree norms.  Returns an MRGraph with .part set."""
+    import numpy as np
+    from .graph import MRGraph
+    t = np.asarray(triples)
+    s, r, o = t[:, 0].astype(np.int64), t[:, 1].astype(np.int64), t[:, 2].astype(np.int64)
+    src, dst, et = np.concatenate([s, o]), np.concatenate([o, s]), np.concatenate([r, r + num_rels])
+    E, T = src.shape[0], s.shape[0]
+    deg = np.bincount(dst, minlength=num_ent)
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]))
+    ranges = partition_by_dst(ptr, world)
+    lo, hi = ranges[rank][0], ranges[rank][1]
+    keep = (dst >= lo) & (dst < hi)
+    half = int(keep[:T].sum())
+    degf = deg.astype(np.float32)
+    with np.errstate(divide="ignore"):
+        n_norm = degf ** -0.5
+    n_norm[np.isinf(n_norm)] = 0
+    g = MRGraph.from_partition(torch.from_numpy(src[keep]), torch.from_numpy(dst[keep]), torch.from_numpy(et[keep]),
+                               num_ent, 2 * num_rels + 1, lo, hi, half, torch.from_numpy(n_norm), device)
+    g.part = Partition(rank, world, lo, hi, num_ent, int(keep.sum()), E, [(a, b) for a, b, _, _ in ranges], group)
+    return g

@@ -4,6 +4,7 @@ matrices happens in the hand-written CUDA kernels (no eager / CPU fallback)."""
 import torch
 
 from . import _lib
+from . import dist as _dist
 from ._lib import act, call, ptr, stream
 
 
@@ -126,7 +127,9 @@ class BNAct(torch.autograd.Function):
                 nparts = stats.numel() // (2 * D)
             mean = torch.empty_like(a)
             invstd = torch.empty_like(a)
-            call("mrg_bn_finalize", ptr(stats), nparts, rows, D, ptr(gamma), ptr(beta), float(eps), float(momentum),
+            ctx.part = _dist.current()
+            stats, nparts, rows_g = _dist.sync_stats(ctx.part, stats, nparts, 2 * D, rows)
+            call("mrg_bn_finalize", ptr(stats), nparts, rows_g, D, ptr(gamma), ptr(beta), float(eps), float(momentum),
                  ptr(running_mean), ptr(running_var), ptr(mean), ptr(invstd), ptr(a), ptr(b), stream())
         else:
             invstd = torch.rsqrt(running_var + eps)
@@ -154,9 +157,11 @@ class BNAct(torch.autograd.Function):
             dgamma = torch.empty(D, dtype=torch.float32, device=dev)
             dbeta = torch.empty_like(dgamma)
             coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
-            call("mrg_bn_bwd_finalize", ptr(bst), nparts, rows, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
+            bst, nparts, rows_g = _dist.sync_stats(getattr(ctx, 'part', None), bst, nparts, 2 * D, rows)
+            call("mrg_bn_bwd_finalize", ptr(bst), nparts, rows_g, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
                  ptr(dbeta), ptr(coef), stream())
             call("mrg_bn_bwd_apply", ptr(ds), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
+            dgamma, dbeta = _dist.unshare_param_grads(getattr(ctx, 'part', None), dgamma, dbeta)
         else:
             coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
             call("mrg_bn_bwd_apply", ptr(ds), yact, ptr(coef), rows, D, ptr(dy), 0, stream())

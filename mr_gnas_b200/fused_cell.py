@@ -17,6 +17,7 @@ edge-level state.  Anything else falls back to the per-module path (still CUDA, 
 import torch
 
 from . import _lib
+from . import dist as D_
 from . import functional as K
 from ._lib import act, call, ptr, stream
 
@@ -79,7 +80,8 @@ class EdgeChain(torch.autograd.Function):
                 a = torch.empty(D, dtype=torch.float32, device=dev)
                 b, mean, invstd = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
                 mom = 0.1 if bn.momentum is None else bn.momentum
-                call("mrg_bn_finalize", ptr(stats), stats.numel() // (2 * D), rows, D, ptr(gamma), ptr(beta), float(bn.eps),
+                stats, nparts_, rows = D_.sync_stats(g.part, stats, stats.numel() // (2 * D), 2 * D, rows)
+                call("mrg_bn_finalize", ptr(stats), nparts_, rows, D, ptr(gamma), ptr(beta), float(bn.eps),
                      float(mom), ptr(bn.running_mean), ptr(bn.running_var), ptr(mean), ptr(invstd), ptr(a), ptr(b),
                      stream())
             else:
@@ -104,7 +106,7 @@ class EdgeChain(torch.autograd.Function):
             y = Y[k] if (lo == 0 and hi is None) else Y[k][lo:hi]
             return act(y) if aff is None else act(y, aff[0], aff[1], True)
 
-        bounds = [(0, E // 2), (E // 2, E), (E, M)]
+        bounds = [(0, g.half), (g.half, E), (E, M)]
         norm = g.norm()
         gate_params = {}
         for node, om, i in gates:
@@ -177,7 +179,7 @@ class EdgeChain(torch.autograd.Function):
                     DS[i] = torch.empty(M, D, dtype=torch.float32, device=dev)
                 call("mrg_seg_reduce_bwd", 0, ptr(dout), None, None, act(None), ptr(g.dst), ptr(g.csr.ptr), E, N, D,
                      ptr(DS[i]), 0 if fresh else 1, stream())
-        bounds = [(0, E // 2), (E // 2, E), (E, M)]
+        bounds = [(0, g.half), (g.half, E), (E, M)]
         norm = g.norm()
         lib = _lib.load()
         fused_bwd = bool(lib.mrg_sparse_gate_bwd_fused_supported(D))
@@ -210,11 +212,12 @@ class EdgeChain(torch.autograd.Function):
             dgamma = torch.empty(D, dtype=torch.float32, device=dev)
             dbeta = torch.empty_like(dgamma)
             coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
-            call("mrg_bn_bwd_finalize", ptr(bst), nparts, M, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
+            bst, nparts, rows_g = D_.sync_stats(g.part, bst, nparts, 2 * D, M)
+            call("mrg_bn_bwd_finalize", ptr(bst), nparts, rows_g, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
                  ptr(dbeta), ptr(coef), stream())
             if not training:
                 coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
-            return (dgamma, dbeta), coef
+            return D_.unshare_param_grads(g.part, dgamma, dbeta), coef
 
         def bn_apply(k, coef):
             """ds_k -> dy_k in place (only where no fused consumer reads the gradient lazily)."""

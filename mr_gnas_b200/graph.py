@@ -54,6 +54,9 @@ class MRGraph:
         self.srcdata = self.ndata
         self.last_arg = None
         self.n_rel_rows = None
+        self.half = None      # rows [0, half) original direction, [half, E) inverse (E // 2 for the full graph)
+        self.part = None      # dist.Partition when this graph holds one destination range of a larger graph
+        self.n_src = None     # rows of the gather tables (== N unless partitioned)
 
     # ----------------------------------------------------------------- construction
     @classmethod
@@ -69,6 +72,43 @@ class MRGraph:
         s, r, o = t[:, 0], t[:, 1], t[:, 2]
         return cls.from_edges(torch.cat([s, o]), torch.cat([o, s]), torch.cat([r, r + num_rels]), num_ent,
                               2 * num_rels + 1, device)
+
+    @classmethod
+    def from_partition(cls, src, dst, etype, num_nodes, n_rel_rows, node_lo, node_hi, half, n_norm, device="cuda"):
+        """The edges (global edge-id order, global node ids) that point into destinations [node_lo, node_hi) of a
+        num_nodes-node graph; `half` of them belong to the original direction; n_norm [num_nodes] are the GLOBAL
+        in-degree norms (mr_lp_train.py:81-84).  Destinations and outputs are local, gather tables global."""
+        dev = torch.device(device)
+        g = cls(int(node_hi - node_lo), dev)
+        lib = _lib.load()
+        E, n_src, n_dst = int(src.numel()), int(num_nodes), int(node_hi - node_lo)
+        i32 = dict(dtype=torch.int32, device=dev)
+        g.E, g.N, g.M, g.n_rel_rows, g.half, g.n_src = E, n_dst, E + n_dst, int(n_rel_rows), int(half), n_src
+        g.src = torch.as_tensor(src).to(device=dev, dtype=torch.int32).contiguous()
+        dst_g = torch.as_tensor(dst).to(device=dev, dtype=torch.int32).contiguous()
+        g.dst = (dst_g - int(node_lo)).contiguous()
+        g.etype = torch.as_tensor(etype).to(device=dev, dtype=torch.int32).contiguous()
+        csr_ptr, csr_eid = torch.empty(n_dst + 1, **i32), torch.empty(max(E, 1), **i32)
+        csc_ptr, csc_row = torch.empty(n_src + 1, **i32), torch.empty(g.M, **i32)
+        rel_ptr, rel_row = torch.empty(g.n_rel_rows + 1, **i32), torch.empty(g.M, **i32)
+        wsb = int(lib.mrg_graph_workspace_bytes(E, n_dst, g.n_rel_rows))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        p = _lib.ptr
+        _lib.call("mrg_graph_build_part", p(g.src), p(g.dst), p(g.etype), E, n_src, n_dst, int(node_lo), g.n_rel_rows,
+                  p(csr_ptr), p(csr_eid), p(csc_ptr), p(csc_row), p(rel_ptr), p(rel_row), p(ws), wsb, _lib.stream())
+        g.in_deg = (csr_ptr[1:] - csr_ptr[:-1]).contiguous()
+        g.n_norm = torch.as_tensor(n_norm).to(device=dev, dtype=torch.float32).contiguous()
+        g.edge_norm = torch.empty(E, dtype=torch.float32, device=dev)
+        _lib.call("mrg_edge_norm", p(g.src), p(dst_g), p(g.n_norm), E, p(g.edge_norm), _lib.stream())
+        g.csr = _Segments(csr_ptr, csr_eid, n_dst, E, dev)
+        g.csc = _Segments(csc_ptr, csc_row, n_src, g.M, dev)
+        g.rel = _Segments(rel_ptr, rel_row, g.n_rel_rows, g.M, dev)
+        g.src_final = torch.cat([g.src, torch.arange(int(node_lo), int(node_hi), **i32)])
+        g.et_final = torch.cat([g.etype, torch.full((n_dst,), g.n_rel_rows - 1, **i32)])
+        g.edata["norm"] = g.edge_norm
+        g.edata["e_type"] = g.etype.long()
+        g._built = True
+        return g
 
     @classmethod
     def from_block(cls, dst, num_dst, device="cuda"):
@@ -122,6 +162,7 @@ class MRGraph:
         M = E + N
         i32 = dict(dtype=torch.int32, device=dev)
         self.E, self.N, self.M, self.n_rel_rows = E, N, M, int(n_rel_rows)
+        self.half, self.n_src = E // 2, N
         self.src = src.to(device=dev, dtype=torch.int32).contiguous()
         self.dst = dst.to(device=dev, dtype=torch.int32).contiguous()
         self.etype = etype.to(device=dev, dtype=torch.int32).contiguous()

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import dist as D_
 from . import functional as K
 from . import fused_cell
 from .operations_lp import MIXED_OPS, MIXED_OPS_sf
@@ -158,6 +159,9 @@ class Network(nn.Module):
 
     def _embed(self, g):
         """model_lp.py:124-133: entity/relation tables through every cell."""
+        if getattr(g, 'part', None) is not None:
+            ent_local, rel_embed = self._embed_partitioned(g)
+            return D_.AllGatherRows.apply(ent_local, g.part), rel_embed
         all_ent_emb = self.linear_e(self.embedding_h.weight)  # == embedding_h(arange(N))
         rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
         for cell in self.cells:
@@ -165,6 +169,23 @@ class Network(nn.Module):
             all_ent_emb = F.dropout(all_ent_emb, self._dropout, training=self.training)
             rel_embed = torch.matmul(rel_embed, self.w_rel)
         return all_ent_emb, rel_embed
+
+    def _embed_partitioned(self, g):
+        """Destination-partitioned form of _embed: `g` holds this rank's destinations; every cell
+        reads the FULL entity table (replicated for the first cell, all-gathered over NVLink for the following
+        ones), writes its own rows, and normalises with statistics summed over the ranks.  Returns the LOCAL rows
+        [hi-lo, D] of the final entity table and the (replicated) relation table."""
+        part = g.part
+        table = self.linear_e(self.embedding_h.weight)
+        rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
+        with D_.use(part):
+            for k, cell in enumerate(self.cells):
+                if k > 0:
+                    table = D_.AllGatherRows.apply(local, part)
+                local = cell.forward_fused(g, table, rel_embed)
+                local = F.dropout(local, self._dropout, training=self.training)
+                rel_embed = torch.matmul(rel_embed, self.w_rel)
+        return local, rel_embed
 
     def _forward_lp(self, g, subj, rel):
         all_ent_emb, rel_embed = self._embed(g)
@@ -176,8 +197,17 @@ class Network(nn.Module):
     def _loss(self, g, subj, rel, label):
         """model_lp.py:148-150.  With the DistMult scorer and BCELoss (the README
         configuration) probabilities are never materialised: fused sigmoid+BCE kernel."""
-        if isinstance(self.criterion, nn.BCELoss) and hasattr(self.score_func, 'loss') \
-                and self.criterion.reduction == 'mean' and self.criterion.weight is None:
+        part = getattr(g, 'part', None)
+        fused_ok = isinstance(self.criterion, nn.BCELoss) and hasattr(self.score_func, 'loss') \
+            and self.criterion.reduction == 'mean' and self.criterion.weight is None
+        if part is not None and fused_ok:
+            # entity dimension of the 1-N scores sharded like the destinations: the [B, D] query block is the only
+            # tensor exchanged; `label` holds this rank's columns [lo, hi) of the [B, N] label matrix
+            ent_local, rel_embed = self._embed_partitioned(g)
+            sub = D_.ShardedRowSelect.apply(ent_local, subj, part)
+            loss_local = self.score_func.loss(ent_local, sub, rel_embed[rel], label)
+            return D_.AllReduceSum.apply(loss_local * (part.n_local / part.n_global), part)
+        if fused_ok:
             all_ent_emb, rel_embed = self._embed(g)
             return self.score_func.loss(all_ent_emb, all_ent_emb[subj], rel_embed[rel], label)
         return self.criterion(self.forward(g, subj, rel), label)

@@ -139,7 +139,9 @@ def _collapse(W, a):
 
 def _comp_bounds(g, rows):
     E = g.num_edges()
-    return [(0, E // 2), (E // 2, E), (E, rows)], E
+    half = getattr(g, 'half', None)
+    half = E // 2 if half is None else half   # a destination partition holds unequal direction halves
+    return [(0, half), (half, E), (E, rows)], E
 
 
 class f_sparse_op_comp(nn.Module):

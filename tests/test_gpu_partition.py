@@ -1,0 +1,108 @@
+"""Destination-partitioned message passing against the single-GPU path on the same seeded
+inputs: loss, every parameter gradient and the BatchNorm running statistics must agree.  world=1 runs on any
+GPU box (exercises mrg_graph_build_part, the sharded scorer and the statistics plumbing); world=2 needs 2 GPUs."""
+import os
+import socket
+import types
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+Genotype = namedtuple("Genotype", "alpha_cell concat_node score_func")
+CELL = Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f_sparse_comp', 3, 2), ('a_max', 4, 2),
+                            ('a_max', 5, 3), ('f_sparse_last', 6, 5), ('f_sparse_last', 7, 5)],
+                concat_node=[4, 5, 6, 7], score_func='sf_DisMult')
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _args(D):
+    return types.SimpleNamespace(feature_dim=D, drop_aggr=0.0, drop_op=0.0, gamma=40, embed_dim=D,
+                                 conve_hid_drop=0.0, feat_drop=0.0, num_filt=4, ker_sz=3, k_w=4, k_h=D // 4)
+
+
+def _err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+def _compare(rank, world, n_cells):
+    from mr_gnas_b200 import dist as D_
+    from mr_gnas_b200.graph import MRGraph
+    from mr_gnas_b200.model_lp import Network
+    from mr_gnas_b200.synth import synth_kg
+    from mr_gnas_b200.utils import weights_init
+    dev = torch.device("cuda", rank)
+    N, R, T, D, B = 700, 9, 6000, 64, 32
+    trip = synth_kg(N, R, T, seed=3)
+    genos = [CELL] * n_cells
+
+    def fresh():
+        torch.manual_seed(0)
+        m = Network(dev, genos, N, R, D, D, 2 * R + 1, nn.BCELoss(), 0.0, _args(D))
+        m.apply(weights_init)
+        return m.to(dev).train()
+
+    rng = np.random.RandomState(5)
+    subj = torch.from_numpy(rng.randint(0, N, B)).to(dev)
+    rel = torch.from_numpy(rng.randint(0, 2 * R, B)).to(dev)
+    label = (torch.from_numpy(rng.rand(B, N)) < 0.02).float().to(dev) * 0.9 + 1.0 / N
+
+    ref = fresh()
+    g_full = MRGraph.from_triples(N, trip, R, device=dev)
+    loss_ref = ref._loss(g_full, subj, rel, label)
+    loss_ref.backward()
+
+    par = fresh()
+    g = D_.lp_partition(trip, N, R, rank, world, device=dev)
+    assert g.part.lo < g.part.hi and g.E == g.part.e_local
+    loss = par._loss(g, subj, rel, label[:, g.part.lo:g.part.hi].contiguous())
+    loss.backward()
+    D_.allreduce_grads_sum(list(par.parameters()), g.part)
+    assert _err(loss, loss_ref) <= 1e-5, (float(loss), float(loss_ref))
+    worst = max((_err(p.grad, q.grad), k) for (k, p), q in zip(par.named_parameters(), ref.parameters())
+                if q.grad is not None)
+    assert worst[0] <= 2e-5, worst
+    for (k, a), b in zip(par.named_buffers(), ref.buffers()):
+        if a.dtype.is_floating_point:
+            assert _err(a, b) <= 1e-5, k
+    # the all-gathered forward (predict path) equals the single-GPU probabilities
+    par.eval(), ref.eval()
+    with torch.no_grad():
+        assert _err(par(g, subj, rel), ref(g_full, subj, rel)) <= 1e-5
+
+
+def _worker(rank, world, port, n_cells):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        _compare(rank, world, n_cells)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cells", [1, 2])
+def test_partitioned_lp_world1_matches_full_graph(n_cells):
+    mp.spawn(_worker, args=(1, _free_port(), n_cells), nprocs=1, join=True)
+
+
+@pytest.mark.parametrize("n_cells", [1, 2])
+def test_partitioned_lp_world2_matches_single_gpu(n_cells):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_worker, args=(2, _free_port(), n_cells), nprocs=2, join=True)
