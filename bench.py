@@ -381,7 +381,12 @@ def main():
                 "loss": float(last_loss)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by a live CUDA graph can stall destroy_process_group(): leave together,
+        # after everything is printed, without tearing the communicator down
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

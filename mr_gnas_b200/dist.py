@@ -167,7 +167,9 @@ class ShardedRowSelect(torch.autograd.Function):
         g = g.contiguous()
         dist.all_reduce(g, group=ctx.part.group)
         d = g.new_zeros(ctx.rows, g.shape[1])
-        d.index_put_((loc[own],), g[own], accumulate=True)   # sort-based on CUDA: deterministic
+        # static shapes (CUDA-graph capturable): rows of other ranks add exact zeros to a clamped index;
+        # index_put_(accumulate) is sort-based on CUDA, hence deterministic
+        d.index_put_((loc,), g * own.unsqueeze(1).to(g.dtype), accumulate=True)
         return d, None, None
 
 

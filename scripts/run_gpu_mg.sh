@@ -7,7 +7,7 @@ timeout 600 python -m pytest tests/test_gpu_partition.py -x -q > gpurun_out/pyte
 echo "partition pytest exit $?"; tail -15 gpurun_out/pytest_partition.log
 for mode in "" "--partition"; do
   tag=dp; [ -n "$mode" ] && tag=part
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 20 --warmup 3 $mode > gpurun_out/bench_g${N}_$tag.log 2>&1
   echo "bench $tag g$N exit $?"; tail -1 gpurun_out/bench_g${N}_$tag.log | cut -c1-900
 done
