@@ -185,6 +185,35 @@ def algo_bytes(key, M, E, N, D):
     return table.get(name)
 
 
+# C-ABI call -> the kernels it launches that move HBM data (ncu names, template arguments dropped)
+CALL_KERNELS = {
+    "mrg_amax_bwd": ["amax_bwd_dw_kernel", "amax_bwd_dx_kernel"],
+    "mrg_amax_tc_fwd": ["tc::amax_tc_kernel"],
+    "mrg_sparse_gate_bwd_fused": ["gate_bwd_pipe_kernel"],
+    "mrg_sparse_gate_fwd": ["sparse_gate_fwd_kernel"],
+    "mrg_bn_bwd_apply": ["bn_bwd_apply_kernel"],
+    "mrg_bn_bwd_reduce": ["bn_bwd_reduce_kernel"],
+    "mrg_compose_fwd": ["compose_fwd_kernel"],
+    "mrg_seg_reduce_fwd": ["seg_reduce_chunk_kernel"],
+}
+
+
+def ncu_traffic(call_key):
+    """DRAM bytes (read + write) per launch of the kernels behind `call_key`, from the committed
+    `ncu --set full` capture of the same workload (profiles/r01_traffic.json); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    cap = json.load(open(p))
+    total, found = 0.0, False
+    for k in CALL_KERNELS.get(call_key.split("(")[0], []):
+        hits = [v["dram_bytes_per_launch"] for name, v in cap.items() if name.split("<")[0].endswith(k.split("::")[-1])]
+        if hits:
+            total += max(hits)      # the full-size launch (small node-level launches share the kernel name)
+            found = True
+    return total if found else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,6 +225,8 @@ def main():
     ap.add_argument("--ref-downscale", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-call CUDA-event profile here")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="profiling aid (ncu): eager warm-up + steps only, no clock sampling / e2e / CPU legs, no JSON")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--partition", action="store_true",
                     help="N>1: destination-partitioned message passing (halo all-gather, global BatchNorm statistics, "
@@ -312,6 +343,11 @@ def main():
     k0 = _lib.launch_count
     step_eager(0)
     lib_launches_per_step = _lib.launch_count - k0
+    if args.kernels_only:
+        for i in range(args.warmup + args.steps):
+            step_eager(i)
+        torch.cuda.synchronize()
+        return
     if not args.no_graph:
         trip_d, y_d = dev_batches[0]
         runner.load(trip_d[:, 0], trip_d[:, 1], y_d)
@@ -345,11 +381,14 @@ def main():
             avg_ms = t / cnt
             prof_rows.append({"call": key, "launches_per_step": cnt / 3, "avg_ms": avg_ms, "ms_per_step": t / 3,
                               "share_of_lib_time": t / 3 / tot if tot else None,
-                              "algo_gbs": (ab / avg_ms / 1e6) if ab else None})
+                              "algo_gbs": (ab / avg_ms / 1e6) if ab else None, "algo_bytes": ab})
         top = next((r for r in prof_rows if r["algo_gbs"]), None)
         if top:
             roofline = {"bound": "hbm", "kernel": top["call"], "achieved": top["algo_gbs"], "peak": hbm, "unit": "GB/s",
-                        "frac": top["algo_gbs"] / hbm, "traffic": None, "peak_source": how,
+                        "frac": top["algo_gbs"] / hbm, "traffic": ncu_traffic(top["call"]),
+                        "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + "
+                                          "dram__bytes_write.sum of the call's kernels, per launch)",
+                        "algorithmic_bytes": top["algo_bytes"], "peak_source": how,
                         "lib_ms_per_step": tot, "step_ms": ms}
         if args.profile_json:
             json.dump(prof_rows, open(args.profile_json, "w"), indent=1)

@@ -318,3 +318,84 @@ def test_fail_loudly_on_cpu_tensor():
     from mr_gnas_b200 import functional as K
     with pytest.raises(RuntimeError):
         K.ComposeRows.apply(torch.randn(4, 8), torch.randn(4, 8), 0)
+
+
+# ------------------------------------------------------------------------------ fused gate backward (TMA row pipeline)
+@pytest.mark.parametrize("D", [64, 200, 256])
+@pytest.mark.parametrize("variant", ["same_lazy_stats_acc", "split_lazy_stats_acc", "split_plain", "noin_lazy"])
+def test_sparse_gate_bwd_fused_vs_fp64(dev, D, variant):
+    """mrg_sparse_gate_bwd_fused (lazy BatchNorm backward on load, BN-backward statistics of the input state,
+    in-place accumulation) against the same algebra in fp64 torch: operations_lp.py:304-343 backward composed
+    with native_batch_norm_backward + threshold_backward on both sides."""
+    from mr_gnas_b200 import _lib
+    from mr_gnas_b200._lib import act, call, grad, ptr, stream
+    lib = _lib.load()
+    rows = 1003                       # not a multiple of the 8-row tile
+    torch.manual_seed(D + len(variant))
+    has_in = not variant.startswith("noin")
+    same = variant.startswith("same")
+    lazy = "lazy" in variant
+    want_stats = "stats" in variant
+    acc = 0
+    if "acc" in variant:
+        acc = 1 if same else 3
+    f32 = dict(dtype=torch.float32, device=dev)
+    ds, yk, yx, yi = (torch.randn(rows, D, **f32) for _ in range(4))
+    if same:
+        yi = yx
+    ak, bk, ax, bx, ai, bi = (torch.randn(D, **f32) * s + o for s, o in ((0.5, 1), (0.5, 0), (0.5, 1), (0.5, 0), (0.5, 1), (0.5, 0)))
+    if same:
+        ai, bi = ax, bx
+    coef = torch.randn(3 * D, **f32) * 0.3
+    gate = torch.rand(rows, **f32)
+    rs = torch.rand(rows, **f32)
+    v1, v2 = torch.randn(D, **f32), torch.randn(D, **f32)
+    dx_old, di_old = torch.randn(rows, D, **f32), torch.randn(rows, D, **f32)
+    # ---- fp64 reference
+    d = lambda t: t.double()
+    dy = d(ds)
+    if lazy:
+        dz = dy * (d(ak) * d(yk) + d(bk) > 0)
+        dy = d(coef[2 * D:]) * dz + d(coef[:D]) + d(coef[D:2 * D]) * d(yk)
+    x = torch.relu(d(ax) * d(yx) + d(bx))
+    xin = torch.relu(d(ai) * d(yi) + d(bi)) if has_in else None
+    sc = d(rs) / 3.0
+    dot = (dy * x).sum(1)
+    dt = sc * d(gate) * (1 - d(gate)) * dot
+    dx_ref = (sc * d(gate)).unsqueeze(1) * dy + dt.unsqueeze(1) * d(v1)
+    di_ref = dt.unsqueeze(1) * d(v2) if has_in else None
+    if same:
+        dx_ref = dx_ref + di_ref
+    if acc & 1:
+        dx_ref = dx_ref + d(dx_old)
+    if has_in and not same and (acc & 2):
+        di_ref = di_ref + d(di_old)
+    dv1_ref = (dt.unsqueeze(1) * x).sum(0)
+    dv2_ref = (dt.unsqueeze(1) * xin).sum(0) if has_in else None
+    dzx = dx_ref * (x > 0)
+    st_ref = torch.stack([dzx.sum(0), (dzx * d(yx)).sum(0)])
+    # ---- kernel
+    dx = dx_old.clone() if (acc & 1) else torch.empty(rows, D, **f32)
+    if same:
+        dxin = dx
+    else:
+        dxin = (di_old.clone() if (acc & 2) else torch.empty(rows, D, **f32)) if has_in else None
+    nparts = int(lib.mrg_stats_nparts(rows))
+    dparam = torch.empty(int(lib.mrg_gate_dparam_count(rows, D)), dtype=torch.float64, device=dev)
+    xst = torch.empty(nparts * 2 * D, dtype=torch.float64, device=dev) if want_stats else None
+    gview = grad(ds, act(yk, ak, bk, True), coef) if lazy else grad(ds)
+    xin_view = act(yi, ai, bi, True) if has_in else act(None)
+    call("mrg_sparse_gate_bwd_fused", gview, act(yx, ax, bx, True), xin_view, ptr(gate), rows, D, ptr(v1),
+         ptr(v2) if has_in else None, ptr(rs), 1.0 / 3.0, ptr(dx), ptr(dxin) if has_in else None, acc, ptr(dparam),
+         ptr(xst), stream())
+    torch.cuda.synchronize()
+    _check("dx", dx, dx_ref.float())
+    if has_in and not same:
+        _check("dxin", dxin, di_ref.float())
+    dp = dparam.view(nparts, 2 * D + 1).sum(0)
+    _check("dv1", dp[:D].float(), dv1_ref.float())
+    if has_in:
+        _check("dv2", dp[D:2 * D].float(), dv2_ref.float())
+    _check("dc", dp[2 * D:].float(), dt.sum().view(1).float())
+    if want_stats:
+        _check("x bwd stats", xst.view(nparts, 2, D).sum(0).float(), st_ref.float())
