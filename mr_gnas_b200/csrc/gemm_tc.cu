@@ -16,14 +16,14 @@
 // lo = rna_tf32(x - hi)) and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM
 // ("3xTF32"), giving ~2^-21 relative operand error, i.e. SGEMM-class results.
 //
-// Pipeline per CTA (persistent, one CTA per SM, 18 warps; tiles are walked in PAIRS -- TMEM slots 0/1 -- with
+// Pipeline per CTA (persistent, one CTA per SM, 26 warps; tiles are walked in PAIRS -- TMEM slots 0/1 -- with
 // their K chunks interleaved so each W chunk streamed from L2 feeds two tiles):
-//   warps 0-7   X producers: 2 threads per tile row gather X by CSR edge id with a 3-chunk-deep register
+//   warps 0-15  X producers: 4 threads per tile row gather X by CSR edge id with a 4-chunk-deep register
 //                            prefetch ring -> (BN affine + ReLU) -> hi/lo split -> 128B-swizzled K-major smem
-//   warp  17    W loader   : one thread, cp.async.bulk (UBLKCP) of the pre-swizzled hi/lo K-chunk image,
+//   warp  25    W loader   : one thread, cp.async.bulk (UBLKCP) of the pre-swizzled hi/lo K-chunk image,
 //                            completion by mbarrier expect_tx
-//   warp  16    MMA issuer : one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
-//   warps 8-15  epilogue   : one 4-warp set per TMEM slot: tcgen05.ld -> +bias, ReLU -> segmented max scan
+//   warp  24    MMA issuer : one elected thread, tcgen05.mma kind::tf32, M=128 per half, N=128, K=8
+//   warps 16-23 epilogue   : one 4-warp set per TMEM slot: tcgen05.ld -> +bias, ReLU -> segmented max scan
 //                            -> atomicMax
 #include "common.cuh"
 
@@ -33,13 +33,15 @@ namespace tc {
 constexpr int TILE_E = 128;   // edges per tile  (UMMA N)
 constexpr int KCH = 32;       // fp32 elements per K chunk = one 128-byte swizzled row
 constexpr int STAGES = 2;
-constexpr int PROD_THREADS = 256;
+constexpr int TPR = 4;         // producer threads per tile row
+constexpr int NU = 8 / TPR;    // 16-byte units of a 128-byte K chunk handled by one producer thread
+constexpr int PROD_THREADS = 128 * TPR;
 constexpr int EPI_THREADS = 128;
-constexpr int THREADS = PROD_THREADS + 2 * EPI_THREADS + 64;   // 18 warps
-constexpr int PD = 3;         // X prefetch depth (items in flight per producer thread)
-constexpr int EPI_WARP0 = PROD_THREADS / 32;   // 8  (8 % 4 == 0 -> TMEM lane quadrants 0..3 for both warp sets)
-constexpr int MMA_WARP = EPI_WARP0 + 8;        // 16
-constexpr int WLD_WARP = MMA_WARP + 1;         // 17
+constexpr int THREADS = PROD_THREADS + 2 * EPI_THREADS + 64;   // 16 producer + 8 epilogue + MMA + W loader warps
+constexpr int PD = 4;         // X prefetch depth (items in flight per producer thread)
+constexpr int EPI_WARP0 = PROD_THREADS / 32;   // multiple of 4 -> TMEM lane quadrants 0..3 for both warp sets
+constexpr int MMA_WARP = EPI_WARP0 + 8;
+constexpr int WLD_WARP = MMA_WARP + 1;
 constexpr uint32_t TILE_BYTES = 128 * 128;  // 128 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -248,15 +250,16 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
 
   if (warp < EPI_WARP0) {
     // ================================ X PRODUCERS ================================
-    const int r = (warp << 4) | (lane & 15);   // tile row
-    const int half = lane >> 4;                // which 16-byte units of a 128-byte chunk: 2j + half
+    constexpr int RPW = 32 / TPR;              // tile rows per producer warp
+    const int r = warp * RPW + (lane % RPW);   // tile row
+    const int half = lane / RPW;               // which 16-byte units of a 128-byte chunk: TPR*j + half
     const bool affine = p.x.scale != nullptr, relu = p.x.relu != 0;
     const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
     const float* xrow0 = nullptr;   // load cursor's row, slot 0 / slot 1
     const float* xrow1 = nullptr;
-    float4 buf[PD][4];
+    float4 buf[PD][NU];
     int lq = 0;
-    auto load = [&](float4(&b)[4], int q) {
+    auto load = [&](float4(&b)[NU], int q) {
       const Item it = item_of(q, p.nchunks, full_pairs);
       if (it.c == 0) {
         const int64_t pos = tile_of(it.pair, it.slot) * TILE_E + r;
@@ -266,12 +269,12 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       }
       const float* xr = it.slot ? xrow1 : xrow0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = it.c * KCH + 4 * (2 * j + half);
+      for (int j = 0; j < NU; ++j) {
+        const int col = it.c * KCH + 4 * (TPR * j + half);
         b[j] = (xr && col < D) ? ld_stream4(xr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto consume = [&](float4(&b)[4], int q) {
+    auto consume = [&](float4(&b)[NU], int q) {
       const Item it = item_of(q, p.nchunks, full_pairs);
       const bool valid = tile_of(it.pair, it.slot) * TILE_E + r < p.E;
       const int s = q % XS;
@@ -280,8 +283,8 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       uint8_t* xhi = smem_x + (size_t)s * XSTAGE;
       uint8_t* xlo = xhi + TILE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int u = 2 * j + half;
+      for (int j = 0; j < NU; ++j) {
+        const int u = TPR * j + half;
         const int col = it.c * KCH + 4 * u;
         float4 v = b[j];
         if (valid && col < D) {
