@@ -26,11 +26,12 @@ constexpr int kBwdWarps = kBwdThreads / 32;
 // routed to it and their W rows are accumulated from shared memory (W resident when it fits).
 // ---------------------------------------------------------------------------------------
 template <int NJ, bool W_SMEM>
-__global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
+__global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(  // NT4 = ceil(NJ / 4) float4 groups per lane
     const float* __restrict__ g, const int32_t* __restrict__ arg, const float* __restrict__ W,
     const int32_t* __restrict__ ptr, const int32_t* __restrict__ eid, const int32_t* __restrict__ chunk_first,
     const int32_t* __restrict__ chunk_seg, int64_t nseg, int D, float* __restrict__ dX) {
   extern __shared__ float smem_w[];  // [D][D] when W_SMEM
+  constexpr int NT4 = (NJ + 3) / 4;
   const int lane = threadIdx.x & 31;
   if (W_SMEM) {
     for (int i = threadIdx.x * 4; i < D * D; i += blockDim.x * 4)
@@ -54,11 +55,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
       gr[j] = f < D ? __ldg(g + (size_t)n * D + f) : 0.f;
       ar[j] = f < D ? __ldg(arg + (size_t)n * D + f) : -1;
     }
+    const int D4 = D >> 2;
+    int32_t e_next = __ldg(eid + lo);
     for (int32_t pz = lo; pz < hi; ++pz) {
-      const int32_t e = __ldg(eid + pz);
-      float acc[NJ];
+      const int32_t e = e_next;
+      if (pz + 1 < hi) e_next = __ldg(eid + pz + 1);
+      // lane owns the float4 column groups c4 = lane + 32 t: 128-bit shared-memory reads of W and 128-bit stores
+      float4 acc[NT4];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+      for (int t = 0; t < NT4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         unsigned m = __ballot_sync(0xffffffffu, ar[j] == e);
@@ -68,17 +73,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
           const float gv = __shfl_sync(0xffffffffu, gr[j], src_lane);
           const float* wrow = Wp + (size_t)(src_lane + 32 * j) * D;
 #pragma unroll
-          for (int t = 0; t < NJ; ++t) {
-            const int k = lane + 32 * t;
-            if (k < D) acc[t] = fmaf(gv, W_SMEM ? wrow[k] : __ldg(wrow + k), acc[t]);
+          for (int t = 0; t < NT4; ++t) {
+            const int c4 = lane + 32 * t;
+            if (c4 < D4) {
+              const float4 w = W_SMEM ? *reinterpret_cast<const float4*>(wrow + 4 * c4) : ldg4(wrow + 4 * c4);
+              acc[t].x = fmaf(gv, w.x, acc[t].x); acc[t].y = fmaf(gv, w.y, acc[t].y);
+              acc[t].z = fmaf(gv, w.z, acc[t].z); acc[t].w = fmaf(gv, w.w, acc[t].w);
+            }
           }
         }
       }
       float* out = dX + (size_t)e * D;
 #pragma unroll
-      for (int t = 0; t < NJ; ++t) {
-        const int k = lane + 32 * t;
-        if (k < D) out[k] = acc[t];
+      for (int t = 0; t < NT4; ++t) {
+        const int c4 = lane + 32 * t;
+        if (c4 < D4) st_stream4(out + 4 * c4, acc[t]);
       }
     }
   }

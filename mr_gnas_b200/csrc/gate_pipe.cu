@@ -10,8 +10,9 @@
 //
 // Data movement per row: dy, y_k, x, (xin), (old dx), (old dxin) in, dx (dxin) out -- streamed through a TMA
 // bulk-copy ring (pipe.cuh), one row per consumer warp per tile; per-column constants live in shared memory.
-// Deterministic: per-warp fp32 partials are folded into doubles every 32 rows, per-CTA partials are written to
-// fixed slots and folded in slot order by the finalize kernels.
+// Deterministic: every consumer warp keeps fp32 column partials in registers for its ~rows/(148*16) rows; at the end
+// the 16 warps' partials are summed in double in warp order, per-CTA partials go to fixed slots and the finalize
+// kernels fold them in slot order.
 #include "pipe.cuh"
 
 namespace mrg {
@@ -42,11 +43,10 @@ __global__ void __launch_bounds__(pipe::kPipeThreads, 1) gate_bwd_pipe_kernel(co
   const int D = a.D, D4 = D >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool lazy = a.coef != nullptr, xst = a.xstats != nullptr;
-  double* stA = reinterpret_cast<double*>(smem_raw);                 // [8][2][D]  dv1 | dv2
-  double* stB = stA + stats_smem_doubles(D);                         // [8][2][D]  sum dz | sum dz*y   (if xst)
-  double* dcs = stB + (xst ? stats_smem_doubles(D) : 0);             // [8]
-  float* cst = reinterpret_cast<float*>(dcs + 8);                    // [K_NCONST][D]
-  size_t off = (size_t)((unsigned char*)(cst + K_NCONST * D) - smem_raw);
+  // xin read through the same view as x (the fused cell's "x is x_in" gates): one activation serves both
+  const bool same_act = SAME && a.xin.scale == a.x.scale && a.xin.shift == a.x.shift && a.xin.relu == a.x.relu;
+  float* cst = reinterpret_cast<float*>(smem_raw);                   // [K_NCONST][D]
+  size_t off = (size_t)K_NCONST * D * 4;
   off = (off + 127) / 128 * 128;
   pipe::Ring ring;
   ring.tiles = reinterpret_cast<float*>(smem_raw + off);
@@ -71,15 +71,16 @@ __global__ void __launch_bounds__(pipe::kPipeThreads, 1) gate_bwd_pipe_kernel(co
   }
   ring.init();   // includes __syncthreads: constants visible
 
+  // per-warp fp32 column partials: dv1 | dv2 (dparam) and sum dz | sum dz*y (statistics of x's state)
+  float4 pa1[NV], pa2[NV], pb1[NV], pb2[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) pa1[v] = pa2[v] = pb1[v] = pb2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dc_f = 0.f;
+
   if (warp == pipe::kConsumerWarps) {
     if (lane == 0) ring.produce(a.st, a.rows);
   } else {
     const bool k_relu = lazy && a.yk.relu != 0, x_relu = a.x.relu != 0, i_relu = HAS_IN && a.xin.relu != 0;
-    ColStats<NV> csA, csB;
-    csA.init(stA, D, D4);
-    if (xst) csB.init(stB, D, D4);
-    float dc_f = 0.f;
-    double dc_d = 0.0;
     const int64_t ntiles = (a.rows + pipe::kTileRows - 1) / pipe::kTileRows;
     int it = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -129,15 +130,19 @@ __global__ void __launch_bounds__(pipe::kPipeThreads, 1) gate_bwd_pipe_kernel(co
               x.z = x.z > 0.f ? x.z : 0.f; x.w = x.w > 0.f ? x.w : 0.f;
             }
             if (HAS_IN) {
-              const float4 rin = SAME ? raw : *reinterpret_cast<const float4*>(t_in + 4 * c4);
-              const float4 is = CST(K_ISC), ih = CST(K_ISH);
-              float4 q = make_float4(fmaf(is.x, rin.x, ih.x), fmaf(is.y, rin.y, ih.y), fmaf(is.z, rin.z, ih.z),
-                                     fmaf(is.w, rin.w, ih.w));
-              if (i_relu) {
-                q.x = q.x > 0.f ? q.x : 0.f; q.y = q.y > 0.f ? q.y : 0.f;
-                q.z = q.z > 0.f ? q.z : 0.f; q.w = q.w > 0.f ? q.w : 0.f;
+              if (same_act) {
+                iv[v] = x;
+              } else {
+                const float4 rin = SAME ? raw : *reinterpret_cast<const float4*>(t_in + 4 * c4);
+                const float4 is = CST(K_ISC), ih = CST(K_ISH);
+                float4 q = make_float4(fmaf(is.x, rin.x, ih.x), fmaf(is.y, rin.y, ih.y), fmaf(is.z, rin.z, ih.z),
+                                       fmaf(is.w, rin.w, ih.w));
+                if (i_relu) {
+                  q.x = q.x > 0.f ? q.x : 0.f; q.y = q.y > 0.f ? q.y : 0.f;
+                  q.z = q.z > 0.f ? q.z : 0.f; q.w = q.w > 0.f ? q.w : 0.f;
+                }
+                iv[v] = q;
               }
-              iv[v] = q;
             }
             dv[v] = d;
             xv[v] = x;
@@ -172,51 +177,63 @@ __global__ void __launch_bounds__(pipe::kPipeThreads, 1) gate_bwd_pipe_kernel(co
               }
               st_stream4(a.dxin + goff, oi);
             }
-            csA.add(make_float4(dt * xv[v].x, dt * xv[v].y, dt * xv[v].z, dt * xv[v].w),
-                    make_float4(dt * iv[v].x, dt * iv[v].y, dt * iv[v].z, dt * iv[v].w), v);
+            pa1[v].x = fmaf(dt, xv[v].x, pa1[v].x); pa1[v].y = fmaf(dt, xv[v].y, pa1[v].y);
+            pa1[v].z = fmaf(dt, xv[v].z, pa1[v].z); pa1[v].w = fmaf(dt, xv[v].w, pa1[v].w);
+            if (HAS_IN) {
+              pa2[v].x = fmaf(dt, iv[v].x, pa2[v].x); pa2[v].y = fmaf(dt, iv[v].y, pa2[v].y);
+              pa2[v].z = fmaf(dt, iv[v].z, pa2[v].z); pa2[v].w = fmaf(dt, iv[v].w, pa2[v].w);
+            }
             if (xst) {
               float4 z = o;
               if (x_relu) {
                 z.x = xv[v].x > 0.f ? z.x : 0.f; z.y = xv[v].y > 0.f ? z.y : 0.f;
                 z.z = xv[v].z > 0.f ? z.z : 0.f; z.w = xv[v].w > 0.f ? z.w : 0.f;
               }
-              csB.add(z, make_float4(z.x * xr[v].x, z.y * xr[v].y, z.z * xr[v].z, z.w * xr[v].w), v);
+              pb1[v].x += z.x; pb1[v].y += z.y; pb1[v].z += z.z; pb1[v].w += z.w;
+              pb2[v].x = fmaf(z.x, xr[v].x, pb2[v].x); pb2[v].y = fmaf(z.y, xr[v].y, pb2[v].y);
+              pb2[v].z = fmaf(z.z, xr[v].z, pb2[v].z); pb2[v].w = fmaf(z.w, xr[v].w, pb2[v].w);
             }
 #undef CST
           }
-        }
-        csA.row_done(D, D4);
-        if (xst) csB.row_done(D, D4);
-        if (csA.pending == 0) {
-          dc_d += dc_f;
-          dc_f = 0.f;
         }
       }
       __syncwarp();
       if (lane == 0) pipe::mbar_arrive(ring.empty + s);
     }
-    csA.fold(D, D4);
-    if (xst) csB.fold(D, D4);
-    dc_d += dc_f;
-    if (lane == 0) dcs[warp] = dc_d;
+  }
+  // ---- fold the 16 warps' partials in warp order (the ring memory is free: every tile was consumed)
+  __syncthreads();
+  float* red = ring.tiles;                        // [kConsumerWarps][4*D + 4] floats (rows stay 16-byte aligned)
+  const int stride = 4 * D + 4;
+  if (warp < pipe::kConsumerWarps) {
+    float* r = red + (size_t)warp * stride;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c4 = lane + 32 * v;
+      if (c4 < D4) {
+        *reinterpret_cast<float4*>(r + 4 * c4) = pa1[v];
+        *reinterpret_cast<float4*>(r + D + 4 * c4) = pa2[v];
+        *reinterpret_cast<float4*>(r + 2 * D + 4 * c4) = pb1[v];
+        *reinterpret_cast<float4*>(r + 3 * D + 4 * c4) = pb2[v];
+      }
+    }
+    if (lane == 0) r[4 * D] = dc_f;
   }
   __syncthreads();
   double* part = a.dparam + (size_t)blockIdx.x * (2 * D + 1);
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) t += stA[(size_t)w * 2 * D + c];
-    part[c] = t;
-    if (xst) {
-      double u = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarpsPerBlock; ++w) u += stB[(size_t)w * 2 * D + c];
-      a.xstats[(size_t)blockIdx.x * 2 * D + c] = u;
+    double t = 0.0, u = 0.0;
+#pragma unroll 4
+    for (int w = 0; w < pipe::kConsumerWarps; ++w) {
+      t += (double)red[(size_t)w * stride + c];
+      u += (double)red[(size_t)w * stride + 2 * D + c];
     }
+    part[c] = t;
+    if (xst) a.xstats[(size_t)blockIdx.x * 2 * D + c] = u;
   }
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w) t += dcs[w];
+    for (int w = 0; w < pipe::kConsumerWarps; ++w) t += (double)red[(size_t)w * stride + 4 * D];
     part[2 * D] = t;
   }
 }
@@ -252,10 +269,15 @@ extern "C" int mrg_sparse_gate_bwd_fused(mrg_grad dy, mrg_act x, mrg_act xin, co
   a.yk = dy.y; a.x = x; a.xin = xin; a.coef = dy.coef; a.gate = gate; a.v1 = v1; a.v2 = v2;
   a.row_scale = row_scale; a.base_scale = base_scale; a.dx = dx; a.dxin = dxin; a.dparam = dparam;
   a.xstats = x_bwd_stats; a.rows = rows; a.D = D;
-  const size_t fixed = (size_t)stats_smem_doubles(D) * 8 * (x_bwd_stats ? 2 : 1) + 8 * 8 + (size_t)K_NCONST * D * 4 + 128;
+  const size_t fixed = (size_t)K_NCONST * D * 4 + 256;
   const size_t budget = 220 * 1024;
   int stages = 8;
   while (stages > 2 && fixed + pipe::ring_bytes(stages, a.st.n, D) > budget) --stages;
+  // the final fold reuses the ring memory: kConsumerWarps * (4D+4) floats <= 2 streams x 2 stages x 16 rows x D floats
+  if (pipe::ring_bytes(stages, a.st.n, D) < (size_t)pipe::kConsumerWarps * (4 * D + 4) * 4) {
+    set_error("sparse_gate_bwd_fused: ring smaller than the fold scratch");
+    return MRG_ERR_INVALID;
+  }
   a.stages = stages;
   const size_t smem = fixed + pipe::ring_bytes(stages, a.st.n, D);
   if (smem > budget) {

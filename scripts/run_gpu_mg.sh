@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 N=${1:-2}
-timeout 600 python -m pytest tests/test_gpu_partition.py -x -q > gpurun_out/pytest_partition.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_partition.py -x -q > gpurun_out/pytest_partition.log 2>&1
 echo "partition pytest exit $?"; tail -15 gpurun_out/pytest_partition.log
 for mode in "" "--partition"; do
   tag=dp; [ -n "$mode" ] && tag=part
