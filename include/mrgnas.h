@@ -282,6 +282,23 @@ int mrg_sigmoid_bce_fwd(const float* logit, const float* label, int64_t n, float
 int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64_t n, const float* gscale, float* dlogit,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K7+K8 fused  DistMult 1-N scoring + sigmoid + BCE in one tcgen05 kernel (3xTF32 operands, fp32 TMEM
+ * accumulation): replaces torch.mm(sub_emb * rel_emb, all_ent.T) (operations_lp.py:121-125) + torch.sigmoid
+ * (:126) + nn.BCELoss (train/mr_lp_train.py:116,235) for the training loss (model_lp.py:148-150).
+ *   logit[b,n] = sum_k query[b,k] * ent[n,k]        query = sub_emb * rel_emb  [B, D],  ent [N, D]
+ *   loss       = mean_{b,n} -( y*max(log p,-100) + (1-y)*max(log(1-p),-100) ),  p = sigmoid(logit), y = label[b,n]
+ * The [B,N] logits are written once (the backward, mrg_sigmoid_bce_bwd, needs them); probabilities are never
+ * materialised.  partial: mrg_distmult_bce_nparts(B) doubles.  Requires D % 8 == 0, D <= 256; any B (256 query
+ * rows per launch), any N (one destination-partition rank passes its own entity rows and label columns).
+ * ---------------------------------------------------------------------------------- */
+int mrg_distmult_bce_supported(int32_t D);
+int32_t mrg_distmult_bce_nparts(int64_t B);
+size_t mrg_distmult_bce_workspace_bytes(int32_t D);
+int mrg_distmult_bce_fwd(const float* query, const float* ent, const float* label, int64_t B, int64_t N, int32_t D,
+                         float* logit, double* partial, float* loss, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

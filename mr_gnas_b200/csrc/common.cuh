@@ -36,8 +36,9 @@ int cuda_fail(cudaError_t e, const char* what);
 
 inline bool valid_D(int D) { return D > 0 && D % 4 == 0 && D <= 512; }
 inline int nv_for(int D) { return D <= 128 ? 1 : (D <= 256 ? 2 : 4); }
+constexpr int kMinRowsPerWarp = 8;       // small (node-level) launches: fewer CTAs -> fewer partials for the finalize kernels
 inline int stats_grid(int64_t rows) {
-  int64_t need = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t need = (rows + kWarpsPerBlock * kMinRowsPerWarp - 1) / (kWarpsPerBlock * kMinRowsPerWarp);
   if (need < 1) need = 1;
   return (int)(need < kMaxParts ? need : kMaxParts);
 }
@@ -107,6 +108,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ float sigmoidf_(float t) { return 1.0f / (1.0f + expf(-t)); }
+
+// one element of sigmoid + BCELoss with torch's log clamp at -100 (operations_lp.py:126, mr_lp_train.py:116)
+__device__ __forceinline__ float bce_term(float logit, float yv, float* p_out) {
+  const float p = sigmoidf_(logit);
+  *p_out = p;
+  const float lp = fmaxf(logf(p), -100.f);
+  const float l1p = fmaxf(logf(1.f - p), -100.f);
+  return -(yv * lp + (1.f - yv) * l1p);
+}
 
 // Per-lane view of an mrg_act: column affine held in registers.
 template <int NV>

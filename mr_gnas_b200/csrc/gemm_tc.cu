@@ -156,7 +156,15 @@ struct AmaxParams {
   unsigned long long* packed;  // [N, D] zero-initialised
   int64_t E;
   int D, MH, Kp, nchunks, num_tiles;
+  int Dout;                  // rows of W actually present (amax: D; DistMult: query rows of this launch)
+  // EPI_DISTMULT: logits [Dout, ldl] row-major (row b, column = tile position), labels likewise
+  const float* label;
+  float* logit;
+  double* loss_partial;      // [gridDim.x]
+  int64_t ldl;
 };
+
+enum { EPI_AMAX = 0, EPI_DISTMULT = 1 };
 
 // One work ITEM = (tile, K chunk).  A CTA walks its tiles in PAIRS (TMEM slots 0/1) with the chunks of the
 // two tiles interleaved, so every W chunk fetched from L2 feeds two tiles (W re-streaming is the dominant
@@ -181,7 +189,7 @@ __device__ __forceinline__ Item item_of(int q, int nchunks, int full_pairs) {
 }
 
 // dynamic smem (1024-B aligned): W ring [WS][Whi MH tiles | Wlo MH tiles], X ring [XS][Xhi | Xlo], small arrays
-template <int MH>
+template <int MH, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t WSTAGE = 2 * MH * TILE_BYTES;
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   int32_t* s_dst = (int32_t*)(s_bias + 256);          // [2 slots][128]
   int32_t* s_eid = s_dst + 2 * TILE_E;                // [2 slots][128]
   uint32_t* s_flag = (uint32_t*)(s_eid + 2 * TILE_E); // [2 slots][4] segment-start bitmask of the tile's columns
+  double* s_loss = (double*)(s_flag + 8);             // [8] per-epilogue-warp BCE partial (EPI_DISTMULT)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = p.D;
@@ -263,7 +272,8 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       const Item it = item_of(q, p.nchunks, full_pairs);
       if (it.c == 0) {
         const int64_t pos = tile_of(it.pair, it.slot) * TILE_E + r;
-        const float* v = pos < p.E ? p.x.data + (size_t)__ldg(p.csr_eid + pos) * D : nullptr;
+        const float* v = pos < p.E ? p.x.data + (size_t)(p.csr_eid ? __ldg(p.csr_eid + pos) : (int32_t)pos) * D
+                                   : nullptr;
         if (it.slot) xrow1 = v;
         else xrow0 = v;
       }
@@ -386,6 +396,51 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     const int quad = warp & 3;                        // TMEM lane quadrant of this warp
     int32_t* sd = s_dst + ts * TILE_E;
     int32_t* se = s_eid + ts * TILE_E;
+    if (EPI == EPI_DISTMULT) {
+      // ---- DistMult 1-N scores + BCE: TMEM lane = query row b, TMEM column = entity of the tile.
+      // logit[b, n] is stored for the backward; the loss terms are summed per thread (fp32 per 32 columns,
+      // double across), per warp, per CTA -> loss_partial[cta]; nothing else leaves the SM.
+      double acc = 0.0;
+      for (int pr = 0; pr < npairs; ++pr) {
+        if (2 * pr + ts >= my_tiles) break;
+        const int64_t pos0 = tile_of(pr, ts) * TILE_E;
+        const int cnt = (int)min((int64_t)TILE_E, p.E - pos0);
+        mbar_wait(&tfull_bar[ts], pr & 1);
+        tc_fence_after();
+        for (int h = 0; h < MH; ++h) {
+          const int b = h * 128 + et;
+          const bool bvalid = b < p.Dout;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * (MH * TILE_E) + h * TILE_E;
+          const float* lab = p.label + (size_t)b * p.ldl + pos0;
+          float* lo = p.logit + (size_t)b * p.ldl + pos0;
+#pragma unroll 1
+          for (int w = 0; w < 4; ++w) {
+            const int cb = 32 * w;
+            if (cb >= cnt) break;   // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(taddr + cb, v);
+            if (bvalid) {
+              float facc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (cb + j < cnt) {
+                  const float z = __uint_as_float(v[j]);
+                  float pr_;
+                  facc += bce_term(z, __ldg(lab + cb + j), &pr_);
+                  lo[cb + j] = z;
+                }
+              }
+              acc += (double)facc;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[ts]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) s_loss[warp - EPI_WARP0] = acc;
+    } else {
     for (int pr = 0; pr < npairs; ++pr) {
       if (2 * pr + ts >= my_tiles) break;
       const int64_t pos0 = tile_of(pr, ts) * TILE_E;
@@ -412,7 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       tc_fence_after();
       for (int h = 0; h < MH; ++h) {
         const int f = h * 128 + et;
-        const bool fvalid = f < D;
+        const bool fvalid = f < p.Dout;
         const float bias = s_bias[f & 255];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * (MH * TILE_E) + h * TILE_E;
         // Register-only segmented max.  relu(v) >= 0, so starting every segment at (best = 0, bcol = first column)
@@ -469,10 +524,16 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       tc_fence_before();
       mbar_arrive(&tempty_bar[ts]);
     }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (EPI == EPI_DISTMULT && threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_loss[w];
+    p.loss_partial[blockIdx.x] = t;
+  }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -547,23 +608,98 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   p.Kp = Kp;
   p.nchunks = Kp / tc::KCH;
   p.num_tiles = (int)((E + tc::TILE_E - 1) / tc::TILE_E);
+  p.Dout = D;
+  p.label = nullptr;
+  p.logit = nullptr;
+  p.loss_partial = nullptr;
+  p.ldl = 0;
   if (p.num_tiles > 0) {
     const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
                         1024 /*align*/ + 8192 /*tail*/;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     if (MH == 1) {
-      e = cudaFuncSetAttribute(tc::amax_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<1, tc::EPI_AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
-      tc::amax_tc_kernel<1><<<grid, tc::THREADS, smem, st>>>(p);
+      tc::amax_tc_kernel<1, tc::EPI_AMAX><<<grid, tc::THREADS, smem, st>>>(p);
     } else {
-      e = cudaFuncSetAttribute(tc::amax_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<2, tc::EPI_AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
-      tc::amax_tc_kernel<2><<<grid, tc::THREADS, smem, st>>>(p);
+      tc::amax_tc_kernel<2, tc::EPI_AMAX><<<grid, tc::THREADS, smem, st>>>(p);
     }
   }
   const int64_t n = N * D;
   tc::amax_finalize_kernel<<<(int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(packed, n, D, residual,
                                                                                                   out, arg);
   MRG_LAUNCH_CHECK("amax_tc_fwd");
+  return MRG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K7+K8 fused: DistMult 1-N scoring + sigmoid + BCE on the same tcgen05 main loop.
+//   logit[b, n] = sum_k query[b,k] * ent[n,k]   (3xTF32, fp32-class accuracy),  loss = mean BCE(sigmoid(logit), label)
+// "W" of the main loop is the [B<=256, D] query block (pre-split hi/lo image), the tile rows are entities.
+// ------------------------------------------------------------------------------------------
+__global__ void distmult_loss_finalize_kernel(const double* __restrict__ partial, int nparts, double n, float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int p = 0; p < nparts; ++p) t += partial[p];
+    loss[0] = (float)(t / n);
+  }
+}
+
+extern "C" int mrg_distmult_bce_supported(int32_t D) { return mrg_amax_tc_supported(D); }
+extern "C" int32_t mrg_distmult_bce_nparts(int64_t B) { return (int32_t)((B + 255) / 256) * kNumSMs; }
+extern "C" size_t mrg_distmult_bce_workspace_bytes(int32_t D) {
+  const int Kp = (D + tc::KCH - 1) / tc::KCH * tc::KCH;
+  return (size_t)2 * 2 * 128 * Kp * sizeof(float) + 1024;
+}
+
+extern "C" int mrg_distmult_bce_fwd(const float* query, const float* ent, const float* label, int64_t B, int64_t N,
+                                    int32_t D, float* logit, double* partial, float* loss, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  MRG_CHECK_ARG(query && ent && label && logit && partial && loss && workspace, "distmult_bce_fwd: null pointer");
+  MRG_CHECK_ARG(B > 0 && N > 0, "distmult_bce_fwd: sizes");
+  MRG_CHECK_ARG(mrg_distmult_bce_supported(D), "distmult_bce_fwd: D must be a multiple of 8 and <= 256");
+  if (workspace_bytes < mrg_distmult_bce_workspace_bytes(D)) {
+    set_error("distmult_bce_fwd: workspace too small");
+    return MRG_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = (D + tc::KCH - 1) / tc::KCH * tc::KCH;
+  const int nparts = mrg_distmult_bce_nparts(B);
+  cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)nparts * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "distmult_bce_fwd memset");
+  int chunk = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += 256, ++chunk) {
+    const int rows = (int)(B - b0 < 256 ? B - b0 : 256);
+    const int MH = rows <= 128 ? 1 : 2;
+    tc::tf32_split_kernel<<<64, 256, 0, st>>>(query + (size_t)b0 * D, rows, D, MH, Kp / tc::KCH, (float*)workspace);
+    tc::AmaxParams p;
+    p.x.data = ent; p.x.scale = nullptr; p.x.shift = nullptr; p.x.relu = 0;
+    p.csr_eid = nullptr; p.dst = nullptr;
+    p.wimg = (const float*)workspace;
+    p.bias = nullptr; p.packed = nullptr;
+    p.E = N; p.D = D; p.MH = MH; p.Kp = Kp; p.nchunks = Kp / tc::KCH;
+    p.num_tiles = (int)((N + tc::TILE_E - 1) / tc::TILE_E);
+    p.Dout = rows;
+    p.label = label + (size_t)b0 * N;
+    p.logit = logit + (size_t)b0 * N;
+    p.loss_partial = partial + (size_t)chunk * kNumSMs;
+    p.ldl = N;
+    const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
+                        1024 /*align*/ + 8192 /*tail*/;
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    if (MH == 1) {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<1, tc::EPI_DISTMULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "distmult_bce_fwd smem attr");
+      tc::amax_tc_kernel<1, tc::EPI_DISTMULT><<<grid, tc::THREADS, smem, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<2, tc::EPI_DISTMULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "distmult_bce_fwd smem attr");
+      tc::amax_tc_kernel<2, tc::EPI_DISTMULT><<<grid, tc::THREADS, smem, st>>>(p);
+    }
+  }
+  distmult_loss_finalize_kernel<<<1, 32, 0, st>>>(partial, nparts, (double)B * (double)N, loss);
+  MRG_LAUNCH_CHECK("distmult_bce_fwd");
   return MRG_OK;
 }

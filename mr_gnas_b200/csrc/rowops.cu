@@ -656,14 +656,6 @@ __global__ void __launch_bounds__(kThreads) dense_gate_bwd_kernel(const float* _
 // ---------------------------------------------------------------------------------------
 constexpr int kBceBlocks = kNumSMs * 8;
 
-__device__ __forceinline__ float bce_term(float logit, float yv, float* p_out) {
-  const float p = sigmoidf_(logit);
-  *p_out = p;
-  const float lp = fmaxf(logf(p), -100.f);
-  const float l1p = fmaxf(logf(1.f - p), -100.f);
-  return -(yv * lp + (1.f - yv) * l1p);
-}
-
 __global__ void __launch_bounds__(kThreads) sigmoid_bce_fwd_kernel(const float* __restrict__ logit,
                                                                    const float* __restrict__ label, int64_t n,
                                                                    float* __restrict__ pred,

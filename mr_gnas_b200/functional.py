@@ -444,6 +444,49 @@ class SigmoidBCE(torch.autograd.Function):
         return dl, None
 
 
+_dm_ws = {}
+
+
+class DistMultBCE(torch.autograd.Function):
+    """loss = BCELoss(sigmoid((sub_emb * rel_emb) @ all_ent.T), label) in ONE tcgen05 kernel (mrg_distmult_bce_fwd):
+    sf_DisMult_op.forward (operations_lp.py:115-127) + nn.BCELoss (mr_lp_train.py:116) for the training loss.
+    Backward: dlogit from the stored logits (mrg_sigmoid_bce_bwd), then the two plain library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, all_ent, sub_emb, rel_emb, label):
+        all_ent, sub_emb, rel_emb, label = _f32c(all_ent), _f32c(sub_emb), _f32c(rel_emb), _f32c(label)
+        lib = _lib.load()
+        B, D = sub_emb.shape
+        N = all_ent.shape[0]
+        dev = all_ent.device
+        query = (sub_emb * rel_emb).contiguous()
+        key = (D, str(dev))
+        if key not in _dm_ws:
+            _dm_ws[key] = torch.empty(int(lib.mrg_distmult_bce_workspace_bytes(D)), dtype=torch.uint8, device=dev)
+        ws = _dm_ws[key]
+        logit = torch.empty(B, N, dtype=torch.float32, device=dev)
+        partial = torch.empty(int(lib.mrg_distmult_bce_nparts(B)), dtype=torch.float64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        call("mrg_distmult_bce_fwd", ptr(query), ptr(all_ent), ptr(label), B, N, D, ptr(logit), ptr(partial), ptr(loss),
+             ptr(ws), ws.numel(), stream(), nbytes=N * D * 4 + 2 * B * N * 4)
+        ctx.save_for_backward(logit, label, all_ent, sub_emb, rel_emb, query)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        logit, label, all_ent, sub_emb, rel_emb, query = ctx.saved_tensors
+        dl = torch.empty_like(logit)
+        gs = gl.reshape(1).float().contiguous()
+        call("mrg_sigmoid_bce_bwd", ptr(logit), ptr(label), logit.numel(), ptr(gs), ptr(dl), stream())
+        dq = torch.mm(dl, all_ent)
+        dent = torch.mm(dl.t(), query) if ctx.needs_input_grad[0] else None
+        return dent, dq * rel_emb, dq * sub_emb, None
+
+
+def distmult_bce_supported(D):
+    return bool(_lib.load().mrg_distmult_bce_supported(int(D)))
+
+
 # ------------------------------------------------------------------------------------------
 # plain ReLU through the same row kernels (NC OpModule without op_norm: model.py:22-28)
 # ------------------------------------------------------------------------------------------

@@ -291,6 +291,8 @@ class sf_DisMult_op(nn.Module):
         return torch.sigmoid(self.logits(all_ent, sub_emb, rel_emb))
 
     def loss(self, all_ent, sub_emb, rel_emb, label):
+        if USE_TENSOR_CORES and all_ent.is_cuda and K.distmult_bce_supported(all_ent.shape[1]):
+            return K.DistMultBCE.apply(all_ent, sub_emb, rel_emb, label)     # fused tcgen05 GEMM + BCE
         return K.SigmoidBCE.apply(self.logits(all_ent, sub_emb, rel_emb), label)
 
 

@@ -399,3 +399,30 @@ def test_sparse_gate_bwd_fused_vs_fp64(dev, D, variant):
     _check("dc", dp[2 * D:].float(), dt.sum().view(1).float())
     if want_stats:
         _check("x bwd stats", xst.view(nparts, 2, D).sum(0).float(), st_ref.float())
+
+
+# ------------------------------------------------------------------------------ fused DistMult + BCE (tcgen05)
+@pytest.mark.parametrize("B,N,D", [(256, 14541, 200), (32, 700, 64), (300, 1000, 128), (1, 5, 8), (130, 257, 256)])
+def test_distmult_bce_fused_vs_fp64(dev, B, N, D):
+    """mrg_distmult_bce_fwd (3xTF32 tcgen05 GEMM + sigmoid + BCE epilogue) and its backward against fp64 torch:
+    sf_DisMult_op.forward (operations_lp.py:115-127) + nn.BCELoss; ragged last tile, B > 256 (two launches),
+    B < 128 (one accumulator half)."""
+    from mr_gnas_b200 import functional as K
+    torch.manual_seed(B + N + D)
+    ent = (torch.randn(N, D, device=dev) * 0.3).requires_grad_(True)
+    sub = (torch.randn(B, D, device=dev) * 0.5).requires_grad_(True)
+    rel = (torch.randn(B, D, device=dev) * 0.5).requires_grad_(True)
+    label = ((torch.rand(B, N, device=dev) < 0.05).float() * 0.9 + 1.0 / N).clamp(max=1.0)
+    loss = K.DistMultBCE.apply(ent, sub, rel, label)
+    loss.backward()
+    e64, s64, r64 = (t.detach().double().requires_grad_(True) for t in (ent, sub, rel))
+    logit64 = (s64 * r64) @ e64.t()
+    ref = torch.nn.functional.binary_cross_entropy(torch.sigmoid(logit64), label.double())
+    ref.backward()
+    _check("loss", loss.view(1), ref.view(1).float())
+    _check("d all_ent", ent.grad, e64.grad.float())
+    _check("d sub_emb", sub.grad, s64.grad.float())
+    _check("d rel_emb", rel.grad, r64.grad.float())
+    # and against the unfused library path of this repo on the same inputs
+    loss_u = K.SigmoidBCE.apply(torch.mm((sub * rel).detach(), ent.detach().t()), label)
+    _check("loss vs cuBLAS + sigmoid_bce kernel", loss.view(1), loss_u.view(1))
