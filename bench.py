@@ -307,9 +307,20 @@ def main():
         trip_d, y_d = dev_batches[i % len(dev_batches)]
         return runner(trip_d[:, 0], trip_d[:, 1], y_d)
 
+    primed = {"ok": False}
+
     def step_e2e(i):                         # inputs in pinned host memory, loss read back
-        t_h, y_h = host_batches[i % len(host_batches)]
-        return runner(t_h[:, 0], t_h[:, 1], y_h).item()
+        # Every step's batch crosses PCIe inside the timed region.  The copy of batch i+1 is enqueued on a side
+        # stream right after step i is enqueued, so it overlaps the step (double-buffered staging set) the way a
+        # DataLoader-fed loop would; step i itself consumes the batch staged during step i-1.
+        if not primed["ok"]:
+            t_h, y_h = host_batches[i % len(host_batches)]
+            runner.prefetch(t_h[:, 0], t_h[:, 1], y_h)
+            primed["ok"] = True
+        loss = runner()
+        t_n, y_n = host_batches[(i + 1) % len(host_batches)]
+        runner.prefetch(t_n[:, 0], t_n[:, 1], y_n)
+        return loss.item()                   # device -> host read of the step's result
 
     def barrier():
         if world > 1:

@@ -27,6 +27,14 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = None
         self._warmup = warmup
+        # input pipeline: the NEXT batch is copied host->device on a side stream into a staging set while the
+        # current step runs; the step then moves it into the graph's static inputs with device-to-device copies
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [(torch.zeros_like(self.subj), torch.zeros_like(self.rel), torch.zeros_like(self.label))
+                       for _ in range(2)]
+        self._staged = [None, None]      # event recorded after the staging copies
+        self._consumed = [None, None]    # event recorded after the step copied the staging set out
+        self._next = 0
 
     def _eager(self):
         self.opt.zero_grad(set_to_none=True)
@@ -57,9 +65,36 @@ class GraphedTrainStep:
         self.rel.copy_(rel, non_blocking=True)
         self.label.copy_(label, non_blocking=True)
 
+    def prefetch(self, subj, rel, label):
+        """Start copying a (pinned host) batch into a staging set; the next __call__() without arguments runs it."""
+        k = self._next
+        with torch.cuda.stream(self._copy_stream):
+            if self._consumed[k] is not None:
+                self._copy_stream.wait_event(self._consumed[k])
+            for dst, src in zip(self._stage[k], (subj, rel, label)):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged[k] = ev
+        self._next = 1 - k
+
+    def _take_staged(self):
+        k = 1 - self._next              # the set filled by the most recent prefetch()
+        if self._staged[k] is None:
+            return False
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged[k])
+        self.load(*self._stage[k])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._consumed[k], self._staged[k] = ev, None
+        return True
+
     def __call__(self, subj=None, rel=None, label=None):
         if subj is not None:
             self.load(subj, rel, label)
+        else:
+            self._take_staged()
         if self.graph is None:
             return self._eager().detach()
         self.graph.replay()
