@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpurun -- bash run_gpu.sh [tests|bench|all]   (outputs under gpurun_out/)
+# usage: gpurun -- bash scripts/run_gpu.sh [tests|bench|all]   (outputs under gpurun_out/)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 what=${1:-all}
