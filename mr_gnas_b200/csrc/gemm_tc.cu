@@ -264,29 +264,53 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     const int half = lane / RPW;               // which 16-byte units of a 128-byte chunk: TPR*j + half
     const bool affine = p.x.scale != nullptr, relu = p.x.relu != 0;
     const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
-    const float* xrow0 = nullptr;   // load cursor's row, slot 0 / slot 1
+    // The producers share the SM's issue slots with the epilogue and sit on the critical path (profiles/r01: ~540
+    // warp instructions per item and warp before this rewrite): item coordinates are tracked incrementally (no
+    // divisions), per-thread shared-memory offsets and per-tile row pointers are hoisted, the BN affine is read
+    // with 128-bit shared loads.
+    struct Cur { int pair, c, slot; };
+    auto advance = [&](Cur& k) {
+      if (k.pair < full_pairs && k.slot == 0) { k.slot = 1; return; }
+      k.slot = 0;
+      if (++k.c == p.nchunks) { k.c = 0; ++k.pair; }
+    };
+    uint32_t uoff[NU];
+    int ucol[NU];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      const int u = TPR * j + half;
+      uoff[j] = roff + (uint32_t)((u ^ (r & 7)) << 4);
+      ucol[j] = 4 * u;
+    }
+    const float* xrow0 = nullptr;   // load cursor's row per slot (null: past the last edge)
     const float* xrow1 = nullptr;
+    bool cvalid0 = false, cvalid1 = false;   // consume cursor's row validity per slot
     float4 buf[PD][NU];
+    Cur lc = {0, 0, 0}, cc = {0, 0, 0};
     int lq = 0;
-    auto load = [&](float4(&b)[NU], int q) {
-      const Item it = item_of(q, p.nchunks, full_pairs);
-      if (it.c == 0) {
-        const int64_t pos = tile_of(it.pair, it.slot) * TILE_E + r;
+    auto load = [&](float4(&b)[NU]) {
+      if (lc.c == 0) {
+        const int64_t pos = tile_of(lc.pair, lc.slot) * TILE_E + r;
         const float* v = pos < p.E ? p.x.data + (size_t)(p.csr_eid ? __ldg(p.csr_eid + pos) : (int32_t)pos) * D
                                    : nullptr;
-        if (it.slot) xrow1 = v;
+        if (lc.slot) xrow1 = v;
         else xrow0 = v;
       }
-      const float* xr = it.slot ? xrow1 : xrow0;
+      const float* xr = lc.slot ? xrow1 : xrow0;
+      const int c0 = lc.c * KCH;
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        const int col = it.c * KCH + 4 * (TPR * j + half);
-        b[j] = (xr && col < D) ? ld_stream4(xr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int j = 0; j < NU; ++j)
+        b[j] = (xr && c0 + ucol[j] < D) ? ld_stream4(xr + c0 + ucol[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      advance(lc);
     };
     auto consume = [&](float4(&b)[NU], int q) {
-      const Item it = item_of(q, p.nchunks, full_pairs);
-      const bool valid = tile_of(it.pair, it.slot) * TILE_E + r < p.E;
+      if (cc.c == 0) {
+        const bool ok = tile_of(cc.pair, cc.slot) * TILE_E + r < p.E;
+        if (cc.slot) cvalid1 = ok;
+        else cvalid0 = ok;
+      }
+      const bool valid = cc.slot ? cvalid1 : cvalid0;
+      const int c0 = cc.c * KCH;
       const int s = q % XS;
       const uint32_t ph = (q / XS) & 1;
       mbar_wait(&xempty_bar[s], ph ^ 1);
@@ -294,15 +318,16 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       uint8_t* xlo = xhi + TILE_BYTES;
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
-        const int u = TPR * j + half;
-        const int col = it.c * KCH + 4 * u;
+        const int col = c0 + ucol[j];
         float4 v = b[j];
         if (valid && col < D) {
           if (affine) {
-            v.x = fmaf(s_scale[col], v.x, s_shift[col]);
-            v.y = fmaf(s_scale[col + 1], v.y, s_shift[col + 1]);
-            v.z = fmaf(s_scale[col + 2], v.z, s_shift[col + 2]);
-            v.w = fmaf(s_scale[col + 3], v.w, s_shift[col + 3]);
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + col);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + col);
+            v.x = fmaf(sc.x, v.x, sh.x);
+            v.y = fmaf(sc.y, v.y, sh.y);
+            v.z = fmaf(sc.z, v.z, sh.z);
+            v.w = fmaf(sc.w, v.w, sh.w);
           }
           if (relu) {
             v.x = v.x > 0.f ? v.x : 0.f;
@@ -313,16 +338,16 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         }
         const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);  // exact; MMA truncates to tf32
-        const uint32_t off = roff + (uint32_t)((u ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(xhi + off) = hi;
-        *reinterpret_cast<float4*>(xlo + off) = lo;
+        *reinterpret_cast<float4*>(xhi + uoff[j]) = hi;
+        *reinterpret_cast<float4*>(xlo + uoff[j]) = lo;
       }
       fence_proxy_async();
       mbar_arrive(&xfull_bar[s]);
+      advance(cc);
     };
 #pragma unroll
     for (int u = 0; u < PD; ++u) {
-      if (lq < total) load(buf[u], lq);
+      if (lq < total) load(buf[u]);
       ++lq;
     }
     for (int q = 0; q < total; q += PD) {
@@ -330,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       for (int u = 0; u < PD; ++u) {
         if (q + u < total) {
           consume(buf[u], q + u);
-          if (lq < total) load(buf[u], lq);
+          if (lq < total) load(buf[u]);
           ++lq;
         }
       }
