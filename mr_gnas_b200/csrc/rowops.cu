@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(mrg_act x, int64_t r
 
 
 // ---------------------------------------------------------------------------------------
-// Deterministic folding of per-CTA partials: a 256-thread block owns 8 columns; 32 "part
-// lanes" stride over the partial rows, then combine through shared memory in a fixed order.
+// Deterministic folding of per-CTA partials: a 512-thread block owns 4 columns; 128 "part
+// lanes" stride over the partial rows, then combine through shared memory in a fixed tree.
 // ---------------------------------------------------------------------------------------
-constexpr int kFinCols = 8;
-constexpr int kFinLanes = 32;
+constexpr int kFinCols = 4;
+constexpr int kFinLanes = 128;
 __device__ __forceinline__ double fold_parts(const double* __restrict__ base, int nparts, size_t row_stride, int col,
                                              bool valid, double* sm /* [kFinLanes][kFinCols] */) {
   const int cc = threadIdx.x % kFinCols, pl = threadIdx.x / kFinCols;
@@ -169,9 +169,12 @@ __device__ __forceinline__ double fold_parts(const double* __restrict__ base, in
     for (int p = pl; p < nparts; p += kFinLanes) t += base[(size_t)p * row_stride + col];
   sm[pl * kFinCols + cc] = t;
   __syncthreads();
-  double r = 0.0;
-  if (pl == 0)
-    for (int q = 0; q < kFinLanes; ++q) r += sm[q * kFinCols + cc];
+#pragma unroll
+  for (int s = kFinLanes / 2; s > 0; s >>= 1) {   // fixed tree: deterministic
+    if (pl < s) sm[pl * kFinCols + cc] += sm[(pl + s) * kFinCols + cc];
+    __syncthreads();
+  }
+  const double r = sm[cc];
   __syncthreads();
   return r;  // valid in part-lane 0 threads
 }
