@@ -283,6 +283,16 @@ int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64_t n, const
                         void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Evaluation: filtered rank of the target object of every query.  Replaces the
+ * torch.where + double argsort over [B, N] of predict() (train/mr_lp_train.py:289-302):
+ *   rank[b] = 1 + #{ n : v(b,n) > v(b,obj[b])  or  (v(b,n) == v(b,obj[b]) and n < obj[b]) },
+ *   v(b,n) = -1e7 if label[b,n] != 0 and n != obj[b] else pred[b,n]        (stable descending order)
+ * pred, label: [B, N] fp32 row-major; obj: [B] int64 (the reference's triplets[:, 2]); rank: [B] int32.
+ * ---------------------------------------------------------------------------------- */
+int mrg_filtered_rank(const float* pred, const float* label, const int64_t* obj, int64_t B, int64_t N, int32_t* rank,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K7+K8 fused  DistMult 1-N scoring + sigmoid + BCE in one tcgen05 kernel (3xTF32 operands, fp32 TMEM
  * accumulation): replaces torch.mm(sub_emb * rel_emb, all_ent.T) (operations_lp.py:121-125) + torch.sigmoid
  * (:126) + nn.BCELoss (train/mr_lp_train.py:116,235) for the training loss (model_lp.py:148-150).

@@ -655,6 +655,39 @@ __global__ void __launch_bounds__(kThreads) dense_gate_bwd_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------
+// Filtered rank of the target entity (evaluation, train/mr_lp_train.py:289-302): the reference overwrites
+// the scores of the other known objects with -1e7, keeps the target's score, and takes
+// 1 + argsort(argsort(pred, descending)) at the target.  That is 1 + the number of entries that sort before
+// the target: strictly greater values, plus equal values with a smaller entity id (stable order).  One CTA per
+// query row counts them in a single pass over the [N] scores and labels.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) filtered_rank_kernel(const float* __restrict__ pred,
+                                                                 const float* __restrict__ label,
+                                                                 const int64_t* __restrict__ obj, int64_t N,
+                                                                 int32_t* __restrict__ rank) {
+  __shared__ int sm[kWarpsPerBlock];
+  const int64_t b = blockIdx.x;
+  const int64_t o = obj[b];
+  const float* pr = pred + b * N;
+  const float* lb = label + b * N;
+  const float t = pr[o];
+  int cnt = 0;
+  for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
+    const float v = (lb[n] != 0.f && n != o) ? -10000000.f : pr[n];
+    cnt += (v > t || (v == t && n < o)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, k);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) tot += sm[w];
+    rank[b] = 1 + tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // K8 epilogue: sigmoid + BCE (elementwise over B*N logits)
 // ---------------------------------------------------------------------------------------
 constexpr int kBceBlocks = kNumSMs * 8;
@@ -999,6 +1032,16 @@ extern "C" int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64
   MRG_CHECK_ARG(logit && label && dlogit && n > 0, "sigmoid_bce_bwd: null pointer / n");
   sigmoid_bce_bwd_kernel<<<bce_grid(n), kThreads, 0, (cudaStream_t)stream>>>(logit, label, n, gscale, dlogit);
   MRG_LAUNCH_CHECK("sigmoid_bce_bwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_filtered_rank(const float* pred, const float* label, const int64_t* obj, int64_t B, int64_t N,
+                                 int32_t* rank, void* stream) {
+  MRG_CHECK_ARG(pred && label && obj && rank, "filtered_rank: null pointer");
+  MRG_CHECK_ARG(B >= 0 && N > 0, "filtered_rank: sizes");
+  if (B == 0) return MRG_OK;
+  filtered_rank_kernel<<<(unsigned)B, kThreads, 0, (cudaStream_t)stream>>>(pred, label, obj, N, rank);
+  MRG_LAUNCH_CHECK("filtered_rank");
   return MRG_OK;
 }
 
