@@ -225,6 +225,9 @@ def main():
     ap.add_argument("--ref-downscale", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-call CUDA-event profile here")
+    ap.add_argument("--sparse-labels", action="store_true",
+                    help="e2e leg: send the batch's object lists (CSR) and expand the smoothed [B,N] labels on the "
+                         "device (mrg_labels_from_csr) instead of copying the dense matrix over PCIe")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling aid (ncu): eager warm-up + steps only, no clock sampling / e2e / CPU legs, no JSON")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying the CUDA graph")
@@ -249,7 +252,7 @@ def main():
     from mr_gnas_b200 import _lib
     from mr_gnas_b200.graph import MRGraph
     from mr_gnas_b200.model_lp import Network
-    from mr_gnas_b200.process_data import make_batch, process
+    from mr_gnas_b200.process_data import make_batch, make_batch_sparse, process
     from mr_gnas_b200.utils import weights_init
     _lib.load()  # fails loudly if the CUDA extension is missing
 
@@ -272,10 +275,11 @@ def main():
     items = process({'train': trip.tolist(), 'valid': [], 'test': []}, R)['train']
     nb = args.steps + args.warmup
     rng = np.random.RandomState(100 + (0 if part_mode else rank))
-    host_batches = []
+    host_batches, sparse_batches = [], []
     for i in range(min(nb, 8)):
         sel = rng.choice(len(items), size=B, replace=False)
         t_h, y_h = make_batch([items[j] for j in sel], N, lbl_smooth=0.1, pin=True)
+        sparse_batches.append(make_batch_sparse([items[j] for j in sel], pin=True))
         if part_mode:   # this rank scores its own entity range only: it needs its columns of the label matrix
             y_h = y_h[:, g.part.lo:g.part.hi].contiguous().pin_memory()
         host_batches.append((t_h, y_h))
@@ -292,7 +296,17 @@ def main():
 
     from mr_gnas_b200.train import GraphedTrainStep
     label_cols = host_batches[0][1].shape[1]
-    runner = GraphedTrainStep(model, g, opt, B, label_cols, grad_sync=lambda ps: allreduce_grads())
+    sparse_cfg = None
+    if args.sparse_labels:
+        sparse_cfg = dict(num_ent=N, lbl_smooth=0.1, cap=2 * max(b[2].numel() for b in sparse_batches),
+                          col_lo=g.part.lo if part_mode else 0, col_hi=g.part.hi if part_mode else N)
+        h2d = sparse_batches[0][0][:, :2].numel() * 8 + sparse_batches[0][1].numel() * 4 + \
+            max(b[2].numel() for b in sparse_batches) * 4
+    runner = GraphedTrainStep(model, g, opt, B, label_cols, grad_sync=lambda ps: allreduce_grads(),
+                              sparse_labels=sparse_cfg)
+    if args.sparse_labels:      # static CSR inputs must hold a valid batch before warm-up / capture
+        t0_, p0_, i0_ = sparse_batches[0]
+        runner.load_sparse(t0_[:, 0], t0_[:, 1], p0_, i0_)
 
     def step_eager(i):                       # per-call profiling pass and --no-graph
         trip_d, y_d = dev_batches[i % len(dev_batches)]
@@ -303,7 +317,12 @@ def main():
         opt.step()
         return loss
 
+    dev_sparse = [(t.to(dev), p_.to(dev), i_.to(dev)) for t, p_, i_ in sparse_batches] if args.sparse_labels else None
+
     def step_resident(i):                    # inputs already in HBM
+        if args.sparse_labels:
+            t_d, p_d, i_d = dev_sparse[i % len(dev_sparse)]
+            return runner(t_d[:, 0], t_d[:, 1], label_csr=(p_d, i_d))
         trip_d, y_d = dev_batches[i % len(dev_batches)]
         return runner(trip_d[:, 0], trip_d[:, 1], y_d)
 
@@ -313,6 +332,9 @@ def main():
         # Every step's batch crosses PCIe inside the timed region.  The copy of batch i+1 is enqueued on a side
         # stream right after step i is enqueued, so it overlaps the step (double-buffered staging set) the way a
         # DataLoader-fed loop would; step i itself consumes the batch staged during step i-1.
+        if args.sparse_labels:               # kilobytes per step: plain copies, nothing to overlap
+            t_h, p_h, i_h = sparse_batches[i % len(sparse_batches)]
+            return runner(t_h[:, 0], t_h[:, 1], label_csr=(p_h, i_h)).item()
         if not primed["ok"]:
             t_h, y_h = host_batches[i % len(host_batches)]
             runner.prefetch(t_h[:, 0], t_h[:, 1], y_h)
@@ -360,8 +382,9 @@ def main():
         torch.cuda.synchronize()
         return
     if not args.no_graph:
-        trip_d, y_d = dev_batches[0]
-        runner.load(trip_d[:, 0], trip_d[:, 1], y_d)
+        if not args.sparse_labels:
+            trip_d, y_d = dev_batches[0]
+            runner.load(trip_d[:, 0], trip_d[:, 1], y_d)
         runner.capture()
     for i in range(args.warmup):
         step_resident(i)
@@ -423,7 +446,9 @@ def main():
                                            "global BatchNorm statistics, entity-sharded 1-N scoring)" if part_mode else
                                            f"dp{world} over query batches (full-graph MP per rank, NCCL grad all-reduce)"),
                            "l2": "edge tensors are 447 MB each (> 126 MB L2); no explicit flush",
-                           "launch": "eager" if args.no_graph else "whole step replayed from one CUDA graph"},
+                           "launch": "eager" if args.no_graph else "whole step replayed from one CUDA graph",
+                           "labels": ("object lists (CSR) sent per step, expanded + smoothed on the device"
+                                      if args.sparse_labels else "dense smoothed [B,N] fp32 matrix per step")},
                 "triples_per_s": units * B / (ms / 1e3),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e, "triples_per_s": units * B / (ms_e2e / 1e3)},

@@ -283,6 +283,16 @@ int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64_t n, const
                         void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Label pipeline.  Replaces TrainDataset.get_label + label smoothing
+ * (utils/data_set.py:17-33) and the per-step host->device copy of the dense [B, N] label matrix
+ * (train/mr_lp_train.py:227): out[b, n - col_lo] = pos if n is listed in idx[ptr[b] .. ptr[b+1]) else neg, for
+ * n in [col_lo, col_hi).  The caller passes neg = fl32(1/N), pos = fl32(fl32(1 - lbl_smooth) + fl32(1/N)) (or 0 / 1
+ * without smoothing), which makes the rows bit-identical to the reference's.  out: [B, col_hi - col_lo] fp32.
+ * ---------------------------------------------------------------------------------- */
+int mrg_labels_from_csr(const int32_t* ptr, const int32_t* idx, int64_t B, int64_t col_lo, int64_t col_hi, float neg,
+                        float pos, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Evaluation: filtered rank of the target object of every query.  Replaces the
  * torch.where + double argsort over [B, N] of predict() (train/mr_lp_train.py:289-302):
  *   rank[b] = 1 + #{ n : v(b,n) > v(b,obj[b])  or  (v(b,n) == v(b,obj[b]) and n < obj[b]) },

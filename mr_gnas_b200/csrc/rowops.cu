@@ -655,6 +655,28 @@ __global__ void __launch_bounds__(kThreads) dense_gate_bwd_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------
+// 1-N training labels from their sparse form.  The reference builds a dense [N] fp32
+// multi-hot row per item on the host, smooths it, (1 - ls) * y + 1/N (utils/data_set.py:17-33), and copies
+// [B, N] floats to the device every step.  Here the host sends the object lists (CSR: ptr [B+1], idx [nnz]) and
+// one CTA per query writes its row: `neg` everywhere, `pos` at the listed objects; neg = fl32(1/N),
+// pos = fl32(fl32(1 - ls) + fl32(1/N)) are computed by the caller exactly as torch does, so the rows are
+// bit-identical to the reference's.  [col_lo, col_hi) selects the columns one destination-partition rank scores.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) labels_from_csr_kernel(const int32_t* __restrict__ ptr,
+                                                                   const int32_t* __restrict__ idx, int64_t col_lo,
+                                                                   int64_t col_hi, float neg, float pos,
+                                                                   float* __restrict__ out) {
+  const int64_t b = blockIdx.x, ld = col_hi - col_lo;
+  float* row = out + b * ld;
+  for (int64_t n = threadIdx.x; n < ld; n += blockDim.x) row[n] = neg;
+  __syncthreads();
+  for (int32_t k = ptr[b] + threadIdx.x; k < ptr[b + 1]; k += blockDim.x) {
+    const int64_t n = idx[k];
+    if (n >= col_lo && n < col_hi) row[n - col_lo] = pos;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Filtered rank of the target entity (evaluation, train/mr_lp_train.py:289-302): the reference overwrites
 // the scores of the other known objects with -1e7, keeps the target's score, and takes
 // 1 + argsort(argsort(pred, descending)) at the target.  That is 1 + the number of entries that sort before
@@ -1032,6 +1054,16 @@ extern "C" int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64
   MRG_CHECK_ARG(logit && label && dlogit && n > 0, "sigmoid_bce_bwd: null pointer / n");
   sigmoid_bce_bwd_kernel<<<bce_grid(n), kThreads, 0, (cudaStream_t)stream>>>(logit, label, n, gscale, dlogit);
   MRG_LAUNCH_CHECK("sigmoid_bce_bwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_labels_from_csr(const int32_t* ptr, const int32_t* idx, int64_t B, int64_t col_lo, int64_t col_hi,
+                                   float neg, float pos, float* out, void* stream) {
+  MRG_CHECK_ARG(ptr && idx && out, "labels_from_csr: null pointer");
+  MRG_CHECK_ARG(B >= 0 && col_hi > col_lo && col_lo >= 0, "labels_from_csr: sizes");
+  if (B == 0) return MRG_OK;
+  labels_from_csr_kernel<<<(unsigned)B, kThreads, 0, (cudaStream_t)stream>>>(ptr, idx, col_lo, col_hi, neg, pos, out);
+  MRG_LAUNCH_CHECK("labels_from_csr");
   return MRG_OK;
 }
 

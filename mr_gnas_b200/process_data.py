@@ -52,3 +52,38 @@ def make_batch(items, num_ent, lbl_smooth=0.0, pin=False):
     if pin:
         trip, y = trip.pin_memory(), y.pin_memory()
     return trip, y
+
+
+def make_batch_sparse(items, pin=False):
+    """The same batch with the labels in their sparse form: (triplets [B,3] int64, ptr [B+1] int32, idx [nnz]
+    int32) -- the object lists of process() (utils/process_data.py:19) as one CSR.  `labels_on_device` expands
+    them on the GPU into exactly the rows TrainDataset would have produced (utils/data_set.py:17-33)."""
+    trip = torch.tensor([list(it['triple']) for it in items], dtype=torch.long)
+    counts = [len(it['label']) for it in items]
+    ptr = torch.zeros(len(items) + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(torch.tensor(counts, dtype=torch.int64), 0).to(torch.int32)
+    idx = torch.tensor([o for it in items for o in it['label']], dtype=torch.int32)
+    if pin:
+        trip, ptr, idx = trip.pin_memory(), ptr.pin_memory(), idx.pin_memory()
+    return trip, ptr, idx
+
+
+def label_values(num_ent, lbl_smooth):
+    """(neg, pos) fp32 label values as torch computes (1.0 - ls) * y + 1.0 / N on an fp32 multi-hot y."""
+    if lbl_smooth == 0.0:
+        return 0.0, 1.0
+    inv = np.float32(1.0 / num_ent)
+    return float(inv), float(np.float32(np.float32(1.0 - lbl_smooth) * np.float32(1.0)) + inv)
+
+
+def labels_on_device(ptr, idx, num_ent, lbl_smooth=0.0, col_lo=0, col_hi=None, out=None):
+    """Dense [B, col_hi - col_lo] fp32 labels written on the device from device-resident (ptr, idx)."""
+    from . import _lib
+    col_hi = num_ent if col_hi is None else col_hi
+    B = ptr.numel() - 1
+    if out is None:
+        out = torch.empty(B, col_hi - col_lo, dtype=torch.float32, device=ptr.device)
+    neg, pos = label_values(num_ent, lbl_smooth)
+    _lib.call("mrg_labels_from_csr", _lib.ptr(ptr), _lib.ptr(idx), B, col_lo, col_hi, neg, pos, _lib.ptr(out),
+              _lib.stream())
+    return out

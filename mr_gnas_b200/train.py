@@ -17,13 +17,21 @@ class GraphedTrainStep:
     `grad_sync(params)` (optional) runs between backward and the optimiser, inside the graph.
     The optimiser must be capturable (torch.optim.Adam(..., fused=True, capturable=True))."""
 
-    def __init__(self, model, g, opt, batch_size, label_cols, grad_sync=None, warmup=3, device=None):
+    def __init__(self, model, g, opt, batch_size, label_cols, grad_sync=None, warmup=3, device=None,
+                 sparse_labels=None):
         dev = device or next(model.parameters()).device
         self.model, self.g, self.opt, self.grad_sync = model, g, opt, grad_sync
         self.params = [p for p in model.parameters()]
         self.subj = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.rel = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.label = torch.zeros(batch_size, label_cols, dtype=torch.float32, device=dev)
+        # sparse_labels = dict(num_ent=N, lbl_smooth=ls, cap=max object ids per batch, col_lo=.., col_hi=..):
+        # the step starts by expanding the batch's object lists (CSR) into self.label ON THE DEVICE
+        # (mrg_labels_from_csr) -- the host then sends kilobytes per step instead of the dense [B, N] matrix
+        self.sparse = sparse_labels
+        if sparse_labels is not None:
+            self.lptr = torch.zeros(batch_size + 1, dtype=torch.int32, device=dev)
+            self.lidx = torch.zeros(int(sparse_labels['cap']), dtype=torch.int32, device=dev)
         self.graph = None
         self.loss = None
         self._warmup = warmup
@@ -37,6 +45,11 @@ class GraphedTrainStep:
         self._next = 0
 
     def _eager(self):
+        if self.sparse is not None:
+            from .process_data import labels_on_device
+            sp = self.sparse
+            labels_on_device(self.lptr, self.lidx, sp['num_ent'], sp.get('lbl_smooth', 0.0), sp.get('col_lo', 0),
+                             sp.get('col_hi'), out=self.label)
         self.opt.zero_grad(set_to_none=True)
         loss = self.model._loss(self.g, self.subj, self.rel, self.label)
         loss.backward()
@@ -65,6 +78,15 @@ class GraphedTrainStep:
         self.rel.copy_(rel, non_blocking=True)
         self.label.copy_(label, non_blocking=True)
 
+    def load_sparse(self, subj, rel, ptr, idx):
+        """Batch with sparse labels (process_data.make_batch_sparse): three small host->device copies."""
+        if idx.numel() > self.lidx.numel():
+            raise RuntimeError(f"batch lists {idx.numel()} objects, capacity is {self.lidx.numel()}")
+        self.subj.copy_(subj, non_blocking=True)
+        self.rel.copy_(rel, non_blocking=True)
+        self.lptr.copy_(ptr, non_blocking=True)
+        self.lidx[:idx.numel()].copy_(idx, non_blocking=True)
+
     def prefetch(self, subj, rel, label):
         """Start copying a (pinned host) batch into a staging set; the next __call__() without arguments runs it."""
         k = self._next
@@ -90,8 +112,10 @@ class GraphedTrainStep:
         self._consumed[k], self._staged[k] = ev, None
         return True
 
-    def __call__(self, subj=None, rel=None, label=None):
-        if subj is not None:
+    def __call__(self, subj=None, rel=None, label=None, label_csr=None):
+        if label_csr is not None:
+            self.load_sparse(subj, rel, *label_csr)
+        elif subj is not None:
             self.load(subj, rel, label)
         else:
             self._take_staged()

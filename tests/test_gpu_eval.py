@@ -104,3 +104,23 @@ def test_predict_matches_reference_loop():
     assert abs(got_loss - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
     res, loss = evaluate.infer(model, g, loader, loader, dev)
     assert res['mr'] == round(ref['mr'] / ref['count'], 5) and res['left_mrr'] == res['right_mrr']
+
+
+@pytest.mark.parametrize("ls", [0.1, 0.0])
+def test_labels_from_csr_bit_identical_to_dense_host_labels(ls):
+    """labels expanded on the device from the sparse object lists == TrainDataset's dense rows."""
+    from mr_gnas_b200.process_data import labels_on_device, make_batch, make_batch_sparse, process
+    from mr_gnas_b200.synth import synth_kg
+    dev = torch.device("cuda:0")
+    N, R, T, B = 14541, 11, 20000, 96
+    trip = synth_kg(N, R, T, seed=2)
+    items = process({'train': trip.tolist(), 'valid': [], 'test': []}, R)['train'][:B]
+    t_dense, y = make_batch(items, N, lbl_smooth=ls)
+    t_sp, ptr, idx = make_batch_sparse(items)
+    assert torch.equal(t_dense, t_sp)
+    out = labels_on_device(ptr.to(dev), idx.to(dev), N, ls)
+    assert torch.equal(out.cpu(), y)
+    lo, hi = 5000, 9000     # one destination-partition rank's columns
+    part = labels_on_device(ptr.to(dev), idx.to(dev), N, ls, lo, hi)
+    assert torch.equal(part.cpu(), y[:, lo:hi])
+    assert idx.numel() * 4 + ptr.numel() * 4 < y.numel() * 4 / 100    # > 100x fewer bytes over PCIe
