@@ -71,12 +71,18 @@ class Partition:
         self.n_local = self.hi - self.lo
 
     def rows_global(self, rows_local):
-        if rows_local == self.e_local + self.n_local:
-            return self.e_global + self.n_global
-        if rows_local == self.n_local:
-            return self.n_global
-        raise RuntimeError(f"partitioned BatchNorm over {rows_local} rows: neither the local edge-expanded rows "
-                           f"({self.e_local + self.n_local}) nor the local nodes ({self.n_local})")
+        """Global row count behind a local BatchNorm: edge-expanded rows (LP: E + N), edge rows (NC blocks: E) or
+        node rows (N)."""
+        table = {}
+        for loc, glob in ((self.e_local + self.n_local, self.e_global + self.n_global),
+                          (self.e_local, self.e_global), (self.n_local, self.n_global)):
+            if table.setdefault(loc, glob) != glob:
+                raise RuntimeError(f"ambiguous partitioned BatchNorm row count {loc} (edges {self.e_local}, nodes "
+                                   f"{self.n_local}): choose another world size")
+        if rows_local not in table:
+            raise RuntimeError(f"partitioned BatchNorm over {rows_local} rows: not the local edge-expanded rows "
+                               f"({self.e_local + self.n_local}), edges ({self.e_local}) or nodes ({self.n_local})")
+        return table[rows_local]
 
 
 _current = None
@@ -227,3 +233,25 @@ def lp_partition(triples, num_ent, num_rels, rank, world, device="cuda", group=N
                                num_ent, 2 * num_rels + 1, lo, hi, half, torch.from_numpy(n_norm), device)
     g.part = Partition(rank, world, lo, hi, num_ent, int(keep.sum()), E, [(a, b) for a, b, _, _ in ranges], group)
     return g
+
+
+def nc_partition(src, dst, etype, num_nodes, layers, rank, world, device="cuda", group=None):
+    """Destination-partitioned FULL-GRAPH message-flow blocks for the NC network (models/model.py:152-184 run on the
+    whole graph instead of sampled 64-seed blocks -- BASELINE configs[3]): this rank's block holds the in-edges
+    of destinations [lo, hi) (ranges balanced by in-edge count), in parent-edge-id order, with parent edge ids,
+    edge types and global destination ids exactly as a DGL block carries them.  Every layer uses the same block.
+    Returns ([block] * layers, Partition)."""
+    import numpy as np
+    from .graph import MRBlock
+    src, dst, etype = (np.asarray(a).astype(np.int64) for a in (src, dst, etype))
+    deg = np.bincount(dst, minlength=num_nodes)
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]))
+    ranges = partition_by_dst(ptr, world)
+    lo, hi = ranges[rank][0], ranges[rank][1]
+    eids = np.nonzero((dst >= lo) & (dst < hi))[0]
+    block = MRBlock.build(torch.from_numpy(eids), torch.from_numpy(etype[eids]), torch.from_numpy(dst[eids] - lo),
+                          torch.arange(lo, hi), device)
+    part = Partition(rank, world, lo, hi, num_nodes, eids.shape[0], src.shape[0], [(a, b) for a, b, _, _ in ranges],
+                     group)
+    block.part = part
+    return [block] * layers, part

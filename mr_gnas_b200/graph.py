@@ -277,6 +277,7 @@ class MRBlock(MRGraph):
         b.edata['_ID'] = torch.as_tensor(parent_eid).to(device).long()
         b.edata['_TYPE'] = torch.as_tensor(etype).to(device).long()
         b.dstdata = {'_ID': torch.as_tensor(dst_nid).to(device).long()}
+        b.part = None
         return b
 
 

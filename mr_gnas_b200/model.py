@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import dist as D_
 from . import functional as K
 from .operations import MIXED_OPS
 
@@ -131,7 +132,37 @@ class Network(nn.Module):
     def _cell(self, i, cell, block, src_embed, edges_embed):
         return cell(block, src_embed, edges_embed)
 
+    def _forward_partitioned(self, trip_index, block, part):
+        """Full-graph layers on ONE destination range (dist.nc_partition): every layer reads the
+        sources of its edges from the full node table (layer 0: the replicated input embedding; later layers: the
+        owned rows of every rank all-gathered over NVLink), BatchNorm statistics are summed over the ranks.
+        Returns this rank's rows [hi - lo, D] of the final node embedding."""
+        src_ls, et_ls = block_inputs(trip_index, block)
+        rel_table = torch.mm(self.rel_wt, self.embedding_e.weight)
+        node_embed = None
+        with D_.use(part):
+            for i, cell in enumerate(self.cells):
+                if i == 0:
+                    src_embed = self.embedding_h_init(self.embedding_h(src_ls[i]))
+                else:
+                    src_embed = D_.AllGatherRows.apply(node_embed, part)[src_ls[i]]
+                edges_embed = self.embedding_e_init(rel_table[et_ls[i]])
+                node_embed = self._cell(i, cell, block[i], src_embed, edges_embed)
+            return K.bn_act(node_embed, self.batchnorm_h, relu=True)
+
+    def _loss_partitioned(self, trip_index, block, labels, idx):
+        """Cross-entropy over the labelled nodes `idx` (global ids, labels[idx] their classes) of a partitioned
+        full-graph forward: every rank classifies the labelled nodes it owns; the mean is taken over ALL of them."""
+        part = block[0].part
+        logits = self.classifier(self._forward_partitioned(trip_index, block, part))
+        own = (idx >= part.lo) & (idx < part.hi)
+        loc = (idx - part.lo).clamp(0, max(part.n_local - 1, 0))
+        per = F.cross_entropy(logits[loc], labels[idx], reduction='none') * own.to(logits.dtype)
+        return D_.AllReduceSum.apply(per.sum() / idx.numel(), part)
+
     def _forward(self, trip_index, block):
+        if getattr(block[0], 'part', None) is not None:
+            return self._forward_partitioned(trip_index, block, block[0].part)
         src_ls, et_ls = block_inputs(trip_index, block)
         rel_table = torch.mm(self.rel_wt, self.embedding_e.weight)  # rows gathered per edge below
         node_embed = src_embed = None

@@ -106,3 +106,71 @@ def test_partitioned_lp_world2_matches_single_gpu(n_cells):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), n_cells), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------------------ NC full-graph layers, partitioned
+NC_GENO = ("[Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_dense', 2, 1), ('f_sparse', 3, 2), ('f_identity', 4, 3), "
+           "('a_sum', 5, 2), ('a_sum', 6, 3), ('a_mean', 7, 4), ('f_dense_last', 8, 7), ('f_sparse_last', 9, 7), "
+           "('f_sparse_last', 10, 5)], concat_node=[5, 6, 7, 8, 9, 10]), Genotype(alpha_cell=[('pre_sub', 1, 0), "
+           "('f_sparse', 2, 1), ('f_identity', 3, 2), ('f_identity', 4, 1), ('a_max', 5, 2), ('a_mean', 6, 3), "
+           "('a_mean', 7, 4), ('f_sparse_last', 8, 7), ('f_sparse_last', 9, 8), ('f_identity', 10, 9)], "
+           "concat_node=[5, 6, 7, 8, 9, 10])]")
+
+
+def _compare_nc(rank, world):
+    from mr_gnas_b200 import dist as D_
+    from mr_gnas_b200.graph import MRBlock
+    from mr_gnas_b200.model import Network
+    GenoNC = namedtuple("Genotype", "alpha_cell concat_node score_func", defaults=(None,))
+    dev = torch.device("cuda", rank)
+    N, ET, E, D, D0, C, NB = 900, 8, 9000, 32, 16, 4, 5
+    rng = np.random.RandomState(11)
+    src, dst, et = rng.randint(0, N, E), (rng.zipf(1.6, E) - 1) % N, rng.randint(0, ET, E)
+    dst[:50] = 3                                     # a hub; some nodes stay isolated
+    trip_index = torch.from_numpy(np.stack([np.arange(E), src, dst], 1)).to(dev)
+    labels = torch.from_numpy(rng.randint(0, C, N)).to(dev)
+    idx = torch.from_numpy(rng.choice(N, 120, replace=False)).to(dev)
+    args = types.SimpleNamespace(feature_dim=D, op_norm=True)
+    genos = eval(NC_GENO, {"Genotype": GenoNC})
+
+    def fresh():
+        torch.manual_seed(0)
+        return Network(dev, genos, N, C, ET, 2, 1, 2, D, D0, NB, nn.CrossEntropyLoss(), args).to(dev).train()
+
+    ref = fresh()
+    full = MRBlock.build(torch.arange(E), torch.from_numpy(et), torch.from_numpy(dst), torch.arange(N), dev)
+    out_ref = ref._forward(trip_index, [full, full])
+    loss_ref = nn.functional.cross_entropy(ref.classifier(out_ref)[idx], labels[idx])
+    loss_ref.backward()
+
+    par = fresh()
+    blocks, part = D_.nc_partition(src, dst, et, N, 2, rank, world, dev)
+    out = par._forward(trip_index, blocks)
+    assert _err(out, out_ref[part.lo:part.hi]) <= 1e-5
+    par.zero_grad()
+    loss = par._loss_partitioned(trip_index, blocks, labels, idx)
+    loss.backward()
+    D_.allreduce_grads_sum(list(par.parameters()), part)
+    assert _err(loss, loss_ref) <= 1e-5, (float(loss), float(loss_ref))
+    worst = max((_err(p.grad, q.grad), k) for (k, p), q in zip(par.named_parameters(), ref.parameters())
+                if q.grad is not None and p.grad is not None)
+    assert worst[0] <= 2e-5, worst
+
+
+def _worker_nc(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        _compare_nc(rank, world)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_partitioned_nc_full_graph_matches_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    mp.spawn(_worker_nc, args=(world, _free_port()), nprocs=world, join=True)
