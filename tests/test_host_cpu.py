@@ -122,3 +122,31 @@ def test_process_matches_reference_items(golden_dir):
         assert list(it["triple"]) == tr and sorted(it["label"]) == sorted(lab)
     t, y = make_batch(items, gd["num_ent"], lbl_smooth=0.1)
     assert torch.equal(y, G["labels"]) and torch.equal(t[:, 0], G["subj"]) and torch.equal(t[:, 1], G["rel"])
+
+
+def test_sparse_batch_and_label_values_match_dense_host_labels():
+    """Host side of the label pipeline: the CSR object lists + the two fp32 label values reproduce TrainDataset's
+    dense smoothed rows (utils/data_set.py:17-33) bit for bit (the device kernel only places `pos` / `neg`)."""
+    import numpy as np
+    import torch
+    from mr_gnas_b200.process_data import label_values, make_batch, make_batch_sparse, process
+    from mr_gnas_b200.synth import synth_kg
+    N, R = 977, 5
+    trip = synth_kg(N, R, 3000, seed=3)
+    items = process({'train': trip.tolist(), 'valid': [], 'test': []}, R)['train'][:64]
+    for ls in (0.1, 0.0, 0.25):
+        t, y = make_batch(items, N, lbl_smooth=ls)
+        t2, ptr, idx = make_batch_sparse(items)
+        assert torch.equal(t, t2) and ptr.dtype == torch.int32 and int(ptr[-1]) == idx.numel()
+        neg, pos = label_values(N, ls)
+        dense = torch.full((len(items), N), neg, dtype=torch.float32)
+        for b in range(len(items)):
+            dense[b, idx[ptr[b]:ptr[b + 1]].long()] = pos
+        assert torch.equal(dense, y)
+        # and the reference's own per-item formula
+        y0 = np.zeros([N], dtype=np.float32)
+        y0[np.int32(items[0]['label'])] = 1
+        ref = torch.tensor(y0, dtype=torch.float32)
+        if ls != 0.0:
+            ref = (1.0 - ls) * ref + (1.0 / N)
+        assert torch.equal(y[0], ref)
