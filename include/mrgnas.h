@@ -172,6 +172,25 @@ int mrg_compose_bwd_rows(const float* dy, const float* x, const float* r, int64_
 int mrg_sparse_gate_fwd(mrg_act x, mrg_act xin, int64_t rows, int32_t D, const float* v1, const float* v2,
                         const float* c, const float* row_scale, float base_scale, float* y, float* gate,
                         double* stats, void* stream);
+/* The collapse itself and its backward for up to three segments (in / out / self) in one launch each:
+ *   v[s,:] = a[s] @ W[s]   (a [D], W [D, K] = nn.Linear(K, D).weight),   c[s] = a[s] . b[s]   (b NULL: 0)
+ * written as v1 = v[:, :D1] ([nseg, D1]) and v2 = v[:, D1:] ([nseg, K-D1]; NULL when K == D1);
+ *   dW[s] = a[s]^T dv[s],   da[s] = W[s] dv[s] + dc[s] b[s],   db[s] = dc[s] a[s].
+ * Replaces the a.weight @ W.weight matmuls that autograd would otherwise run per segment, gate and step. */
+typedef struct {
+  const float* W[3];
+  const float* b[3];
+  const float* a[3];
+} mrg_gate_params;
+typedef struct {
+  float* dW[3];
+  float* db[3];
+  float* da[3];
+} mrg_gate_grads;
+int mrg_gate_collapse_fwd(mrg_gate_params p, int32_t nseg, int32_t D, int32_t K, int32_t D1, float* v1, float* v2,
+                          float* c, void* stream);
+int mrg_gate_collapse_bwd(mrg_gate_params p, int32_t nseg, int32_t D, int32_t K, int32_t D1, const float* dv1,
+                          const float* dv2, const float* dc, mrg_gate_grads g, void* stream);
 int64_t mrg_gate_dparam_count(int64_t rows, int32_t D);
 int mrg_sparse_gate_bwd(const float* dy, mrg_act x, mrg_act xin, const float* gate, int64_t rows, int32_t D,
                         const float* v1, const float* v2, const float* row_scale, float base_scale, float* dx,

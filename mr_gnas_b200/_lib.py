@@ -25,6 +25,14 @@ class MrgGrad(Structure):
     _fields_ = [("ds", c_void_p), ("y", MrgAct), ("coef", c_void_p)]
 
 
+class MrgGateParams(Structure):
+    _fields_ = [("W", c_void_p * 3), ("b", c_void_p * 3), ("a", c_void_p * 3)]
+
+
+class MrgGateGrads(Structure):
+    _fields_ = [("dW", c_void_p * 3), ("db", c_void_p * 3), ("da", c_void_p * 3)]
+
+
 class MrgActList(Structure):
     _fields_ = [("acts", MrgAct * 8), ("n", c_int32)]
 
@@ -52,6 +60,8 @@ _SIGNATURES = {
     "mrg_compose_fwd": (I32, [P, P, P, P, I64, I32, I32, P, P, P]),
     "mrg_compose_bwd_rows": (I32, [P, P, P, I64, I32, I32, P, P, P]),
     "mrg_sparse_gate_fwd": (I32, [MrgAct, MrgAct, I64, I32, P, P, P, P, F32, P, P, P, P]),
+    "mrg_gate_collapse_fwd": (I32, [MrgGateParams, I32, I32, I32, I32, P, P, P, P]),
+    "mrg_gate_collapse_bwd": (I32, [MrgGateParams, I32, I32, I32, I32, P, P, P, MrgGateGrads, P]),
     "mrg_gate_dparam_count": (I64, [I64, I32]),
     "mrg_sparse_gate_bwd": (I32, [P, MrgAct, MrgAct, P, I64, I32, P, P, P, F32, P, P, I32, P, P]),
     "mrg_sparse_gate_bwd_finalize": (I32, [P, I64, I32, P, P, P, P]),

@@ -655,6 +655,74 @@ __global__ void __launch_bounds__(kThreads) dense_gate_bwd_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------
+// Collapse of the sparse gates' Linear pair (operations_lp.py:319-320,347-350,408-411: a(W z + b) with no
+// non-linearity in between):  v[s,:] = a_s @ W_s  ([1,D] x [D,K]),  c[s] = a_s . b_s,  for up to three row
+// segments, and its backward (dW_s = a_s^T dv_s, da_s = W_s dv_s + dc_s b_s, db_s = dc_s a_s).  One launch each
+// way instead of ~12 + ~24 library GEMV / outer-product / cat / copy kernels per gate and step.
+// v is written as its two halves v1 = v[:, :D1], v2 = v[:, D1:] (the x / x_in parts the gate kernels take).
+// ---------------------------------------------------------------------------------------
+// block = 32 output columns k x 8 warps that split the D-long reduction; the 8 partials are summed in warp order
+__global__ void __launch_bounds__(256) gate_collapse_fwd_kernel(mrg_gate_params p, int D, int K, int D1,
+                                                                float* __restrict__ v1, float* __restrict__ v2,
+                                                                float* __restrict__ c) {
+  __shared__ float sm[8][33];
+  const int s = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  const float* W = p.W[s];
+  const float* a = p.a[s];
+  float t = 0.f;
+  if (k < K)
+    for (int d = warp; d < D; d += 8) t = fmaf(__ldg(a + d), __ldg(W + (size_t)d * K + k), t);
+  sm[warp][lane] = t;
+  __syncthreads();
+  if (warp == 0 && k < K) {
+    float r = sm[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) r += sm[w][lane];
+    if (k < D1) v1[(size_t)s * D1 + k] = r;
+    else v2[(size_t)s * (K - D1) + (k - D1)] = r;
+  }
+  if (blockIdx.x == 0 && warp == 1) {
+    float u = 0.f;
+    if (p.b[s])
+      for (int d = lane; d < D; d += 32) u = fmaf(__ldg(a + d), __ldg(p.b[s] + d), u);
+    u = warp_sum(u);
+    if (lane == 0) c[s] = u;
+  }
+}
+
+// one 128-thread block per (row d of W_s, segment s)
+__global__ void __launch_bounds__(128) gate_collapse_bwd_kernel(mrg_gate_params p, int D, int K, int D1,
+                                                                const float* __restrict__ dv1,
+                                                                const float* __restrict__ dv2,
+                                                                const float* __restrict__ dc, mrg_gate_grads g) {
+  __shared__ float sm[4];
+  const int s = blockIdx.y, d = blockIdx.x;
+  const float ad = __ldg(p.a[s] + d);
+  const float* Wr = p.W[s] + (size_t)d * K;
+  float* dWr = g.dW[s] + (size_t)d * K;
+  float t = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float dvk = k < D1 ? __ldg(dv1 + (size_t)s * D1 + k) : __ldg(dv2 + (size_t)s * (K - D1) + (k - D1));
+    dWr[k] = ad * dvk;
+    t = fmaf(__ldg(Wr + k), dvk, t);
+  }
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float dcs = __ldg(dc + s);
+    float da = sm[0] + sm[1] + sm[2] + sm[3];
+    if (p.b[s]) {
+      da = fmaf(dcs, __ldg(p.b[s] + d), da);
+      g.db[s][d] = dcs * ad;
+    }
+    g.da[s][d] = da;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 1-N training labels from their sparse form.  The reference builds a dense [N] fp32
 // multi-hot row per item on the host, smooths it, (1 - ls) * y + 1/N (utils/data_set.py:17-33), and copies
 // [B, N] floats to the device every step.  Here the host sends the object lists (CSR: ptr [B+1], idx [nnz]) and
@@ -1054,6 +1122,28 @@ extern "C" int mrg_sigmoid_bce_bwd(const float* logit, const float* label, int64
   MRG_CHECK_ARG(logit && label && dlogit && n > 0, "sigmoid_bce_bwd: null pointer / n");
   sigmoid_bce_bwd_kernel<<<bce_grid(n), kThreads, 0, (cudaStream_t)stream>>>(logit, label, n, gscale, dlogit);
   MRG_LAUNCH_CHECK("sigmoid_bce_bwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_gate_collapse_fwd(mrg_gate_params p, int32_t nseg, int32_t D, int32_t K, int32_t D1, float* v1,
+                                     float* v2, float* c, void* stream) {
+  MRG_CHECK_ARG(nseg >= 1 && nseg <= 3 && D > 0 && K >= D1 && D1 > 0 && v1 && c, "gate_collapse_fwd: arguments");
+  MRG_CHECK_ARG(K == D1 || v2, "gate_collapse_fwd: K > D1 needs v2");
+  for (int s = 0; s < nseg; ++s) MRG_CHECK_ARG(p.W[s] && p.a[s], "gate_collapse_fwd: null W / a");
+  gate_collapse_fwd_kernel<<<dim3((K + 31) / 32, nseg), 256, 0, (cudaStream_t)stream>>>(p, D, K, D1, v1, v2, c);
+  MRG_LAUNCH_CHECK("gate_collapse_fwd");
+  return MRG_OK;
+}
+
+extern "C" int mrg_gate_collapse_bwd(mrg_gate_params p, int32_t nseg, int32_t D, int32_t K, int32_t D1,
+                                     const float* dv1, const float* dv2, const float* dc, mrg_gate_grads g,
+                                     void* stream) {
+  MRG_CHECK_ARG(nseg >= 1 && nseg <= 3 && D > 0 && K >= D1 && D1 > 0 && dv1 && dc, "gate_collapse_bwd: arguments");
+  MRG_CHECK_ARG(K == D1 || dv2, "gate_collapse_bwd: K > D1 needs dv2");
+  for (int s = 0; s < nseg; ++s)
+    MRG_CHECK_ARG(p.W[s] && p.a[s] && g.dW[s] && g.da[s] && (!p.b[s] || g.db[s]), "gate_collapse_bwd: null pointer");
+  gate_collapse_bwd_kernel<<<dim3(D, nseg), 128, 0, (cudaStream_t)stream>>>(p, D, K, D1, dv1, dv2, dc, g);
+  MRG_LAUNCH_CHECK("gate_collapse_bwd");
   return MRG_OK;
 }
 

@@ -184,6 +184,88 @@ def bn_act(y, bn, relu=True, stats=None):
 
 
 # ------------------------------------------------------------------------------------------
+# collapse of the gates' Linear pair: (W_s, b_s, a_s) per segment -> v1 [S, D1], v2 [S, K-D1], c [S]
+# ------------------------------------------------------------------------------------------
+class CollapseGates(torch.autograd.Function):
+    """v[s] = a_s.weight @ W_s.weight, c[s] = a_s.weight . W_s.bias for up to three (W, a) pairs in one kernel each
+    way (mrg_gate_collapse_fwd/bwd): no non-linearity sits between W and a in the reference
+    (operations_lp.py:319-320), so the [rows,K]x[K,D] GEMM of the gate collapses to one dot product per row.
+    Inputs: D1, then (W.weight [D,K], W.bias [D], a.weight [1,D]) per segment.  Gradients land on those tensors."""
+
+    @staticmethod
+    def forward(ctx, D1, *wba):
+        nseg = len(wba) // 3
+        Ws = [_f32c(t) for t in wba[0::3]]
+        bs = [(_f32c(t) if t is not None else None) for t in wba[1::3]]
+        As = [_f32c(t) for t in wba[2::3]]
+        D, Kdim = Ws[0].shape
+        dev = Ws[0].device
+        gp = _lib.MrgGateParams()
+        for s_ in range(3):
+            gp.W[s_] = Ws[s_].data_ptr() if s_ < nseg else None
+            gp.b[s_] = bs[s_].data_ptr() if (s_ < nseg and bs[s_] is not None) else None
+            gp.a[s_] = As[s_].data_ptr() if s_ < nseg else None
+        v1 = torch.empty(nseg, D1, dtype=torch.float32, device=dev)
+        v2 = torch.empty(nseg, Kdim - D1, dtype=torch.float32, device=dev) if Kdim > D1 else None
+        c = torch.empty(nseg, dtype=torch.float32, device=dev)
+        call("mrg_gate_collapse_fwd", gp, nseg, D, Kdim, D1, ptr(v1), ptr(v2), ptr(c), stream())
+        ctx.dims = (nseg, D, Kdim, D1)
+        ctx.has_b = [b is not None for b in bs]
+        ctx.save_for_backward(*Ws, *[b for b in bs if b is not None], *As)
+        if v2 is None:
+            return v1, c
+        return v1, v2, c
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        nseg, D, Kdim, D1 = ctx.dims
+        saved = list(ctx.saved_tensors)
+        Ws = saved[:nseg]
+        nb = sum(ctx.has_b)
+        b_saved = saved[nseg:nseg + nb]
+        As = saved[nseg + nb:]
+        bs, k = [], 0
+        for hb in ctx.has_b:
+            bs.append(b_saved[k] if hb else None)
+            k += 1 if hb else 0
+        if Kdim > D1:
+            dv1, dv2, dc = gouts
+        else:
+            (dv1, dc), dv2 = gouts, None
+        dev = Ws[0].device
+        dv1 = _f32c(dv1) if dv1 is not None else torch.zeros(nseg, D1, dtype=torch.float32, device=dev)
+        if Kdim > D1:
+            dv2 = _f32c(dv2) if dv2 is not None else torch.zeros(nseg, Kdim - D1, dtype=torch.float32, device=dev)
+        dc = _f32c(dc) if dc is not None else torch.zeros(nseg, dtype=torch.float32, device=dev)
+        gp, gg = _lib.MrgGateParams(), _lib.MrgGateGrads()
+        dWs = [torch.empty_like(W) for W in Ws]
+        dbs = [torch.empty_like(b) if b is not None else None for b in bs]
+        das = [torch.empty(1, D, dtype=torch.float32, device=dev) for _ in range(nseg)]
+        for s_ in range(3):
+            live = s_ < nseg
+            gp.W[s_] = Ws[s_].data_ptr() if live else None
+            gp.b[s_] = bs[s_].data_ptr() if (live and bs[s_] is not None) else None
+            gp.a[s_] = As[s_].data_ptr() if live else None
+            gg.dW[s_] = dWs[s_].data_ptr() if live else None
+            gg.db[s_] = dbs[s_].data_ptr() if (live and dbs[s_] is not None) else None
+            gg.da[s_] = das[s_].data_ptr() if live else None
+        call("mrg_gate_collapse_bwd", gp, nseg, D, Kdim, D1, ptr(dv1), ptr(dv2), ptr(dc), gg, stream())
+        out = [None]
+        for s_ in range(nseg):
+            out += [dWs[s_], dbs[s_], das[s_]]
+        return tuple(out)
+
+
+def collapse_gates(D1, pairs):
+    """pairs: [(W Linear, a Linear)] per row segment -> (v1 [S,D1], v2 [S,K-D1] or None, c [S])."""
+    flat = []
+    for W, a in pairs:
+        flat += [W.weight, W.bias, a.weight]
+    res = CollapseGates.apply(D1, *flat)
+    return res if len(res) == 3 else (res[0], None, res[1])
+
+
+# ------------------------------------------------------------------------------------------
 # K3/K6: collapsed sparse gate over one or more row segments
 # ------------------------------------------------------------------------------------------
 class SparseGate(torch.autograd.Function):

@@ -309,16 +309,13 @@ class EdgeChain(torch.autograd.Function):
 
 def run(cell, g, ent, rel, plan):
     """Edge-level chain of `cell` -> {node: pre-BN aggregated [N, D] tensor}."""
-    from .operations_lp import _collapse
     first, gates, aggs = plan
     params = [first.batchnorm_h.weight, first.batchnorm_h.bias]
     D = cell._feature_dim
     for node, om, i in gates:
         op = om.op
-        vs, cs = zip(*[_collapse(W, a) for W, a in ((op.W_in, op.a_in), (op.W_out, op.a_out), (op.W_self, op.a_self))])
-        v = torch.cat(vs, 0)
-        params += [v[:, :D].contiguous(), v[:, D:].contiguous(), torch.cat(cs), om.batchnorm_h.weight,
-                   om.batchnorm_h.bias]
+        v1, v2, c = K.collapse_gates(D, ((op.W_in, op.a_in), (op.W_out, op.a_out), (op.W_self, op.a_self)))
+        params += [v1, v2, c, om.batchnorm_h.weight, om.batchnorm_h.bias]
     for node, om, i in aggs:
         if om.op_name == 'a_max':
             params += [om.op.linear.weight, om.op.linear.bias]

@@ -128,15 +128,6 @@ class a_sum_op(nn.Module):
 
 
 # ------------------------------------------------------------------ sparse gates (K3/K6)
-def _collapse(W, a):
-    """a(W z + b) == z . (a.weight @ W.weight) + a.weight . b : no non-linearity between W and a
-    (operations_lp.py:319-320), so the [rows,2D]x[2D,D] GEMM collapses to a GEMV.  Gradients
-    reach W.weight, W.bias and a.weight through this tiny matmul on the autograd tape."""
-    v = a.weight @ W.weight  # [1, K]
-    c = (a.weight @ W.bias.view(-1, 1)).view(1) if W.bias is not None else v.new_zeros(1)
-    return v, c
-
-
 def _comp_bounds(g, rows):
     E = g.num_edges()
     half = getattr(g, 'half', None)
@@ -161,11 +152,8 @@ class f_sparse_op_comp(nn.Module):
     def forward(self, g, src_emb, src_emb_in):
         D = self._feature_dim
         bounds, E = _comp_bounds(g, src_emb.shape[0])
-        vs, cs = zip(*[_collapse(W, a) for W, a in ((self.W_in, self.a_in), (self.W_out, self.a_out),
-                                                    (self.W_self, self.a_self))])
-        v = torch.cat(vs, 0)
-        y, stats = K.SparseGate.apply(src_emb, src_emb_in, v[:, :D].contiguous(), v[:, D:].contiguous(),
-                                      torch.cat(cs), bounds, g.norm(), E, (1 / 3, 1 / 3, 1 / 3))
+        v1, v2, c = K.collapse_gates(D, ((self.W_in, self.a_in), (self.W_out, self.a_out), (self.W_self, self.a_self)))
+        y, stats = K.SparseGate.apply(src_emb, src_emb_in, v1, v2, c, bounds, g.norm(), E, (1 / 3, 1 / 3, 1 / 3))
         return _with_stats(y, stats)
 
 
@@ -180,9 +168,8 @@ class f_sparse_op(nn.Module):
 
     def forward(self, g, src_emb, src_emb_in):
         D = self._feature_dim
-        v, c = _collapse(self.W, self.a)
-        y, stats = K.SparseGate.apply(src_emb, src_emb_in, v[:, :D].contiguous(), v[:, D:].contiguous(), c,
-                                      [(0, src_emb.shape[0])], None, 0, (1.0,))
+        v1, v2, c = K.collapse_gates(D, ((self.W, self.a),))
+        y, stats = K.SparseGate.apply(src_emb, src_emb_in, v1, v2, c, [(0, src_emb.shape[0])], None, 0, (1.0,))
         return _with_stats(y, stats)
 
 
@@ -196,8 +183,8 @@ class f_sparse_op_last(nn.Module):
         self.a = nn.Linear(self._feature_dim, 1, bias=False)
 
     def forward(self, g, src_emb, src_emb_in):
-        v, c = _collapse(self.W, self.a)
-        y, stats = K.SparseGate.apply(src_emb, None, v.contiguous(), None, c, [(0, src_emb.shape[0])], None, 0, (1.0,))
+        v1, _, c = K.collapse_gates(self._feature_dim, ((self.W, self.a),))
+        y, stats = K.SparseGate.apply(src_emb, None, v1, None, c, [(0, src_emb.shape[0])], None, 0, (1.0,))
         return _with_stats(y, stats)
 
 
