@@ -59,7 +59,10 @@ class GraphedTrainStep:
         return loss
 
     def capture(self):
-        """Warm up on a side stream (lazy workspaces, cudaFuncSetAttribute, NCCL channels), then capture."""
+        """Warm up on a side stream (lazy workspaces, cudaFuncSetAttribute, NCCL channels), then capture.
+        The warm-up runs `warmup` REAL training steps on the batch currently in the static inputs (load a batch
+        first); replaying the graph afterwards is bit-identical to issuing the same steps eagerly
+        (tests/test_gpu_network_lp.py::test_graphed_train_step_replays_the_eager_step)."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

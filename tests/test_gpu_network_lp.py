@@ -146,3 +146,54 @@ def test_network_lp_oracle_seeded(D, geno, fused):
     # or within 1e-5 of it in the scale-relative norm
     for e_gpu64, e_cpu64, e_gpu_cpu, k in rep:
         assert e_gpu64 <= max(1e-5, 4 * e_cpu64), (k, e_gpu64, e_cpu64)
+
+
+def test_graphed_train_step_replays_the_eager_step():
+    """train.GraphedTrainStep: replaying the captured CUDA graph must give exactly the losses and parameters of the
+    same steps issued eagerly (same kernels, same order, deterministic reductions) -- dense and sparse-label inputs."""
+    from mr_gnas_b200.graph import MRGraph
+    from mr_gnas_b200.process_data import make_batch, make_batch_sparse, process
+    from mr_gnas_b200.train import GraphedTrainStep
+    from mr_gnas_b200.utils import weights_init
+    dev = torch.device("cuda:0")
+    N, R, T, D, B = 700, 6, 6000, 64, 32
+    trip = O.synth_kg(N, R, T, seed=9)
+    g = MRGraph.from_triples(N, trip, R, device=dev)
+    items = process({'train': trip.tolist(), 'valid': [], 'test': []}, R)['train']
+    batches = [[items[j] for j in range(k * B, (k + 1) * B)] for k in range(4)]
+    dense = [make_batch(b, N, lbl_smooth=0.1) for b in batches]
+    sparse = [make_batch_sparse(b) for b in batches]
+
+    def fresh():
+        torch.manual_seed(0)
+        m = _build('cpu', eval(README), N, R, D, D)
+        m.apply(weights_init)
+        m = m.to(dev).train()
+        return m, torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+
+    # eager: 3 warm-up steps on batch 0 (what capture() does), then batches 1..3
+    m_e, opt_e = fresh()
+    run_e = GraphedTrainStep(m_e, g, opt_e, B, N, warmup=3)
+    t0, y0 = dense[0]
+    for _ in range(3):
+        run_e(t0[:, 0].to(dev), t0[:, 1].to(dev), y0.to(dev))
+    losses_e = [float(run_e(t[:, 0].to(dev), t[:, 1].to(dev), y.to(dev))) for t, y in dense[1:]]
+    for mode in ("dense", "sparse"):
+        m_g, opt_g = fresh()
+        cfg = dict(num_ent=N, lbl_smooth=0.1, cap=4 * max(s[2].numel() for s in sparse)) if mode == "sparse" else None
+        run_g = GraphedTrainStep(m_g, g, opt_g, B, N, warmup=3, sparse_labels=cfg)
+        if mode == "dense":
+            run_g.load(t0[:, 0].to(dev), t0[:, 1].to(dev), y0.to(dev))
+        else:
+            run_g.load_sparse(sparse[0][0][:, 0].to(dev), sparse[0][0][:, 1].to(dev), sparse[0][1].to(dev),
+                              sparse[0][2].to(dev))
+        run_g.capture()
+        assert run_g.graph is not None
+        if mode == "dense":
+            losses_g = [float(run_g(t[:, 0].to(dev), t[:, 1].to(dev), y.to(dev))) for t, y in dense[1:]]
+        else:
+            losses_g = [float(run_g(t[:, 0].to(dev), t[:, 1].to(dev), label_csr=(p.to(dev), i.to(dev))))
+                        for t, p, i in sparse[1:]]
+        assert losses_g == losses_e, (mode, losses_g, losses_e)
+        for (k, a), b in zip(m_g.state_dict().items(), m_e.state_dict().values()):
+            assert torch.equal(a, b), (mode, k)
