@@ -223,6 +223,9 @@ def lp_partition(triples, num_ent, num_rels, rank, world, device="cuda", group=N
     ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]))
     ranges = partition_by_dst(ptr, world)
     lo, hi = ranges[rank][0], ranges[rank][1]
+    if hi <= lo:
+        raise RuntimeError(f"rank {rank} of {world} would own no destination (a hub holds more than 1/{world} of the "
+                           "edges): use fewer ranks for this graph")
     keep = (dst >= lo) & (dst < hi)
     half = int(keep[:T].sum())
     degf = deg.astype(np.float32)
@@ -248,6 +251,8 @@ def nc_partition(src, dst, etype, num_nodes, layers, rank, world, device="cuda",
     ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]))
     ranges = partition_by_dst(ptr, world)
     lo, hi = ranges[rank][0], ranges[rank][1]
+    if hi <= lo:
+        raise RuntimeError(f"rank {rank} of {world} would own no destination: use fewer ranks for this graph")
     eids = np.nonzero((dst >= lo) & (dst < hi))[0]
     block = MRBlock.build(torch.from_numpy(eids), torch.from_numpy(etype[eids]), torch.from_numpy(dst[eids] - lo),
                           torch.arange(lo, hi), device)
