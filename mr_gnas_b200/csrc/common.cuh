@@ -107,7 +107,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__device__ __forceinline__ float sigmoidf_(float t) { return 1.0f / (1.0f + expf(-t)); }
+// correctly rounded reciprocal instead of the IEEE division subroutine (one call per row in the gate kernels)
+__device__ __forceinline__ float sigmoidf_(float t) { return __frcp_rn(1.0f + expf(-t)); }
 
 // one element of sigmoid + BCELoss with torch's log clamp at -100 (operations_lp.py:126, mr_lp_train.py:116)
 __device__ __forceinline__ float bce_term(float logit, float yv, float* p_out) {
