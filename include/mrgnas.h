@@ -338,6 +338,18 @@ int mrg_distmult_bce_fwd(const float* query, const float* ent, const float* labe
                          float* logit, double* partial, float* loss, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Node-level Linear on the tcgen05 main loop (3xTF32, fp32-class accuracy):
+ *   out[r, f] = sum_k x[r,k] * W[f,k] + bias[f]      x [rows, K], W [F, K] (= nn.Linear.weight), out [rows, ldo]
+ * Replaces the fp32 SIMT library GEMMs of nn.Linear on the path -- the cell's `concat` Linear (model_lp.py:70-71)
+ * and `linear_e` (model_lp.py:124) -- and, called with W^T, their input gradients.  K % 8 == 0; any F
+ * (256 output features per launch); bias may be NULL.
+ * ---------------------------------------------------------------------------------- */
+int mrg_linear_tc_supported(int32_t K);
+size_t mrg_linear_tc_workspace_bytes(int32_t K);
+int mrg_linear_tc_fwd(const float* x, const float* W, const float* bias, int64_t rows, int32_t K, int32_t F, float* out,
+                      int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

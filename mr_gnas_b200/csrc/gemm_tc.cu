@@ -162,9 +162,12 @@ struct AmaxParams {
   float* logit;
   double* loss_partial;      // [gridDim.x]
   int64_t ldl;
+  // EPI_STORE: store[(tile position) * lds + f] = acc + bias[f]   (plain Linear: out = x W^T + b)
+  float* store;
+  int64_t lds;
 };
 
-enum { EPI_AMAX = 0, EPI_DISTMULT = 1 };
+enum { EPI_AMAX = 0, EPI_DISTMULT = 1, EPI_STORE = 2 };
 
 // One work ITEM = (tile, K chunk).  A CTA walks its tiles in PAIRS (TMEM slots 0/1) with the chunks of the
 // two tiles interleaved, so every W chunk fetched from L2 feeds two tiles (W re-streaming is the dominant
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
   for (int c = threadIdx.x; c < 256; c += THREADS) {
     s_scale[c] = (p.x.scale && c < D) ? p.x.scale[c] : 1.f;
     s_shift[c] = (p.x.scale && c < D) ? p.x.shift[c] : 0.f;
-    s_bias[c] = (p.bias && c < D) ? p.bias[c] : 0.f;
+    s_bias[c] = (p.bias && c < p.Dout) ? p.bias[c] : 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < XS; ++s) {
@@ -421,7 +424,38 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     const int quad = warp & 3;                        // TMEM lane quadrant of this warp
     int32_t* sd = s_dst + ts * TILE_E;
     int32_t* se = s_eid + ts * TILE_E;
-    if (EPI == EPI_DISTMULT) {
+    if (EPI == EPI_STORE) {
+      // ---- plain GEMM epilogue: TMEM lane = output feature f, TMEM column = input row of the tile; the 32 lanes of a
+      // warp write 32 consecutive features of one output row (coalesced).
+      for (int pr = 0; pr < npairs; ++pr) {
+        if (2 * pr + ts >= my_tiles) break;
+        const int64_t pos0 = tile_of(pr, ts) * TILE_E;
+        const int cnt = (int)min((int64_t)TILE_E, p.E - pos0);
+        mbar_wait(&tfull_bar[ts], pr & 1);
+        tc_fence_after();
+        for (int h = 0; h < MH; ++h) {
+          const int f = h * 128 + et;
+          const bool fvalid = f < p.Dout;
+          const float bias = s_bias[f & 255];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * (MH * TILE_E) + h * TILE_E;
+          float* o = p.store + (size_t)pos0 * p.lds + f;
+#pragma unroll 1
+          for (int w = 0; w < 4; ++w) {
+            const int cb = 32 * w;
+            if (cb >= cnt) break;   // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(taddr + cb, v);
+            if (fvalid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cb + j < cnt) o[(size_t)(cb + j) * p.lds] = __uint_as_float(v[j]) + bias;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[ts]);
+      }
+    } else if (EPI == EPI_DISTMULT) {
       // ---- DistMult 1-N scores + BCE: TMEM lane = query row b, TMEM column = entity of the tile.
       // logit[b, n] is stored for the backward; the loss terms are summed per thread (fp32 per 32 columns,
       // double across), per warp, per CTA -> loss_partial[cta]; nothing else leaves the SM.
@@ -638,6 +672,8 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   p.logit = nullptr;
   p.loss_partial = nullptr;
   p.ldl = 0;
+  p.store = nullptr;
+  p.lds = 0;
   if (p.num_tiles > 0) {
     const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
                         1024 /*align*/ + 8192 /*tail*/;
@@ -711,6 +747,8 @@ extern "C" int mrg_distmult_bce_fwd(const float* query, const float* ent, const 
     p.logit = logit + (size_t)b0 * N;
     p.loss_partial = partial + (size_t)chunk * kNumSMs;
     p.ldl = N;
+    p.store = nullptr;
+    p.lds = 0;
     const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
                         1024 /*align*/ + 8192 /*tail*/;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
@@ -726,5 +764,62 @@ extern "C" int mrg_distmult_bce_fwd(const float* query, const float* ent, const 
   }
   distmult_loss_finalize_kernel<<<1, 32, 0, st>>>(partial, nparts, (double)B * (double)N, loss);
   MRG_LAUNCH_CHECK("distmult_bce_fwd");
+  return MRG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Node-level Linear on the same main loop: out[r, f] = sum_k x[r,k] * W[f,k] + bias[f]  (3xTF32, fp32-class
+// accuracy).  Replaces the cuBLAS fp32 SIMT GEMMs of nn.Linear on the path (model_lp.py:70-71 `concat`,
+// :124 `linear_e`) and, called with W^T, their input gradients.  256 output features per launch.
+// ------------------------------------------------------------------------------------------
+extern "C" int mrg_linear_tc_supported(int32_t K) { return (K > 0 && K % 8 == 0) ? 1 : 0; }
+extern "C" size_t mrg_linear_tc_workspace_bytes(int32_t K) {
+  const int Kp = (K + tc::KCH - 1) / tc::KCH * tc::KCH;
+  return (size_t)2 * 2 * 128 * Kp * sizeof(float) + 1024;
+}
+
+extern "C" int mrg_linear_tc_fwd(const float* x, const float* W, const float* bias, int64_t rows, int32_t K, int32_t F,
+                                 float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
+  MRG_CHECK_ARG(x && W && out && workspace, "linear_tc_fwd: null pointer");
+  MRG_CHECK_ARG(rows >= 0 && F > 0 && ldo >= F, "linear_tc_fwd: sizes");
+  MRG_CHECK_ARG(mrg_linear_tc_supported(K), "linear_tc_fwd: K must be a positive multiple of 8");
+  if (workspace_bytes < mrg_linear_tc_workspace_bytes(K)) {
+    set_error("linear_tc_fwd: workspace too small");
+    return MRG_ERR_WORKSPACE;
+  }
+  if (rows == 0) return MRG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = (K + tc::KCH - 1) / tc::KCH * tc::KCH;
+  cudaError_t e;
+  for (int f0 = 0; f0 < F; f0 += 256) {
+    const int nf = F - f0 < 256 ? F - f0 : 256;
+    const int MH = nf <= 128 ? 1 : 2;
+    tc::tf32_split_kernel<<<64, 256, 0, st>>>(W + (size_t)f0 * K, nf, K, MH, Kp / tc::KCH, (float*)workspace);
+    tc::AmaxParams p;
+    p.x.data = x; p.x.scale = nullptr; p.x.shift = nullptr; p.x.relu = 0;
+    p.csr_eid = nullptr; p.dst = nullptr;
+    p.wimg = (const float*)workspace;
+    p.bias = bias ? bias + f0 : nullptr;
+    p.packed = nullptr;
+    p.E = rows; p.D = K; p.MH = MH; p.Kp = Kp; p.nchunks = Kp / tc::KCH;
+    p.num_tiles = (int)((rows + tc::TILE_E - 1) / tc::TILE_E);
+    p.Dout = nf;
+    p.label = nullptr; p.logit = nullptr; p.loss_partial = nullptr; p.ldl = 0;
+    p.store = out + f0;
+    p.lds = ldo;
+    const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
+                        1024 /*align*/ + 8192 /*tail*/;
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    if (MH == 1) {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<1, tc::EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "linear_tc_fwd smem attr");
+      tc::amax_tc_kernel<1, tc::EPI_STORE><<<grid, tc::THREADS, smem, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<2, tc::EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "linear_tc_fwd smem attr");
+      tc::amax_tc_kernel<2, tc::EPI_STORE><<<grid, tc::THREADS, smem, st>>>(p);
+    }
+  }
+  MRG_LAUNCH_CHECK("linear_tc_fwd");
   return MRG_OK;
 }

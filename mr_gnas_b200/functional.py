@@ -526,6 +526,63 @@ class SigmoidBCE(torch.autograd.Function):
         return dl, None
 
 
+# ------------------------------------------------------------------------------------------
+# node-level Linear on the tcgen05 main loop (3xTF32)
+# ------------------------------------------------------------------------------------------
+USE_TC_LINEAR = True
+_lin_ws = {}
+
+
+def _linear_tc(x, W, bias, out_cols=None):
+    """out = x @ W.T (+ bias) through mrg_linear_tc_fwd; x [rows, K], W [F, K] contiguous fp32."""
+    lib = _lib.load()
+    rows, Kd = x.shape
+    F_ = W.shape[0]
+    key = (Kd, str(x.device))
+    if key not in _lin_ws:
+        _lin_ws[key] = torch.empty(int(lib.mrg_linear_tc_workspace_bytes(Kd)), dtype=torch.uint8, device=x.device)
+    ws = _lin_ws[key]
+    out = torch.empty(rows, F_, dtype=torch.float32, device=x.device)
+    call("mrg_linear_tc_fwd", ptr(x), ptr(W), ptr(bias), rows, Kd, F_, ptr(out), F_, ptr(ws), ws.numel(), stream(),
+         nbytes=rows * (Kd + F_) * 4)
+    return out
+
+
+class LinearTC(torch.autograd.Function):
+    """nn.Linear forward and input gradient on the tensor cores with fp32-class accuracy (3xTF32): the cell's
+    `concat` Linear and `linear_e` (model_lp.py:70-71,124).  The weight gradient (reduction over the rows) stays a
+    library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight = _f32c(x), _f32c(weight)
+        bias = _f32c(bias) if bias is not None else None
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return _linear_tc(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = _f32c(gy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _linear_tc(gy, weight.t().contiguous(), None)      # dY [rows, F] x W [F, K]
+        if ctx.needs_input_grad[1]:
+            dw = torch.mm(gy.t(), x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = gy.sum(0)
+        return dx, dw, db
+
+
+def linear(module, x):
+    """module(x) for an nn.Linear, on the tensor-core path when the shapes allow it."""
+    if USE_TC_LINEAR and x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0 and module.weight.shape[0] % 8 == 0 \
+            and x.shape[0] >= 1024:
+        return LinearTC.apply(x, module.weight, module.bias)
+    return module(x)
+
+
 _dm_ws = {}
 
 

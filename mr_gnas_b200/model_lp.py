@@ -84,7 +84,7 @@ class Cell(nn.Module):
                 if len(self._ops[n][i]) > 0:
                     hs.append(self._ops[n][i][0](g, states[i], zero_out))
             states.append(hs[0] if len(hs) == 1 else sum(hs))  # 0 + t == t exactly; skip the extra pass
-        h = self.concat(torch.cat([states[idx] for idx in self._concat_node], dim=1))
+        h = K.linear(self.concat, torch.cat([states[idx] for idx in self._concat_node], dim=1))
         return K.bn_act(h, self.batchnorm_h, relu=True)
 
     def forward(self, g, src_emb, hr):
@@ -119,7 +119,7 @@ class Cell(nn.Module):
                 continue
             hs = [self._ops[n][i][0](g, states[i], None) for i in range(n + 1) if len(self._ops[n][i]) > 0]
             states[node] = hs[0] if len(hs) == 1 else sum(hs)
-        h = self.concat(torch.cat([states[idx] for idx in self._concat_node], dim=1))
+        h = K.linear(self.concat, torch.cat([states[idx] for idx in self._concat_node], dim=1))
         return K.bn_act(h, self.batchnorm_h, relu=True)
 
 
@@ -162,7 +162,7 @@ class Network(nn.Module):
         if getattr(g, 'part', None) is not None:
             ent_local, rel_embed = self._embed_partitioned(g)
             return D_.AllGatherRows.apply(ent_local, g.part), rel_embed
-        all_ent_emb = self.linear_e(self.embedding_h.weight)  # == embedding_h(arange(N))
+        all_ent_emb = K.linear(self.linear_e, self.embedding_h.weight)  # == embedding_h(arange(N))
         rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
         for cell in self.cells:
             all_ent_emb = cell.forward_fused(g, all_ent_emb, rel_embed)
@@ -176,7 +176,7 @@ class Network(nn.Module):
         ones), writes its own rows, and normalises with statistics summed over the ranks.  Returns the LOCAL rows
         [hi-lo, D] of the final entity table and the (replicated) relation table."""
         part = g.part
-        table = self.linear_e(self.embedding_h.weight)
+        table = K.linear(self.linear_e, self.embedding_h.weight)
         rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
         with D_.use(part):
             for k, cell in enumerate(self.cells):

@@ -426,3 +426,25 @@ def test_distmult_bce_fused_vs_fp64(dev, B, N, D):
     # and against the unfused library path of this repo on the same inputs
     loss_u = K.SigmoidBCE.apply(torch.mm((sub * rel).detach(), ent.detach().t()), label)
     _check("loss vs cuBLAS + sigmoid_bce kernel", loss.view(1), loss_u.view(1))
+
+
+# ------------------------------------------------------------------------------ node-level Linear (tcgen05, 3xTF32)
+@pytest.mark.parametrize("rows,K,F", [(14541, 800, 200), (14541, 200, 200), (3000, 64, 64), (1500, 256, 520), (2000, 40, 8)])
+def test_linear_tc_vs_fp64(dev, rows, K, F):
+    """mrg_linear_tc_fwd (forward and, with W^T, the input gradient) against fp64: nn.Linear of the cell's `concat`
+    (model_lp.py:70-71) and `linear_e` (:124); F > 256 runs several launches, K not a multiple of 32 is zero padded (K % 8 == 0 is required)."""
+    from mr_gnas_b200 import functional as K_
+    torch.manual_seed(rows + K + F)
+    lin = torch.nn.Linear(K, F).to(dev)
+    x = torch.randn(rows, K, device=dev, requires_grad=True)
+    y = K_.LinearTC.apply(x, lin.weight, lin.bias)
+    cot = torch.randn(rows, F, device=dev)
+    y.backward(cot)
+    x64 = x.detach().double().requires_grad_(True)
+    w64, b64 = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    y64 = x64 @ w64.t() + b64
+    y64.backward(cot.double())
+    _check("y", y, y64.float())
+    _check("dx", x.grad, x64.grad.float())
+    _check("dw", lin.weight.grad, w64.grad.float())
+    _check("db", lin.bias.grad, b64.grad.float())
