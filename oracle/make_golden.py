@@ -364,7 +364,52 @@ def gen_network_nc():
     torch.save(out, os.path.join(OUT, "network_nc.pt"))
 
 
+def gen_predict():
+    """The REAL predict() of train/mr_lp_train.py:269-314 (imported from the script with stub modules for its
+    non-path imports) on pre-computed probability matrices: a fake model returns them batch by batch.  Scores are
+    distinct inside every row, so the (upstream unspecified) order of exact ties plays no role."""
+    import importlib.util
+    for name, attrs in (("tensorboardX", {"SummaryWriter": object}), ("dataloader", {"get_dataset": None}),
+                        ("dgl.contrib", {}), ("dgl.contrib.data", {"load_data": None})):
+        mod = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        sys.modules.setdefault(name, mod)
+    spec = importlib.util.spec_from_file_location("ref_lp_train", os.path.join(REF, "train", "mr_lp_train.py"))
+    ref_train = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_train)
+    torch.manual_seed(11)
+    rng = np.random.RandomState(11)
+    N, B, nb = 523, 17, 5
+    batches = []
+    for _ in range(nb):
+        pred = torch.rand(B, N) * 0.98 + 0.01              # distinct with probability 1
+        trip = torch.from_numpy(np.stack([rng.randint(0, N, B), rng.randint(0, 6, B), rng.randint(0, N, B)], 1))
+        lab = (torch.rand(B, N) < 0.03).float()
+        lab[torch.arange(B), trip[:, 2]] = 1.0
+        batches.append((pred, trip, lab))
+
+    class FakeModel:
+        def __init__(self):
+            self.k = 0
+
+        def eval(self):
+            return self
+
+        def __call__(self, g, subj, rel):
+            out = batches[self.k][0].clone()
+            self.k += 1
+            return out
+
+    results, loss = ref_train.predict([(t, l) for _, t, l in batches], None, FakeModel(), "cpu")
+    torch.save({"batches": batches, "results": results, "loss": float(loss)}, os.path.join(OUT, "predict.pt"))
+    print("predict:", results)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "predict":
+        gen_predict()
+        sys.exit(0)
     os.makedirs(OUT, exist_ok=True)
     gen_ops_lp()
     gen_ops_nc()
@@ -373,5 +418,6 @@ if __name__ == "__main__":
     gen_search_lp()
     gen_compgcn()
     gen_network_nc()
+    gen_predict()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -124,3 +124,21 @@ def test_labels_from_csr_bit_identical_to_dense_host_labels(ls):
     part = labels_on_device(ptr.to(dev), idx.to(dev), N, ls, lo, hi)
     assert torch.equal(part.cpu(), y[:, lo:hi])
     assert idx.numel() * 4 + ptr.numel() * 4 < y.numel() * 4 / 100    # > 100x fewer bytes over PCIe
+
+
+def test_filtered_rank_kernel_matches_real_reference_golden(golden_dir):
+    """mrg_filtered_rank on the fixture generated by the REAL reference predict() (tests/golden/predict.pt)."""
+    import os
+    from mr_gnas_b200.evaluate import filtered_rank
+    dev = torch.device("cuda:0")
+    G = torch.load(os.path.join(golden_dir, "predict.pt"), weights_only=False)
+    mr = mrr = 0.0
+    hits = {1: 0, 3: 0, 10: 0}
+    for pred, trip, lab in G["batches"]:
+        ranks = filtered_rank(pred.to(dev), lab.to(dev), trip[:, 2].to(dev)).float()
+        mr += torch.sum(ranks).item()
+        mrr += torch.sum(1.0 / ranks).item()
+        for k in hits:
+            hits[k] += torch.numel(ranks[ranks <= k])
+    ref = G["results"]
+    assert mr == ref["mr"] and abs(mrr - ref["mrr"]) <= 1e-6 and all(hits[k] == ref[f"hits@{k}"] for k in hits)

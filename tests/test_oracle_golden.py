@@ -141,3 +141,15 @@ def test_compgcn(golden_dir, comp):
     for k, g in c["dparams"].items():
         if g is not None:
             _close(P["l." + k].grad, g, tol=1e-5)
+
+
+def test_oracle_predict_matches_real_reference_predict(golden_dir):
+    """Evaluation path: the oracle's sort-free filtered rank reproduces the result dictionary and
+    the summed test loss of the REAL predict() (train/mr_lp_train.py:269-314), fixture tests/golden/predict.pt."""
+    import os
+    import torch
+    from oracle import mrg_oracle as O
+    G = torch.load(os.path.join(golden_dir, "predict.pt"), weights_only=False)
+    results, loss = O.predict_results(G["batches"])
+    assert results == G["results"], (results, G["results"])
+    assert abs(loss - G["loss"]) <= 1e-6 * max(1.0, abs(G["loss"]))
