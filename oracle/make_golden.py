@@ -364,6 +364,22 @@ def gen_network_nc():
     torch.save(out, os.path.join(OUT, "network_nc.pt"))
 
 
+def gen_labels():
+    """1-N training items and their dense smoothed label rows from the REAL process() (utils/process_data.py:4-31)
+    and TrainDataset (utils/data_set.py:6-33): the fixture behind the host-side batch builders and the device-side
+    label expansion."""
+    N, R, T = 311, 4, 900
+    trip = synth_kg(N, R, T, seed=5)
+    items = process({'train': trip, 'valid': trip[:0], 'test': trip[:0]}, R)['train'][:24]
+    out = {"N": N, "R": R, "triples": torch.from_numpy(trip), "items": items, "rows": {}}
+    for ls in (0.1, 0.0):
+        ds = TrainDataset(items, N, types.SimpleNamespace(lbl_smooth=ls))
+        trs, ys = zip(*[ds[i] for i in range(len(items))])
+        out["rows"][ls] = (torch.stack(trs), torch.stack(ys))
+    torch.save(out, os.path.join(OUT, "labels.pt"))
+    print("labels:", len(items), "items")
+
+
 def gen_predict():
     """The REAL predict() of train/mr_lp_train.py:269-314 (imported from the script with stub modules for its
     non-path imports) on pre-computed probability matrices: a fake model returns them batch by batch.  Scores are
@@ -407,8 +423,8 @@ def gen_predict():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "predict":
-        gen_predict()
+    if len(sys.argv) > 1 and sys.argv[1] in ("predict", "labels"):
+        {"predict": gen_predict, "labels": gen_labels}[sys.argv[1]]()
         sys.exit(0)
     os.makedirs(OUT, exist_ok=True)
     gen_ops_lp()
@@ -419,5 +435,6 @@ if __name__ == "__main__":
     gen_compgcn()
     gen_network_nc()
     gen_predict()
+    gen_labels()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -150,3 +150,24 @@ def test_sparse_batch_and_label_values_match_dense_host_labels():
         if ls != 0.0:
             ref = (1.0 - ls) * ref + (1.0 / N)
         assert torch.equal(y[0], ref)
+
+
+def test_batch_builders_match_real_reference_dataset(golden_dir):
+    """process() + make_batch / make_batch_sparse + label_values against rows produced by the REAL
+    utils/process_data.process and utils/data_set.TrainDataset (tests/golden/labels.pt)."""
+    import torch
+    from mr_gnas_b200.process_data import label_values, make_batch, make_batch_sparse, process
+    G = torch.load(os.path.join(golden_dir, "labels.pt"), weights_only=False)
+    N, R, trip = G["N"], G["R"], G["triples"].numpy()
+    items = process({'train': trip, 'valid': trip[:0], 'test': trip[:0]}, R)['train'][:len(G["items"])]
+    assert [it['triple'] for it in items] == [tuple(it['triple']) for it in G["items"]]
+    assert [sorted(it['label']) for it in items] == [sorted(it['label']) for it in G["items"]]
+    for ls, (t_ref, y_ref) in G["rows"].items():
+        t, y = make_batch(items, N, lbl_smooth=ls)
+        assert torch.equal(t, t_ref) and torch.equal(y, y_ref)
+        t2, ptr, idx = make_batch_sparse(items)
+        neg, pos = label_values(N, ls)
+        dense = torch.full((len(items), N), neg, dtype=torch.float32)
+        for b in range(len(items)):
+            dense[b, idx[ptr[b]:ptr[b + 1]].long()] = pos
+        assert torch.equal(dense, y_ref)
