@@ -148,7 +148,7 @@ class AllGatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         part = ctx.part
-        g = g.contiguous()
+        g = g.clone(memory_format=torch.contiguous_format)   # autograd may share `g` with another consumer
         dist.all_reduce(g, group=part.group)
         return g[part.lo:part.hi].contiguous(), None
 
@@ -170,7 +170,7 @@ class ShardedRowSelect(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         own, loc = ctx.saved_tensors
-        g = g.contiguous()
+        g = g.clone(memory_format=torch.contiguous_format)   # never all-reduce autograd's own buffer in place
         dist.all_reduce(g, group=ctx.part.group)
         d = g.new_zeros(ctx.rows, g.shape[1])
         # static shapes (CUDA-graph capturable): rows of other ranks add exact zeros to a clamped index;

@@ -61,6 +61,15 @@ def seg_reduce_raw(seg, kind, m_act, D, out, arg=None, mul=None, mul_idx=None, a
     return out
 
 
+def check_tables(g, ent, rel):
+    """The gather reads ent[src_final] / rel[et_final] and its backward writes one row per CSC / relation
+    segment: both tables must have exactly the rows the graph was segmented for (else rows of the gradient
+    would stay unwritten)."""
+    if ent.shape[0] != g.n_src or rel.shape[0] != g.n_rel_rows:
+        raise RuntimeError(f"gather tables [{ent.shape[0]}, {rel.shape[0]}] rows do not match the graph "
+                           f"(entities {g.n_src}, relation rows {g.n_rel_rows}); see MRGraph.require_tables")
+
+
 class GatherCompose(torch.autograd.Function):
     """y[i] = h[src_final[i]] (-|*|+) r[et_final[i]] over the M edge-expanded rows, plus BN
     column statistics -- model_lp.py:126-131 fused with operations_lp.py:71-98.  Backward is
@@ -71,6 +80,7 @@ class GatherCompose(torch.autograd.Function):
     def forward(ctx, h, r, g, comp):
         h, r = _f32c(h), _f32c(r)
         D = h.shape[1]
+        check_tables(g, h, r)
         y = torch.empty(g.M, D, dtype=torch.float32, device=h.device)
         nparts = stats_nparts(g.M)
         stats = _stats_buf(nparts, D, h.device)
@@ -172,12 +182,22 @@ class BNAct(torch.autograd.Function):
         return dy, dgamma, dbeta, None, None, None, None, None, None, None
 
 
+def bn_momentum(bn):
+    """Running-statistics update factor.  momentum=None (PyTorch: cumulative average 1/num_batches_tracked) would
+    need a host read of a device counter inside the captured step; the reference only builds default
+    nn.BatchNorm1d(D) (momentum 0.1), so it is refused rather than silently replaced by 0.1."""
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative average) is not supported by the fused "
+                                  "BatchNorm path; the reference uses the default momentum=0.1")
+    return float(bn.momentum)
+
+
 def bn_act(y, bn, relu=True, stats=None):
     """Apply an nn.BatchNorm1d module's parameters/buffers through the fused kernels."""
     training = bn.training or not bn.track_running_stats
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    momentum = 0.1 if bn.momentum is None else bn.momentum
+    momentum = bn_momentum(bn)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     return BNAct.apply(y, bn.weight, bn.bias, rm, rv, training, momentum, bn.eps, relu, stats)
@@ -741,5 +761,5 @@ def mixed_sum(weights, ys, bn_modules):
         bns.append((bn.running_mean, bn.running_var))
         stats.append(getattr(y, 'mrg_stats', None))
         flat += [y, bn.weight, bn.bias]
-    mom = 0.1 if bn_modules[0].momentum is None else bn_modules[0].momentum
+    mom = bn_momentum(bn_modules[0])
     return MixedSum.apply(weights, training, bn_modules[0].eps, mom, bns, stats, *flat)

@@ -63,6 +63,7 @@ class EdgeChain(torch.autograd.Function):
     def forward(ctx, g, plan, training, ent, rel, *params):
         first, gates, aggs = plan
         ent, rel = K._f32c(ent), K._f32c(rel)
+        K.check_tables(g, ent, rel)
         D = ent.shape[1]
         dev = ent.device
         M, E, N = g.M, g.E, g.N
@@ -79,7 +80,7 @@ class EdgeChain(torch.autograd.Function):
                 bn.num_batches_tracked.add_(1)
                 a = torch.empty(D, dtype=torch.float32, device=dev)
                 b, mean, invstd = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
-                mom = 0.1 if bn.momentum is None else bn.momentum
+                mom = K.bn_momentum(bn)
                 stats, nparts_, rows = D_.sync_stats(g.part, stats, stats.numel() // (2 * D), 2 * D, rows)
                 call("mrg_bn_finalize", ptr(stats), nparts_, rows, D, ptr(gamma), ptr(beta), float(bn.eps),
                      float(mom), ptr(bn.running_mean), ptr(bn.running_var), ptr(mean), ptr(invstd), ptr(a), ptr(b),

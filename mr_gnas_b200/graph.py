@@ -57,6 +57,7 @@ class MRGraph:
         self.half = None      # rows [0, half) original direction, [half, E) inverse (E // 2 for the full graph)
         self.part = None      # dist.Partition when this graph holds one destination range of a larger graph
         self.n_src = None     # rows of the gather tables (== N unless partitioned)
+        self._rel_rows_inferred = False
 
     # ----------------------------------------------------------------- construction
     @classmethod
@@ -153,7 +154,29 @@ class MRGraph:
             nrel = 1
         else:
             nrel = int(et.max().item()) + 2 if et.numel() else 1  # + self-loop relation row
+        # The DGL-style deferred build never states the relation count: what the data shows is a lower bound
+        # (the highest inverse relation may have no edge).  The model states the real table size through
+        # require_tables(), which rebuilds the relation segments if the guess was short.
+        self._rel_rows_inferred = True
         self._finalize(src, dst, et, nrel, with_norm=True)
+
+    def require_tables(self, n_ent_rows, n_rel_rows):
+        """Called by the networks before the gather: the entity / relation tables must have exactly the rows this
+        graph's gather indices and backward segment lists cover (src ids < n_src, relation ids < n_rel_rows, the
+        self-loop rows use relation n_rel_rows - 1 = 2R).  A graph assembled DGL-style (add_edges + edata) only
+        guessed its relation count and is re-segmented here; anything else is an error, not silent garbage."""
+        self._ensure()
+        if int(n_ent_rows) != self.n_src:
+            raise RuntimeError(f"entity table has {n_ent_rows} rows, the graph gathers from {self.n_src}")
+        if int(n_rel_rows) == self.n_rel_rows:
+            return self
+        if self._rel_rows_inferred and self.part is None and int(n_rel_rows) > int(self.etype.max().item()) + 1:
+            norm = self.edata.get("norm")
+            self._finalize(self.src, self.dst, self.etype, int(n_rel_rows), with_norm=True)
+            if norm is not None:         # keep a norm the script wrote itself (mr_lp_search.py:30-36)
+                self.edata["norm"] = norm
+            return self
+        raise RuntimeError(f"relation table has {n_rel_rows} rows, the graph was built for {self.n_rel_rows}")
 
     def _finalize(self, src, dst, etype, n_rel_rows, with_norm=True, dst_only=False):
         dev = self._device

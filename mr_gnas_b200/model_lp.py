@@ -162,6 +162,7 @@ class Network(nn.Module):
         if getattr(g, 'part', None) is not None:
             ent_local, rel_embed = self._embed_partitioned(g)
             return D_.AllGatherRows.apply(ent_local, g.part), rel_embed
+        g.require_tables(self._num_ent, self._num_rel)
         all_ent_emb = K.linear(self.linear_e, self.embedding_h.weight)  # == embedding_h(arange(N))
         rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
         for cell in self.cells:
@@ -176,6 +177,7 @@ class Network(nn.Module):
         ones), writes its own rows, and normalises with statistics summed over the ranks.  Returns the LOCAL rows
         [hi-lo, D] of the final entity table and the (replicated) relation table."""
         part = g.part
+        g.require_tables(self._num_ent, self._num_rel)
         table = K.linear(self.linear_e, self.embedding_h.weight)
         rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
         with D_.use(part):
@@ -207,6 +209,12 @@ class Network(nn.Module):
             sub = D_.ShardedRowSelect.apply(ent_local, subj, part)
             loss_local = self.score_func.loss(ent_local, sub, rel_embed[rel], label)
             return D_.AllReduceSum.apply(loss_local * (part.n_local / part.n_global), part)
+        if part is not None and part.world > 1:
+            # the replicated-loss form would hand every rank the COMPLETE table gradient, which the partitioned
+            # step's gradient sum then multiplies by the world size
+            raise RuntimeError("destination-partitioned training supports sf_DisMult with mean nn.BCELoss (the "
+                               "entity-sharded fused loss); got "
+                               f"{type(self.score_func).__name__} / {type(self.criterion).__name__}")
         if fused_ok:
             all_ent_emb, rel_embed = self._embed(g)
             return self.score_func.loss(all_ent_emb, all_ent_emb[subj], rel_embed[rel], label)

@@ -3,35 +3,75 @@ utils/data_set.py:6-59): 1-N training items {(s, r) -> objects} including invers
 dense multi-hot labels with label smoothing.  Also the place where the training graph is
 rebuilt as destination-sorted CSR + (relation, direction) segments (north_star): see
 ``build_graph`` -> mr_gnas_b200.graph.MRGraph."""
-from collections import defaultdict as ddict
-
 import numpy as np
 import torch
 
 from .graph import MRGraph
 
 
+def _queries(triples, num_rel):
+    """[T,3] (s, r, o) -> the 2T 1-N queries in the order the reference visits them: (s, r)->o and (o, r+R)->s
+    interleaved per triple.  Returns (key [2T] = subj * 2R + rel, answer [2T])."""
+    t = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+    subj = np.stack([t[:, 0], t[:, 2]], 1).reshape(-1)
+    rel = np.stack([t[:, 1], t[:, 1] + num_rel], 1).reshape(-1)
+    return subj * (2 * num_rel) + rel, np.stack([t[:, 2], t[:, 0]], 1).reshape(-1)
+
+
+class QueryCSR:
+    """The (subject, relation) -> {objects} map as one sorted-unique CSR (the form the device label kernel and
+    make_batch_sparse want): `keys` ascending, `ptr` [K+1], `obj` ascending inside a key, `first` = position of the
+    key's first occurrence in the visiting order (the reference's dict insertion order)."""
+
+    def __init__(self, key, ans):
+        order = np.lexsort((ans, key))
+        k_s, a_s = key[order], ans[order]
+        keep = np.ones(k_s.shape[0], dtype=bool)
+        keep[1:] = (k_s[1:] != k_s[:-1]) | (a_s[1:] != a_s[:-1])
+        k_u, self.obj = k_s[keep], a_s[keep]
+        self.keys, start = np.unique(k_u, return_index=True)
+        self.ptr = np.append(start, k_u.shape[0]).astype(np.int64)
+        _, self.first = np.unique(key, return_index=True)
+        self._lists = None
+
+    def lookup(self, key):
+        """rows of `key` in this CSR (every key must be present)."""
+        return np.searchsorted(self.keys, key)
+
+    def labels(self, row):
+        """object list of CSR row `row` (one shared list per row, like the reference's shared sr2o lists)."""
+        if self._lists is None:
+            flat, p = self.obj.tolist(), self.ptr.tolist()
+            self._lists = [flat[a:b] for a, b in zip(p[:-1], p[1:])]
+        return self._lists[row]
+
+
 def process(dataset, num_rel):
-    """reference: utils/process_data.py:4-31 (same keys, same item order)."""
-    sr2o = ddict(set)
-    for subj, rel, obj in dataset['train']:
-        sr2o[(subj, rel)].add(obj)
-        sr2o[(obj, rel + num_rel)].add(subj)
-    sr2o_train = {k: list(v) for k, v in sr2o.items()}
-    for split in ['valid', 'test', 'train']:
-        for subj, rel, obj in dataset[split]:
-            sr2o[(subj, rel)].add(obj)
-            sr2o[(obj, rel + num_rel)].add(subj)
-    sr2o_all = {k: list(v) for k, v in sr2o.items()}
-    triplets = ddict(list)
-    for (subj, rel), obj in sr2o_train.items():
-        triplets['train'].append({'triple': (subj, rel, -1), 'label': sr2o_train[(subj, rel)]})
-    for split in ['valid', 'test', 'train']:
-        for subj, rel, obj in dataset[split]:
-            triplets[f"{split}_tail"].append({'triple': (subj, rel, obj), 'label': sr2o_all[(subj, rel)]})
-            triplets[f"{split}_head"].append(
-                {'triple': (obj, rel + num_rel, subj), 'label': sr2o_all[(obj, rel + num_rel)]})
-    return dict(triplets)
+    """Same result dictionary as the reference's utils/process_data.py:4-31 -- 'train' holds one
+    {'triple': (s, r, -1), 'label': objects seen in train} item per distinct query in first-seen order,
+    '{split}_tail' / '{split}_head' one item per triple with the objects seen in ANY split -- built from two
+    sorted-unique CSRs instead of per-triple Python set updates.  Label lists come out ascending (the reference's
+    `list(set)` order is arbitrary; every consumer scatters them into a multi-hot row)."""
+    R2 = 2 * num_rel
+    splits = {s: np.asarray(dataset[s], dtype=np.int64).reshape(-1, 3) for s in ('train', 'valid', 'test')}
+    k_tr, a_tr = _queries(splits['train'], num_rel)
+    train = QueryCSR(k_tr, a_tr)
+    k_all, a_all = _queries(np.concatenate([splits['valid'], splits['test'], splits['train']]), num_rel)
+    every = QueryCSR(k_all, a_all)
+    seen = np.argsort(train.first, kind='stable')
+    out = {'train': [{'triple': (s, r, -1), 'label': train.labels(j)} for s, r, j in
+                     zip((train.keys[seen] // R2).tolist(), (train.keys[seen] % R2).tolist(), seen.tolist())]}
+    for split in ('valid', 'test', 'train'):
+        t = splits[split]
+        key, _ = _queries(t, num_rel)
+        rows = every.lookup(key).reshape(-1, 2)
+        tails, heads = [], []
+        for (s, r, o), (jt, jh) in zip(t.tolist(), rows.tolist()):
+            tails.append({'triple': (s, r, o), 'label': every.labels(jt)})
+            heads.append({'triple': (o, r + num_rel, s), 'label': every.labels(jh)})
+        if tails:
+            out[f"{split}_tail"], out[f"{split}_head"] = tails, heads
+    return out
 
 
 def build_graph(num_ent, data, num_rels, device="cuda"):

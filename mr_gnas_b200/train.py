@@ -58,11 +58,18 @@ class GraphedTrainStep:
         self.opt.step()
         return loss
 
-    def capture(self):
+    def capture(self, keep_warmup_updates=False):
         """Warm up on a side stream (lazy workspaces, cudaFuncSetAttribute, NCCL channels), then capture.
-        The warm-up runs `warmup` REAL training steps on the batch currently in the static inputs (load a batch
-        first); replaying the graph afterwards is bit-identical to issuing the same steps eagerly
-        (tests/test_gpu_network_lp.py::test_graphed_train_step_replays_the_eager_step)."""
+        The warm-up runs `warmup` training steps on the batch currently in the static inputs; model parameters
+        and buffers (BatchNorm running statistics, num_batches_tracked) and the optimiser state (moments, step
+        counters) are restored afterwards, so training starts from exactly the state capture() was called in
+        (`keep_warmup_updates=True` keeps them: then graph replay continues the eager steps bit-identically,
+        tests/test_gpu_network_lp.py::test_graphed_train_step_replays_the_eager_step)."""
+        import copy
+        snap = None
+        if not keep_warmup_updates:
+            snap = ({k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                    copy.deepcopy(self.opt.state_dict()))
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -70,6 +77,22 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if snap is not None:
+            with torch.no_grad():
+                for k, v in self.model.state_dict().items():     # in place: the graph captures these addresses
+                    v.copy_(snap[0][k])
+                had_state = len(snap[1]['state']) > 0
+                if had_state:
+                    cur = self.opt.state_dict()
+                    for pid, st in cur['state'].items():
+                        for name, val in st.items():
+                            if torch.is_tensor(val):
+                                val.copy_(snap[1]['state'][pid][name])
+                else:            # fresh optimiser: zero the lazily created moments / step counters in place
+                    for st in self.opt.state.values():
+                        for val in st.values():
+                            if torch.is_tensor(val):
+                                val.zero_()
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):

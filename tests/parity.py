@@ -1,0 +1,61 @@
+"""Parity metrics shared by the GPU tests (the north_star's "within 1e-5 relative in fp32").
+
+Every float comparison is RELATIVE TO THE REFERENCE TENSOR'S OWN SCALE -- there is no absolute floor, so a
+gradient whose entries are all ~1e-6 must still agree to ~1e-11:
+
+  rel_err(a, b)  = max|a - b| / max|b|          (max-norm relative error)
+  norm_err(a, b) = ||a - b||_2 / ||b||_2        (norm-wise relative error)
+
+and `check` asserts BOTH <= tol (default RTOL = 1e-5).  An element-wise bound |a-b| <= rtol*|b| with no scale
+term cannot hold for fp32 sums that nearly cancel (the element's own magnitude says nothing about the size of
+the terms that were added), so the element-wise form used is |a - b| <= RTOL*|b| + RTOL*max|b|, which the
+max-norm bound implies.  When the reference tensor is exactly zero the error is absolute (max|a|).
+
+`truth` (optional): an fp64 evaluation of the same quantity.  fp32 CPU and fp32 GPU sum in different orders, so
+against fp64 the bar is max(tol, 4 x the fp32 CPU reference's own error vs fp64): the product may not be further
+from the truth than a small multiple of what the reference's fp32 path itself achieves."""
+import torch
+
+RTOL = 1e-5
+
+
+def _d(t):
+    return t.detach().double().cpu()
+
+
+def rel_err(a, b):
+    a, b = _d(a), _d(b)
+    if a.numel() == 0:
+        return 0.0
+    scale = float(b.abs().max())
+    diff = float((a - b).abs().max())
+    return diff if scale == 0.0 else diff / scale
+
+
+def norm_err(a, b):
+    a, b = _d(a), _d(b)
+    if a.numel() == 0:
+        return 0.0
+    scale = float(b.norm())
+    diff = float((a - b).norm())
+    return diff if scale == 0.0 else diff / scale
+
+
+def bar(ref32=None, truth=None, tol=RTOL):
+    """Tolerance against `truth` given the fp32 reference's own distance from it."""
+    if truth is None or ref32 is None:
+        return tol
+    return max(tol, 4.0 * rel_err(ref32, truth))
+
+
+def check(name, a, b, tol=RTOL, truth=None):
+    """a: product result, b: fp32 reference (oracle / golden), truth: optional fp64 evaluation."""
+    assert tuple(a.shape) == tuple(b.shape), f"{name}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    if truth is not None:
+        t = bar(b, truth, tol)
+        e, n = rel_err(a, truth), norm_err(a, truth)
+    else:
+        t = tol
+        e, n = rel_err(a, b), norm_err(a, b)
+    assert e <= t and n <= t, f"{name}: max-norm rel err {e:.3e}, 2-norm rel err {n:.3e} > {t:.1e}"
+    return e

@@ -26,9 +26,7 @@ README = [Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f_s
 REL = 1e-5
 
 
-def _err(a, b):
-    a, b = a.detach().double(), b.detach().double()
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 @pytest.fixture(scope="module")

@@ -18,9 +18,7 @@ README = ("[Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f
           "concat_node=[4, 5, 6, 7], score_func='sf_DisMult')]")
 
 
-def _err(a, b):
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _args(D):
@@ -171,14 +169,18 @@ def test_graphed_train_step_replays_the_eager_step():
         m = m.to(dev).train()
         return m, torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
 
-    # eager: 3 warm-up steps on batch 0 (what capture() does), then batches 1..3
+    # eager reference A: batches 0..3 from the fresh state (default capture() restores model + optimiser state
+    # after its warm-up); eager reference B: 3 warm-up steps on batch 0 then batches 1..3 (keep_warmup_updates)
+    t0, y0 = dense[0]
+    m_a, opt_a = fresh()
+    run_a = GraphedTrainStep(m_a, g, opt_a, B, N, warmup=3)
+    losses_a = [float(run_a(t[:, 0].to(dev), t[:, 1].to(dev), y.to(dev))) for t, y in dense]
     m_e, opt_e = fresh()
     run_e = GraphedTrainStep(m_e, g, opt_e, B, N, warmup=3)
-    t0, y0 = dense[0]
     for _ in range(3):
         run_e(t0[:, 0].to(dev), t0[:, 1].to(dev), y0.to(dev))
     losses_e = [float(run_e(t[:, 0].to(dev), t[:, 1].to(dev), y.to(dev))) for t, y in dense[1:]]
-    for mode in ("dense", "sparse"):
+    for mode, keep in (("dense", False), ("dense", True), ("sparse", False), ("sparse", True)):
         m_g, opt_g = fresh()
         cfg = dict(num_ent=N, lbl_smooth=0.1, cap=4 * max(s[2].numel() for s in sparse)) if mode == "sparse" else None
         run_g = GraphedTrainStep(m_g, g, opt_g, B, N, warmup=3, sparse_labels=cfg)
@@ -187,13 +189,15 @@ def test_graphed_train_step_replays_the_eager_step():
         else:
             run_g.load_sparse(sparse[0][0][:, 0].to(dev), sparse[0][0][:, 1].to(dev), sparse[0][1].to(dev),
                               sparse[0][2].to(dev))
-        run_g.capture()
+        run_g.capture(keep_warmup_updates=keep)
         assert run_g.graph is not None
+        first = 1 if keep else 0
         if mode == "dense":
-            losses_g = [float(run_g(t[:, 0].to(dev), t[:, 1].to(dev), y.to(dev))) for t, y in dense[1:]]
+            losses_g = [float(run_g(t[:, 0].to(dev), t[:, 1].to(dev), y.to(dev))) for t, y in dense[first:]]
         else:
             losses_g = [float(run_g(t[:, 0].to(dev), t[:, 1].to(dev), label_csr=(p.to(dev), i.to(dev))))
-                        for t, p, i in sparse[1:]]
-        assert losses_g == losses_e, (mode, losses_g, losses_e)
-        for (k, a), b in zip(m_g.state_dict().items(), m_e.state_dict().values()):
-            assert torch.equal(a, b), (mode, k)
+                        for t, p, i in sparse[first:]]
+        want, m_want = (losses_e, m_e) if keep else (losses_a, m_a)
+        assert losses_g == want, (mode, keep, losses_g, want)
+        for (k, a), b in zip(m_g.state_dict().items(), m_want.state_dict().values()):
+            assert torch.equal(a, b), (mode, keep, k)

@@ -33,9 +33,7 @@ def _args(D):
                                  conve_hid_drop=0.0, feat_drop=0.0, num_filt=4, ker_sz=3, k_w=4, k_h=D // 4)
 
 
-def _err(a, b):
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _compare(rank, world, n_cells):

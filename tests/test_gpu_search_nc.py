@@ -19,9 +19,7 @@ def _load(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name), weights_only=False)
 
 
-def _err(a, b):
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _check(name, a, b, tol=REL):
