@@ -14,6 +14,33 @@ import torch
 import torch.distributed as dist
 
 
+def _staged(t, group):
+    """True when the process group cannot move device memory itself (gloo: used by the CPU tests and by the
+    2-rank tests on a one-GPU box, where NCCL refuses two ranks on one device): bounce through the host."""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def all_reduce_(t, group=None):
+    """In-place sum all-reduce of `t` over `group` (NCCL over NVLink on the GPU path)."""
+    if _staged(t, group):
+        h = t.detach().cpu()
+        dist.all_reduce(h, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, group=group)
+    return t
+
+
+def all_gather_into_(out, inp, group=None):
+    if _staged(inp, group):
+        ho, hi = out.detach().cpu(), inp.detach().cpu()
+        dist.all_gather_into_tensor(ho, hi, group=group)
+        out.copy_(ho)
+    else:
+        dist.all_gather_into_tensor(out, inp, group=group)
+    return out
+
+
 def allreduce_grads(params, world_size=None, group=None):
     """Average .grad of `params` across ranks with one flat all-reduce (deterministic packing order)."""
     world_size = world_size or (dist.get_world_size(group) if dist.is_initialized() else 1)
@@ -23,7 +50,7 @@ def allreduce_grads(params, world_size=None, group=None):
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
+    all_reduce_(flat, group)
     flat /= world_size
     off = 0
     for g in grads:
@@ -51,7 +78,7 @@ def allreduce_stats(stats, group=None):
     [2, D] double vector of each rank is all-reduced; mrg_bn_finalize then runs with nparts=1 and the GLOBAL
     row count so every rank derives identical scale/shift."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(stats, group=group)
+        all_reduce_(stats, group)
     return stats
 
 
@@ -116,7 +143,7 @@ def sync_stats(part, stats, nparts, width, rows):
     if part is None or part.world <= 1:
         return stats, nparts, rows
     folded = stats[:nparts * width].view(nparts, width).sum(0)
-    dist.all_reduce(folded, group=part.group)
+    all_reduce_(folded, part.group)
     return folded.contiguous(), 1, part.rows_global(rows)
 
 
@@ -142,14 +169,14 @@ class AllGatherRows(torch.autograd.Function):
         buf = x.new_zeros(pad, x.shape[1])
         buf[:x.shape[0]] = x
         out = x.new_empty(part.world * pad, x.shape[1])
-        dist.all_gather_into_tensor(out, buf, group=part.group)
+        all_gather_into_(out, buf, part.group)
         return torch.cat([out[r * pad:r * pad + sizes[r]] for r in range(part.world)], 0)
 
     @staticmethod
     def backward(ctx, g):
         part = ctx.part
         g = g.clone(memory_format=torch.contiguous_format)   # autograd may share `g` with another consumer
-        dist.all_reduce(g, group=part.group)
+        all_reduce_(g, part.group)
         return g[part.lo:part.hi].contiguous(), None
 
 
@@ -162,7 +189,7 @@ class ShardedRowSelect(torch.autograd.Function):
         own = (idx >= part.lo) & (idx < part.hi)
         loc = (idx - part.lo).clamp(0, max(part.n_local - 1, 0))
         out = table[loc] * own.unsqueeze(1).to(table.dtype)
-        dist.all_reduce(out, group=part.group)
+        all_reduce_(out, part.group)
         ctx.part, ctx.rows = part, table.shape[0]
         ctx.save_for_backward(own, loc)
         return out
@@ -171,7 +198,7 @@ class ShardedRowSelect(torch.autograd.Function):
     def backward(ctx, g):
         own, loc = ctx.saved_tensors
         g = g.clone(memory_format=torch.contiguous_format)   # never all-reduce autograd's own buffer in place
-        dist.all_reduce(g, group=ctx.part.group)
+        all_reduce_(g, ctx.part.group)
         d = g.new_zeros(ctx.rows, g.shape[1])
         # static shapes (CUDA-graph capturable): rows of other ranks add exact zeros to a clamped index;
         # index_put_(accumulate) is sort-based on CUDA, hence deterministic
@@ -185,7 +212,7 @@ class AllReduceSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, part):
         y = x.clone()
-        dist.all_reduce(y, group=part.group)
+        all_reduce_(y, part.group)
         return y
 
     @staticmethod
@@ -201,7 +228,7 @@ def allreduce_grads_sum(params, part):
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=part.group)
+    all_reduce_(flat, part.group)
     off = 0
     for g in grads:
         n = g.numel()

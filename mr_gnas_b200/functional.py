@@ -460,6 +460,8 @@ class AMaxTC(torch.autograd.Function):
         ctx.g, ctx.has_residual = g, has_residual
         ctx.save_for_backward(x, weight, arg)
         g.last_arg = arg
+        if getattr(g, 'arg_trace', None) is not None:
+            g.arg_trace.append(arg)
         return out
 
     @staticmethod

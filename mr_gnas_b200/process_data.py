@@ -74,6 +74,20 @@ def process(dataset, num_rel):
     return out
 
 
+def train_items(triples, num_rel, select=None):
+    """process(...)['train'] (or only its items `select`, positions in that list) without building the evaluation
+    splits -- what a training loop that draws query batches needs.  -> (items, number of distinct queries)."""
+    R2 = 2 * num_rel
+    key, ans = _queries(triples, num_rel)
+    csr = QueryCSR(key, ans)
+    seen = np.argsort(csr.first, kind='stable')
+    total = seen.shape[0]
+    if select is not None:
+        seen = seen[np.asarray(select, dtype=np.int64)]
+    return [{'triple': (int(csr.keys[j] // R2), int(csr.keys[j] % R2), -1),
+             'label': csr.obj[csr.ptr[j]:csr.ptr[j + 1]].tolist()} for j in seen.tolist()], total
+
+
 def build_graph(num_ent, data, num_rels, device="cuda"):
     """reference: train/mr_lp_train.py:77-89, rebuilt on the device as dst-sorted CSR."""
     return MRGraph.from_triples(num_ent, np.asarray(data), num_rels, device=device)

@@ -84,6 +84,7 @@ class StubGraph:
         self.dstdata = self.ndata
         self.srcdata = self.ndata
         self.last_arg = None
+        self.arg_trace = []        # every update_all(max) appends its argmax table (test infrastructure)
 
     # --- construction API used by the scripts (mr_lp_train.py:78-88) ---
     def add_nodes(self, n):
@@ -153,6 +154,7 @@ class StubGraph:
         elif red.kind == "max":
             out, arg = _SegMax.apply(m, dst, N)
             self.last_arg = arg
+            self.arg_trace.append(arg)
         else:
             raise NotImplementedError(red.kind)
         self.ndata[out_key] = out

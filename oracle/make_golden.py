@@ -364,6 +364,195 @@ def gen_network_nc():
     torch.save(out, os.path.join(OUT, "network_nc.pt"))
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE.json configuration shapes, run through the REAL reference; results stored as compact summaries
+# (oracle/summary.py) so the fixtures stay small.  Inputs are regenerated from seeds by the tests (checksums stored).
+# ------------------------------------------------------------------------------------------------------------
+def _summ_all(prefix, named):
+    from oracle.summary import summarize
+    return {k: (summarize(prefix + k, v) if v is not None else None) for k, v in named.items()}
+
+
+def gen_config_c1():
+    """configs[0]/C1: README genotype LP training step on the FB15k-237-shaped KG, full size, no rescaling of any
+    parameter: N=14,541 R=237 T=272,115 D=200 B=256, label smoothing 0.1 (mr_lp_train.py:222-246)."""
+    import time
+    from oracle.summary import checksum, positions, summarize
+    N, R, T, D, B = 14541, 237, 272115, 200, 256
+    trip = synth_kg(N, R, T, seed=0)
+    g = ref_build_graph(N, trip, R)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = ref_model_lp.Network('cpu', eval(README_GENOTYPE), N, R, D, D, 2 * R + 1, nn.BCELoss(), 0.0, _lp_args(D))
+    model.apply(weights_init)
+    state0 = _sd(model)
+    items = process({'train': trip, 'valid': trip[:0], 'test': trip[:0]}, R)['train'][:B]
+    ds = TrainDataset(items, N, types.SimpleNamespace(lbl_smooth=0.1))
+    rows = [ds[i] for i in range(B)]
+    tr, labels = torch.stack([r[0] for r in rows]), torch.stack([r[1] for r in rows])
+    model.train()
+    seen = {}
+    hook = model.score_func.register_forward_hook(lambda mod, inp, out: seen.update(inp=[t.detach() for t in inp]))
+    t0 = time.time()
+    pred = model(g, tr[:, 0], tr[:, 1])
+    loss = model.criterion(pred, labels)
+    loss.backward()
+    hook.remove()
+    all_ent, sub_emb, rel_emb = seen["inp"]
+    logits = torch.mm(sub_emb * rel_emb, all_ent.t())      # operations_lp.py:121-126 before the sigmoid
+    assert torch.equal(torch.sigmoid(logits), pred.detach())
+    print("config_c1: real reference fwd+bwd %.1f s, loss %.8f, max|logit| %.2f" %
+          (time.time() - t0, loss.item(), float(logits.abs().max())))
+    state1 = _sd(model)
+    args32 = list(g.arg_trace)
+    # "truth": the same REAL modules in float64 from the same initial state, with the reference's fp32 scoring head
+    # (fp32 sigmoid + BCELoss on the logits rounded to fp32) -- in fp64 the probabilities would not saturate and
+    # BCELoss's clamp / zero-gradient semantics, which ARE the reference's behaviour at this init, would vanish
+    import copy
+    model64 = copy.deepcopy(model)
+    model64.load_state_dict(state0)
+    model64 = model64.double().train()
+    model64.zero_grad()
+
+    class _Head32(nn.Module):
+        def forward(self, all_ent, sub_emb, rel_emb):
+            self.logits = torch.mm(sub_emb * rel_emb, all_ent.t())
+            return torch.sigmoid(self.logits.float())
+    model64.score_func = _Head32()
+    g.edata['norm'] = g.edata['norm'].double()
+    t0 = time.time()
+    pred64 = model64(g, tr[:, 0], tr[:, 1])
+    loss64 = model.criterion(pred64, labels)
+    loss64.backward()
+    g.edata['norm'] = g.edata['norm'].float()
+    print("config_c1: fp64 truth %.1f s, loss %.8f" % (time.time() - t0, loss64.item()))
+    out = {"dims": {"N": N, "R": R, "T": T, "D": D, "B": B}, "genotype": README_GENOTYPE,
+           "truth64": {"loss": loss64.detach().clone(), "logits": summarize("logits", model64.score_func.logits),
+                       "grads": _summ_all("grad.", _grads(model64))},
+           "inputs": {"triples": checksum(trip), "subj": tr[:, 0].clone(), "rel": tr[:, 1].clone(),
+                      "labels": summarize("labels", labels)},
+           "loss": loss.detach().clone(), "pred": summarize("pred", pred), "logits": summarize("logits", logits),
+           "all_ent": summarize("all_ent", all_ent),
+           "saturated": {"p_eq_1": int((pred == 1).sum()), "p_eq_0": int((pred == 0).sum()), "numel": pred.numel()},
+           "grads": _summ_all("grad.", _grads(model)),
+           "buffers": {k: v.clone() for k, v in state1.items() if "running" in k or "num_batches" in k},
+           "arg_vals": [a.reshape(-1)[positions(a.numel(), 1234 + i, 8192)].clone() for i, a in enumerate(args32)]}
+    torch.save(out, os.path.join(OUT, "config_c1.pt"))
+
+
+def gen_config_c3():
+    """configs[2]/C3: LP supernet step (model_search_lp.py:131-194, search/mr_lp_search.py:188-236) on the
+    WN18RR-shaped KG: N=40,943 R=11 T=86,835, D=200, init 100, num_base_r=23, 2 layers, zero/first/last nodes
+    1/2/2, graph_batch_size 30,000, split 0.5, negative_sample 10, uniform edge sampler, np seed 0."""
+    import time
+    import utils.utils_rgcn as ref_rgcn
+    from oracle.summary import checksum, summarize
+    N, R, T, D, D0, GB = 40943, 11, 86835, 200, 100, 30000
+    trip = synth_kg(N, R, T, seed=0)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    g, node_id, src_in, edge_type, node_norm, data, labels = ref_rgcn.generate_sampled_graph_and_labels(
+        trip, GB, 0.5, R, None, None, 10, "uniform")
+    node_id_t = torch.from_numpy(node_id).view(-1, 1).long()
+    src_in_t, edge_type_t = torch.from_numpy(src_in), torch.from_numpy(edge_type)
+    g.ndata['norm'] = torch.from_numpy(node_norm).view(-1, 1)                      # node_norm_to_edge_norm :30-36
+    g.apply_edges(lambda edges: {'norm': edges.dst['norm'] * edges.src['norm']})
+    data_t, labels_t = torch.from_numpy(data), torch.from_numpy(labels)
+    model = ref_search_lp.Network('cpu', N, R, 2, 1, 2, 2, D, D0, 2 * R + 1, 40, 0.0, 0.0)
+    model.apply(weights_init)
+    model.train()
+    state0 = _sd(model)
+    alphas0 = [a.detach().clone() for a in model.arch_parameters()]
+    t0 = time.time()
+    ent_embed, rel_embed = model(g, node_id_t, src_in_t, edge_type_t)
+    loss = model.get_loss(g, ent_embed, rel_embed, data_t, labels_t)
+    loss.backward()
+    print("config_c3: real reference supernet fwd+bwd %.1f s, loss %.8f, %d nodes, %d edges, %d samples" %
+          (time.time() - t0, loss.item(), len(node_id), len(src_in), len(data)))
+    _, dst, _ = g.edges(form='all')
+    import copy
+    model64 = copy.deepcopy(model)
+    model64.load_state_dict(state0)
+    model64 = model64.double().train()
+    model64.zero_grad()
+    for a, a0 in zip(model64.arch_parameters(), alphas0):
+        a.data.copy_(a0)
+        a.grad = None
+    g.edata['norm'] = g.edata['norm'].double()
+    # MixedOp casts every candidate output with .float() (cell_lp.py:30): make that a no-op for the fp64 run only
+    _float = torch.Tensor.float
+    torch.Tensor.float = lambda self, *a, **k: self
+    try:
+        e64, r64 = model64(g, node_id_t, src_in_t, edge_type_t)
+        loss64 = model64.get_loss(g, e64, r64, data_t, labels_t.double())
+        loss64.backward()
+    finally:
+        torch.Tensor.float = _float
+    g.edata['norm'] = g.edata['norm'].float()
+    print("config_c3: fp64 truth loss %.10f" % loss64.item())
+    out = {"dims": {"N": N, "R": R, "T": T, "D": D, "D0": D0, "graph_batch_size": GB, "negative_sample": 10},
+           "truth64": {"loss": loss64.detach().clone(), "ent_embed": summarize("ent_embed", e64),
+                       "grads": _summ_all("grad.", _grads(model64)),
+                       "dalphas": [a.grad.clone() if a.grad is not None else None for a in model64.arch_parameters()]},
+           "inputs": {"triples": checksum(trip), "node_id": checksum(node_id), "src": checksum(src_in),
+                      "dst": checksum(dst.numpy()), "etype": checksum(edge_type), "samples": checksum(data),
+                      "norm": summarize("norm", g.edata['norm'])},
+           "loss": loss.detach().clone(), "ent_embed": summarize("ent_embed", ent_embed),
+           "rel_embed": summarize("rel_embed", rel_embed), "grads": _summ_all("grad.", _grads(model)),
+           "dalphas": [a.grad.clone() if a.grad is not None else None for a in model.arch_parameters()],
+           "genotypes": str(model.show_genotypes()),
+           "buffers": {k: v.clone() for k, v in _sd(model).items() if "running" in k or "num_batches" in k}}
+    torch.save(out, os.path.join(OUT, "config_c3.pt"))
+
+
+def gen_config_c2():
+    """configs[1]/C2: NC derived network (default genotype, op_norm) on the AIFB-shaped graph: 8,285 nodes, 90 edge
+    types, 58,086 directed edges, 4 classes, D=64, init 16, num_base_r=50, 2 layers, one 64-seed mini-batch of
+    2-layer full-neighbour blocks (mr_nc_train.py:42-72, models/model.py:152-199)."""
+    import time
+    import models.model as ref_model_nc
+    from collections import namedtuple
+    from oracle.mrg_oracle import synth_nc_graph
+    from oracle.summary import checksum, summarize
+    G2 = namedtuple('Genotype', 'alpha_cell concat_node score_func', defaults=(None,))
+    N, ET, E, D, D0, C, NB, B = 8285, 90, 58086, 64, 16, 4, 50, 64
+    gr = synth_nc_graph(N, ET, E, C, 176, seed=0)
+    src, dst, etype = gr["src"], gr["dst"], gr["etype"]
+    seeds = np.sort(gr["labelled"][:B])
+    blocks = _nc_blocks(src, dst, etype, seeds, 2)
+    trip_index = torch.from_numpy(np.stack([np.arange(E), src, dst], 1)).long()
+    labels = torch.from_numpy(gr["labels"][seeds]).long()
+    torch.manual_seed(0)
+    args = types.SimpleNamespace(feature_dim=D, op_norm=True)
+    model = ref_model_nc.Network('cpu', eval(NC_GENOTYPE, {"Genotype": G2}), N, C, ET, 2, 1, 2, D, D0, NB,
+                                 nn.CrossEntropyLoss(), args)
+    model.apply(weights_init)
+    model.train()
+    state0 = _sd(model)
+    t0 = time.time()
+    logits = model(trip_index, [b for (b, _, _, _) in blocks])
+    loss = nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    print("config_c2: real reference NC fwd+bwd %.1f s, loss %.8f, block edges %s" %
+          (time.time() - t0, loss.item(), [len(e) for (_, e, _, _) in blocks]))
+    import copy
+    model64 = copy.deepcopy(model)
+    model64.load_state_dict(state0)
+    model64 = model64.double().train()
+    model64.zero_grad()
+    logits64 = model64(trip_index, [b for (b, _, _, _) in blocks])
+    loss64 = nn.CrossEntropyLoss()(logits64, labels)
+    loss64.backward()
+    out = {"dims": {"N": N, "ET": ET, "E": E, "D": D, "D0": D0, "C": C, "NB": NB, "B": B}, "genotype": NC_GENOTYPE,
+           "truth64": {"loss": loss64.detach().clone(), "logits": logits64.detach().clone(),
+                       "grads": _summ_all("grad.", _grads(model64))},
+           "inputs": {"src": checksum(src), "dst": checksum(dst), "etype": checksum(etype), "seeds": torch.from_numpy(seeds),
+                      "block_eids": [checksum(e) for (_, e, _, _) in blocks]},
+           "loss": loss.detach().clone(), "logits": logits.detach().clone(), "grads": _summ_all("grad.", _grads(model)),
+           "buffers": {k: v.clone() for k, v in _sd(model).items() if "running" in k or "num_batches" in k}}
+    torch.save(out, os.path.join(OUT, "config_c2.pt"))
+
+
 def gen_labels():
     """1-N training items and their dense smoothed label rows from the REAL process() (utils/process_data.py:4-31)
     and TrainDataset (utils/data_set.py:6-33): the fixture behind the host-side batch builders and the device-side
@@ -423,8 +612,11 @@ def gen_predict():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("predict", "labels"):
-        {"predict": gen_predict, "labels": gen_labels}[sys.argv[1]]()
+    single = {"predict": gen_predict, "labels": gen_labels, "config_c1": gen_config_c1, "config_c2": gen_config_c2,
+              "config_c3": gen_config_c3}
+    if len(sys.argv) > 1 and sys.argv[1] in single:
+        for name in sys.argv[1:]:
+            single[name]()
         sys.exit(0)
     os.makedirs(OUT, exist_ok=True)
     gen_ops_lp()
@@ -436,5 +628,8 @@ if __name__ == "__main__":
     gen_network_nc()
     gen_predict()
     gen_labels()
+    gen_config_c2()
+    gen_config_c3()
+    gen_config_c1()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -107,15 +107,12 @@ def test_search_lp_golden(golden_dir):
 
 
 # ------------------------------------------------------------------------------ NC operators
-@pytest.mark.parametrize("name", ['a_max', 'a_mean', 'a_sum', 'a_std', 'f_dense', 'f_sparse', 'f_dense_last',
-                                  'f_sparse_last'])
-@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("name,tc", [(n, True) for n in ['a_max', 'a_mean', 'a_sum', 'a_std', 'f_dense', 'f_sparse',
+                                                         'f_dense_last', 'f_sparse_last']] + [('a_max', False)])
 def test_nc_op_golden(golden_dir, name, tc):
     from mr_gnas_b200 import operations as ops
     from mr_gnas_b200 import operations_lp
     from mr_gnas_b200.graph import MRGraph
-    if not tc and name != 'a_max':
-        pytest.skip("tensor-core switch only affects a_max")
     G = _load(golden_dir, "ops_nc.pt")
     c = G["cases"][name]
     g = MRGraph.from_block(G["dst"], G["n_dst"], device=DEV)
