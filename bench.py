@@ -342,6 +342,9 @@ def main():
         probe = (float(loss_p), {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()
                                  if p.grad is not None},
                  (host_batches[0][0][:, 0].clone(), host_batches[0][0][:, 1].clone(), host_batches[0][1].clone()))
+        # a live loss tensor keeps its autograd graph -- and with it every parameter's AccumulateGrad node, which
+        # remembers the (legacy default) stream it was created on -- alive into the CUDA-graph capture below
+        del loss_p
         model.zero_grad(set_to_none=True)
         model.load_state_dict(state0)          # BatchNorm buffers back to the init
         model._dropout = args.dropout_cell

@@ -164,6 +164,8 @@ class AllGatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, part):
         ctx.part = part
+        if part.world == 1:
+            return x.clone()
         sizes = [h - l for l, h in part.bounds]
         pad = max(sizes)
         buf = x.new_zeros(pad, x.shape[1])
@@ -175,6 +177,8 @@ class AllGatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         part = ctx.part
+        if part.world == 1:
+            return g, None
         g = g.clone(memory_format=torch.contiguous_format)   # autograd may share `g` with another consumer
         all_reduce_(g, part.group)
         return g[part.lo:part.hi].contiguous(), None
@@ -189,7 +193,8 @@ class ShardedRowSelect(torch.autograd.Function):
         own = (idx >= part.lo) & (idx < part.hi)
         loc = (idx - part.lo).clamp(0, max(part.n_local - 1, 0))
         out = table[loc] * own.unsqueeze(1).to(table.dtype)
-        all_reduce_(out, part.group)
+        if part.world > 1:
+            all_reduce_(out, part.group)
         ctx.part, ctx.rows = part, table.shape[0]
         ctx.save_for_backward(own, loc)
         return out
@@ -197,8 +202,9 @@ class ShardedRowSelect(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         own, loc = ctx.saved_tensors
-        g = g.clone(memory_format=torch.contiguous_format)   # never all-reduce autograd's own buffer in place
-        all_reduce_(g, ctx.part.group)
+        if ctx.part.world > 1:
+            g = g.clone(memory_format=torch.contiguous_format)   # never all-reduce autograd's own buffer in place
+            all_reduce_(g, ctx.part.group)
         d = g.new_zeros(ctx.rows, g.shape[1])
         # static shapes (CUDA-graph capturable): rows of other ranks add exact zeros to a clamped index;
         # index_put_(accumulate) is sort-based on CUDA, hence deterministic
@@ -212,7 +218,8 @@ class AllReduceSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, part):
         y = x.clone()
-        all_reduce_(y, part.group)
+        if part.world > 1:
+            all_reduce_(y, part.group)
         return y
 
     @staticmethod

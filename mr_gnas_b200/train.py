@@ -64,7 +64,9 @@ class GraphedTrainStep:
         and buffers (BatchNorm running statistics, num_batches_tracked) and the optimiser state (moments, step
         counters) are restored afterwards, so training starts from exactly the state capture() was called in
         (`keep_warmup_updates=True` keeps them: then graph replay continues the eager steps bit-identically,
-        tests/test_gpu_network_lp.py::test_graphed_train_step_replays_the_eager_step)."""
+        tests/test_gpu_network_lp.py::test_graphed_train_step_replays_the_eager_step).
+        No loss tensor of an earlier eager step on the default stream may still be alive: its autograd graph pins
+        the parameters' AccumulateGrad nodes to the legacy stream, which cannot be used during capture."""
         import copy
         snap = None
         if not keep_warmup_updates:

@@ -368,6 +368,10 @@ def gen_network_nc():
 # BASELINE.json configuration shapes, run through the REAL reference; results stored as compact summaries
 # (oracle/summary.py) so the fixtures stay small.  Inputs are regenerated from seeds by the tests (checksums stored).
 # ------------------------------------------------------------------------------------------------------------
+def _buffers(module):
+    return {k: v.detach().clone() for k, v in module.state_dict().items() if "running" in k or "num_batches" in k}
+
+
 def _summ_all(prefix, named):
     from oracle.summary import summarize
     return {k: (summarize(prefix + k, v) if v is not None else None) for k, v in named.items()}
@@ -428,7 +432,7 @@ def gen_config_c1():
     print("config_c1: fp64 truth %.1f s, loss %.8f" % (time.time() - t0, loss64.item()))
     out = {"dims": {"N": N, "R": R, "T": T, "D": D, "B": B}, "genotype": README_GENOTYPE,
            "truth64": {"loss": loss64.detach().clone(), "logits": summarize("logits", model64.score_func.logits),
-                       "grads": _summ_all("grad.", _grads(model64))},
+                       "grads": _summ_all("grad.", _grads(model64)), "buffers": _buffers(model64)},
            "inputs": {"triples": checksum(trip), "subj": tr[:, 0].clone(), "rel": tr[:, 1].clone(),
                       "labels": summarize("labels", labels)},
            "loss": loss.detach().clone(), "pred": summarize("pred", pred), "logits": summarize("logits", logits),
@@ -492,7 +496,7 @@ def gen_config_c3():
     print("config_c3: fp64 truth loss %.10f" % loss64.item())
     out = {"dims": {"N": N, "R": R, "T": T, "D": D, "D0": D0, "graph_batch_size": GB, "negative_sample": 10},
            "truth64": {"loss": loss64.detach().clone(), "ent_embed": summarize("ent_embed", e64),
-                       "grads": _summ_all("grad.", _grads(model64)),
+                       "grads": _summ_all("grad.", _grads(model64)), "buffers": _buffers(model64),
                        "dalphas": [a.grad.clone() if a.grad is not None else None for a in model64.arch_parameters()]},
            "inputs": {"triples": checksum(trip), "node_id": checksum(node_id), "src": checksum(src_in),
                       "dst": checksum(dst.numpy()), "etype": checksum(edge_type), "samples": checksum(data),
@@ -545,7 +549,7 @@ def gen_config_c2():
     loss64.backward()
     out = {"dims": {"N": N, "ET": ET, "E": E, "D": D, "D0": D0, "C": C, "NB": NB, "B": B}, "genotype": NC_GENOTYPE,
            "truth64": {"loss": loss64.detach().clone(), "logits": logits64.detach().clone(),
-                       "grads": _summ_all("grad.", _grads(model64))},
+                       "grads": _summ_all("grad.", _grads(model64)), "buffers": _buffers(model64)},
            "inputs": {"src": checksum(src), "dst": checksum(dst), "etype": checksum(etype), "seeds": torch.from_numpy(seeds),
                       "block_eids": [checksum(e) for (_, e, _, _) in blocks]},
            "loss": loss.detach().clone(), "logits": logits.detach().clone(), "grads": _summ_all("grad.", _grads(model)),

@@ -59,3 +59,24 @@ def check(name, a, b, tol=RTOL, truth=None):
         e, n = rel_err(a, b), norm_err(a, b)
     assert e <= t and n <= t, f"{name}: max-norm rel err {e:.3e}, 2-norm rel err {n:.3e} > {t:.1e}"
     return e
+
+
+def grad_errors(named_a, named_b, negligible=1e-5):
+    """Per-tensor rel_err of gradient dict `named_a` (product) against `named_b` (reference), as a list of
+    (err, name).  A parameter whose TRUE gradient is exactly zero -- the bias of a Linear that feeds a BatchNorm
+    (linear_e.bias, concat.bias, the NC OpModule.linear.bias): a shift the normalisation removes -- holds only
+    rounding noise on both sides, ~1e-7 of the network's gradient scale, and has no relative error to speak of.
+    Such tensors (reference max <= `negligible` x the largest gradient max of the model) are required to be
+    negligible in the product too and are reported with err 0."""
+    top = max(float(b.detach().abs().max()) for b in named_b.values() if b is not None)
+    out = []
+    for k, b in named_b.items():
+        if b is None:
+            continue
+        a = named_a[k]
+        if float(b.detach().abs().max()) <= negligible * top:
+            assert float(a.detach().abs().max()) <= 10 * negligible * top, f"{k}: reference gradient is ~0, ours is not"
+            out.append((0.0, k))
+        else:
+            out.append((rel_err(a, b), k))
+    return out

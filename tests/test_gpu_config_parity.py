@@ -25,11 +25,7 @@ DEV = "cuda:0"
 Genotype = namedtuple("Genotype", "alpha_cell concat_node score_func", defaults=(None,))
 
 
-def _report(tag, rep):
-    rep = [r for r in rep if r[1] < 1.0]        # (skip tensors whose true value is 0: bias before a BatchNorm)
-    worst = max(rep)
-    print(f"{tag}: worst sampled err vs fp64 truth: ours %.2e, real reference's own %.2e (2-norm %.2e / %.2e) at %s"
-          % worst)
+from config_cases import assert_report as _report  # noqa: E402
 
 
 def test_c1_full_train_step_vs_real_reference_and_oracle(golden_dir):
@@ -58,7 +54,9 @@ def test_c1_full_train_step_vs_real_reference_and_oracle(golden_dir):
     # BatchNorm running statistics after one training forward (reference buffers, fp32)
     for k, v in model.state_dict().items():
         if "running" in k:
-            assert rel_err(v, G["buffers"][k]) <= 1e-5, k
+            t64 = T64["buffers"][k]
+            bar = max(1e-5, 4 * rel_err(G["buffers"][k], t64))
+            assert rel_err(v, t64) <= bar, (k, rel_err(v, t64), bar)
         if "num_batches" in k:
             assert int(v) == int(G["buffers"][k]), k
     grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
@@ -166,7 +164,9 @@ def test_c3_supernet_step_vs_real_reference(golden_dir):
         assert rel_err(a.grad.cpu(), r64.float()) <= bar, (rel_err(a.grad.cpu(), r64.float()), bar)
     for k, v in model.state_dict().items():
         if "running" in k:
-            assert rel_err(v, G["buffers"][k]) <= 1e-5, k
+            t64 = T64["buffers"][k]
+            bar = max(1e-5, 4 * rel_err(G["buffers"][k], t64))
+            assert rel_err(v, t64) <= bar, (k, rel_err(v, t64), bar)
 
 
 def test_c2_nc_block_step_vs_real_reference(golden_dir):
@@ -207,17 +207,26 @@ def test_c2_nc_block_step_vs_real_reference(golden_dir):
     _report("C2 vs real reference", rep)
     for k, v in model.state_dict().items():
         if "running" in k:
-            assert rel_err(v, G["buffers"][k]) <= 1e-5, k
+            t64 = T64["buffers"][k]
+            bar = max(1e-5, 4 * rel_err(G["buffers"][k], t64))
+            assert rel_err(v, t64) <= bar, (k, rel_err(v, t64), bar)
 
 
 def test_loss_and_mrr_curves_follow_the_oracle_on_eighth_scale_c1():
     """North-star target "matching loss / MRR curves": 60 Adam steps (lr 1e-3, a new 256-query batch per step) of the
-    README genotype on the 1/8-scale C1 graph (N=14,541 R=237 D=200, first 34,014 train triples), CUDA path vs the
-    CPU oracle from the same seeded init; then the filtered MRR / Hits@10 of BOTH final models on 1,024 held-out
-    triples in eval mode (running statistics), CUDA through evaluate.predict (mrg_filtered_rank), oracle through
-    its sort-free restatement of predict().  reference: train/mr_lp_train.py:222-246, 269-314.
-    Trajectories of two fp32 implementations separate slowly (rounding differences are amplified by training and by
-    the saturation jumps of BCELoss, see test_c1_*): the bars below are on the curve, not per-tensor."""
+    README genotype on the 1/8-scale C1 graph (N=14,541 R=237 D=200, first 34,014 train triples) from the same seeded
+    init, three ways: the CUDA path, the fp32 CPU oracle, and the oracle in float64 (with the reference's fp32
+    sigmoid + BCELoss head, as in make_golden's truth runs).  Then the filtered MRR / MR / Hits@10 of each final
+    model in eval mode (running statistics) on 1,024 training queries and 1,024 held-out ones -- CUDA through
+    evaluate.predict (mrg_filtered_rank), oracle through its restatement of predict().
+    reference: train/mr_lp_train.py:222-246, 269-314.
+
+    Adam turns every rounding difference into an O(lr) parameter difference within a few steps (sign(g) updates on
+    small gradients) and BCELoss is discontinuous where sigmoid saturates, so ANY two floating-point evaluations of
+    this training run separate: the fp32 and fp64 CPU curves themselves do.  The bar is therefore relative to that
+    separation: at every step the running-max distance between the CUDA curve and the fp32 oracle curve may be at
+    most 8 x the running-max distance between the oracle's own fp32 and fp64 curves."""
+    import torch.nn.functional as F
     from mr_gnas_b200.evaluate import predict
     from mr_gnas_b200.graph import MRGraph
     from mr_gnas_b200.model_lp import Network
@@ -234,10 +243,13 @@ def test_loss_and_mrr_curves_follow_the_oracle_on_eighth_scale_c1():
     rng = np.random.RandomState(7)
     batches = [make_batch([items[j] for j in rng.choice(len(items), B, replace=False)], N, lbl_smooth=0.1)
                for _ in range(STEPS)]
+    ev_sets = {"train": data['train_tail'][:512] + data['train_head'][:512],
+               "valid": data['valid_tail'] + data['valid_head']}
+    ev_batches = {k: [make_batch(v[i:i + 256], N) for i in range(0, len(v), 256)] for k, v in ev_sets.items()}
     torch.manual_seed(0)
     model = Network('cpu', genos, N, R, D, D, 2 * R + 1, nn.BCELoss(), 0.0, lp_args(D))
     model.apply(weights_init)
-    P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     # ---- CUDA path
     model = model.to(DEV).train()
     g = MRGraph.from_triples(N, trip, R, device=DEV)
@@ -249,35 +261,57 @@ def test_loss_and_mrr_curves_follow_the_oracle_on_eighth_scale_c1():
         l.backward()
         opt.step()
         loss_g.append(float(l))
-    ev = data['valid_tail'] + data['valid_head']
-    ev_batches = [make_batch(ev[i:i + 256], N) for i in range(0, len(ev), 256)]
-    res_g, _ = predict(ev_batches, g, model, DEV)
-    # ---- oracle
+        del l
+    res_g = {k: predict(v, g, model, DEV)[0] for k, v in ev_batches.items()}
+    # ---- oracle, fp32 and fp64
     graph = O.build_graph(N, trip, R)
-    opt_o = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=1e-3)
-    loss_o = []
-    O.TRACK_RUNNING_STATS = True
-    try:
-        for t, y in batches:
-            opt_o.zero_grad()
-            l = O.bce_loss(O.network_lp(genos, P, graph, t[:, 0], t[:, 1], R, training=True), y)
-            l.backward()
-            opt_o.step()
-            loss_o.append(float(l))
-    finally:
-        O.TRACK_RUNNING_STATS = False
-    with torch.no_grad():
-        res_o, _ = O.predict_results([(O.network_lp(genos, P, graph, t[:, 0], t[:, 1], R, training=False), t, y)
-                                      for t, y in ev_batches])
-    rel = [abs(a - b) / abs(b) for a, b in zip(loss_g, loss_o)]
-    for k in range(0, STEPS, 6):
-        print(f"step {k:3d}: loss ours {loss_g[k]:.6f} oracle {loss_o[k]:.6f} rel diff {rel[k]:.2e}")
-    cnt = res_o['count']
-    mrr_g, mrr_o = res_g['mrr'] / cnt, res_o['mrr'] / cnt
-    print(f"after {STEPS} steps: filtered MRR ours {mrr_g:.6f} oracle {mrr_o:.6f}; MR {res_g['mr'] / cnt:.2f} / "
-          f"{res_o['mr'] / cnt:.2f}; hits@10 {res_g['hits@10'] / cnt:.4f} / {res_o['hits@10'] / cnt:.4f}")
-    assert loss_g[-1] < 0.5 * loss_g[0], "the loss must fall"
-    assert max(rel[:10]) <= 5e-3 and max(rel) <= 5e-2, (max(rel[:10]), max(rel))
-    assert res_g['count'] == cnt
-    assert abs(mrr_g - mrr_o) <= 0.05 * mrr_o + 1e-4
-    assert abs(res_g['mr'] - res_o['mr']) <= 0.05 * res_o['mr']
+
+    def oracle_run(dtype):
+        P = {k: (v.clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in state0.items()}
+        for v in P.values():
+            if v.is_floating_point():
+                v.requires_grad_(True)
+        opt_o = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=1e-3)
+
+        def probs(t, training):
+            _, ent, rel_embed = O.network_lp(genos, P, graph, t[:, 0], t[:, 1], R, training=training, return_emb=True)
+            z = torch.mm(ent[t[:, 0]] * rel_embed[t[:, 1]], ent.t())
+            return torch.sigmoid(z.float())                  # the reference's fp32 scoring head
+        losses = []
+        O.TRACK_RUNNING_STATS = True
+        try:
+            for t, y in batches:
+                opt_o.zero_grad()
+                l = F.binary_cross_entropy(probs(t, True), y)
+                l.backward()
+                opt_o.step()
+                losses.append(float(l))
+        finally:
+            O.TRACK_RUNNING_STATS = False
+        with torch.no_grad():
+            res = {k: O.predict_results([(probs(t, False), t, y) for t, y in v])[0] for k, v in ev_batches.items()}
+        return losses, res
+
+    loss_o, res_o = oracle_run(torch.float32)
+    loss_t, res_t = oracle_run(torch.float64)
+    d_gpu = np.maximum.accumulate([abs(a - b) / abs(b) for a, b in zip(loss_g, loss_o)])
+    d_ref = np.maximum.accumulate([abs(a - b) / abs(b) for a, b in zip(loss_o, loss_t)])
+    for k in list(range(0, STEPS, 6)) + [STEPS - 1]:
+        print(f"step {k:3d}: loss ours {loss_g[k]:.6f} oracle fp32 {loss_o[k]:.6f} fp64 {loss_t[k]:.6f} | running-max rel "
+              f"distance ours-oracle {d_gpu[k]:.2e}, oracle fp32-fp64 {d_ref[k]:.2e}")
+    assert loss_g[-1] < 0.05 * loss_g[0], "the loss must fall"
+    assert abs(loss_g[0] - loss_o[0]) <= 1e-4 * loss_o[0]            # step 0: before any chaos (saturation jumps only)
+    ratio = max(dg / max(dr, 1e-6) for dg, dr in zip(d_gpu, d_ref))
+    print(f"largest ratio of the two running-max distances over the {STEPS} steps: {ratio:.2f}")
+    assert ratio <= 8.0
+    for name in ev_sets:
+        cnt = res_o[name]['count']
+        assert res_g[name]['count'] == cnt
+        row = {m: (res_g[name][m] / cnt, res_o[name][m] / cnt, res_t[name][m] / cnt) for m in ('mrr', 'mr', 'hits@10')}
+        print(f"after {STEPS} steps, {name} queries (ours / oracle fp32 / oracle fp64): " +
+              "; ".join(f"{m} {a:.5f} / {b:.5f} / {c:.5f}" for m, (a, b, c) in row.items()))
+        # after 60 steps the model ranks barely better than chance (MRR ~3e-4 = a handful of lucky queries): the
+        # mean rank is the stable statistic (2 %), MRR / Hits are held to 8 x the oracle's own fp32-fp64 gap or 25 %
+        for m, (a, b, c) in row.items():
+            rel_bar = 0.02 if m == 'mr' else 0.25
+            assert abs(a - b) <= max(8.0 * abs(b - c), rel_bar * abs(b)) + 1e-6, (name, m, a, b, c)

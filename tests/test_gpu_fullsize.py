@@ -26,7 +26,7 @@ README = [Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f_s
 REL = 1e-5
 
 
-from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
+from parity import grad_errors, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 @pytest.fixture(scope="module")
@@ -164,7 +164,7 @@ def test_c1_fused_cell_equals_modular_path_and_is_deterministic(c1):
     for k, gk in runs["fused"][1].items():
         assert torch.equal(gk, runs["fused2"][1][k]), f"{k}: two runs differ (non-deterministic reduction?)"
     assert _err(runs["fused"][0], runs["modular"][0]) <= REL
-    worst = max((_err(gk, runs["modular"][1][k]), k) for k, gk in runs["fused"][1].items())
+    worst = max(grad_errors(runs["fused"][1], runs["modular"][1]))
     assert worst[0] <= 2e-5, worst
 
 

@@ -18,7 +18,7 @@ README = ("[Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f
           "concat_node=[4, 5, 6, 7], score_func='sf_DisMult')]")
 
 
-from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
+from parity import grad_errors, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _args(D):
@@ -55,7 +55,7 @@ def test_network_lp_golden(golden_dir, fused):
     loss = model.criterion(pred, labels)
     assert _err(loss, G["loss"]) <= 1e-5
     loss.backward()
-    worst = max((_err(p.grad, G["grads"][k]), k) for k, p in model.named_parameters() if G["grads"][k] is not None)
+    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, G["grads"]))
     # gradients of a 7-op cell with 9 BatchNorms, fp32 end to end: scale-relative 1e-5 on every tensor
     assert worst[0] <= 1e-5, worst
     # running statistics after one training forward
@@ -68,7 +68,7 @@ def test_network_lp_golden(golden_dir, fused):
     l2 = model._loss(g, subj, rel, labels)
     assert _err(l2, G["loss"]) <= 1e-5
     l2.backward()
-    worst = max((_err(p.grad, G["grads"][k]), k) for k, p in model.named_parameters() if G["grads"][k] is not None)
+    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, G["grads"]))
     assert worst[0] <= 1e-5, worst
     # short Adam loss curve (4 steps) against the reference's
     model.load_state_dict(G["state0"])

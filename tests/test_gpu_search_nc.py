@@ -19,7 +19,7 @@ def _load(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name), weights_only=False)
 
 
-from parity import rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
+from parity import grad_errors, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _check(name, a, b, tol=REL):
@@ -99,7 +99,7 @@ def test_search_lp_golden(golden_dir):
                        G["labels"].to(DEV))
     _check("loss", loss.view(1), G["loss"].view(1))
     loss.backward()
-    worst = max((_err(p.grad, G["grads"][k]), k) for k, p in model.named_parameters() if G["grads"][k] is not None)
+    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, G["grads"]))
     assert worst[0] <= REL, worst
     for a, ref in zip(alphas, G["dalphas"]):
         if ref is not None:
@@ -168,7 +168,7 @@ def test_network_nc_golden(golden_dir, op_norm):
     loss = nn.CrossEntropyLoss()(logits, G["labels"].to(DEV))
     _check("loss", loss.view(1), ref["loss"].view(1))
     loss.backward()
-    worst = max((_err(p.grad, ref["grads"][k]), k) for k, p in model.named_parameters() if ref["grads"][k] is not None)
+    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, ref["grads"]))
     assert worst[0] <= REL, worst
 
 
@@ -195,7 +195,7 @@ def test_search_nc_golden(golden_dir):
     _check("logits", logits, ref["logits"])
     loss = nn.CrossEntropyLoss()(logits, G["labels"].to(DEV))
     loss.backward()
-    worst = max((_err(p.grad, ref["grads"][k]), k) for k, p in model.named_parameters() if ref["grads"][k] is not None)
+    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, ref["grads"]))
     assert worst[0] <= REL, worst
     for a, r in zip(alphas, ref["dalphas"]):
         _check("dalpha", a.grad, r)
