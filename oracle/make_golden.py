@@ -241,7 +241,11 @@ def gen_search_lp():
     alphas0 = [a.detach().clone() for a in model.arch_parameters()]
     loss = model._loss(g, node_id, src_in, edge_type, samples, labels)
     loss.backward()
-    torch.save({"num_ent": N, "num_rels": R, "D": D, "D0": D0, "src": src_in, "dst": torch.from_numpy(dst).long(),
+    g.edata['norm'] = g.edata['norm'].double()
+    grads64, dalphas64, loss64 = _truth64(model, state0, lambda m: m._loss(g, node_id, src_in, edge_type, samples,
+                                                                            labels.double()), alphas0)
+    g.edata['norm'] = g.edata['norm'].float()
+    torch.save({"grads64": grads64, "dalphas64": dalphas64, "loss64": loss64, "num_ent": N, "num_rels": R, "D": D, "D0": D0, "src": src_in, "dst": torch.from_numpy(dst).long(),
                 "etype": edge_type, "norm": g.edata['norm'].clone(), "node_id": node_id, "samples": samples,
                 "labels": labels, "state0": state0, "alphas0": alphas0, "loss": loss.detach(),
                 "grads": _grads(model),
@@ -286,7 +290,21 @@ def gen_compgcn():
         n_out, r_out = layer(g0, h, r)
         c1, c2 = torch.randn_like(n_out), torch.randn_like(r_out)
         (n_out * c1).sum().add((r_out * c2).sum()).backward()
-        cases[comp] = {"h": h.detach().clone(), "r": r.detach().clone(), "state": _sd(layer), "n_out": n_out.detach(),
+        import copy
+        l64 = copy.deepcopy(layer).double().train()
+        l64.zero_grad()
+        h64, r64 = h.detach().double().requires_grad_(True), r.detach().double().requires_grad_(True)
+        g0.edata['norm'] = g0.edata['norm'].double()
+        torch.set_default_dtype(torch.float64)      # compgcn.py:79 allocates with the default dtype
+        try:
+            n64, ro64 = l64(g0, h64, r64)
+            (n64 * c1.double()).sum().add((ro64 * c2.double()).sum()).backward()
+        finally:
+            torch.set_default_dtype(torch.float32)
+        g0.edata['norm'] = g0.edata['norm'].float()
+        truth = {"dh": h64.grad.clone(), "dr": r64.grad.clone(), "dparams": _grads(l64)}
+        cases[comp] = {"truth64": truth,
+                       "h": h.detach().clone(), "r": r.detach().clone(), "state": _sd(layer), "n_out": n_out.detach(),
                        "r_out": r_out.detach(), "c1": c1, "c2": c2, "dh": h.grad.clone(), "dr": r.grad.clone(),
                        "dparams": _grads(layer)}
     torch.save({"graph": gd, "Din": Din, "Dout": Dout, "cases": cases}, os.path.join(OUT, "compgcn.pt"))
@@ -346,8 +364,11 @@ def gen_network_nc():
         logits = model(trip_index, [b for (b, _, _, _) in blocks])
         loss = nn.CrossEntropyLoss()(logits, labels)
         loss.backward()
+        g64, _, l64 = _truth64(model, state0, lambda m: nn.CrossEntropyLoss()(
+            m(trip_index, [b for (b, _, _, _) in blocks]), labels))
         out["derived_norm%d" % int(op_norm)] = {"state0": state0, "logits": logits.detach(), "loss": loss.detach(),
-                                                 "grads": _grads(model), "state_keys": list(state0.keys())}
+                                                 "grads": _grads(model), "state_keys": list(state0.keys()),
+                                                 "grads64": g64, "loss64": l64}
     torch.manual_seed(9)
     sm = ref_search_nc.Network('cpu', N, C, ET, 2, 1, 2, D, D0, NB, 0.0)
     sm.apply(weights_init)
@@ -358,7 +379,10 @@ def gen_network_nc():
     loss = nn.CrossEntropyLoss()(logits, labels)
     loss.backward()
     import configs.genotypes as cg
-    out["search"] = {"state0": state0, "alphas0": alphas0, "logits": logits.detach(), "loss": loss.detach(),
+    g64, da64, l64 = _truth64(sm, state0, lambda m: nn.CrossEntropyLoss()(
+        m(trip_index, [b for (b, _, _, _) in blocks]), labels), alphas0)
+    out["search"] = {"grads64": g64, "dalphas64": da64, "loss64": l64,
+                     "state0": state0, "alphas0": alphas0, "logits": logits.detach(), "loss": loss.detach(),
                      "grads": _grads(sm), "dalphas": [a.grad.clone() for a in sm.arch_parameters()],
                      "genotypes": str(sm.show_genotypes()), "state_keys": list(state0.keys())}
     torch.save(out, os.path.join(OUT, "network_nc.pt"))
@@ -368,6 +392,37 @@ def gen_network_nc():
 # BASELINE.json configuration shapes, run through the REAL reference; results stored as compact summaries
 # (oracle/summary.py) so the fixtures stay small.  Inputs are regenerated from seeds by the tests (checksums stored).
 # ------------------------------------------------------------------------------------------------------------
+class _no_float_cast:
+    """MixedOp casts every candidate output with .float() (cell_lp.py:30, cell.py:28): a no-op inside fp64 truth runs."""
+
+    def __enter__(self):
+        self._f = torch.Tensor.float
+        torch.Tensor.float = lambda t, *a, **k: t
+
+    def __exit__(self, *exc):
+        torch.Tensor.float = self._f
+        return False
+
+
+def _truth64(model, state0, run, alphas0=None):
+    """Gradients of the SAME reference modules evaluated in float64 from `state0`: run(model64) -> loss.
+    -> (grads64, dalphas64 or None).  Consumes no random numbers."""
+    import copy
+    m = copy.deepcopy(model)
+    m.load_state_dict(state0)
+    m = m.double().train()
+    m.zero_grad()
+    if alphas0 is not None:
+        for a, a0 in zip(m.arch_parameters(), alphas0):
+            a.data.copy_(a0)
+            a.grad = None
+    with _no_float_cast():
+        loss = run(m)
+        loss.backward()
+    dal = [a.grad.clone() if a.grad is not None else None for a in m.arch_parameters()] if alphas0 is not None else None
+    return {k: (g.double() if g is not None else None) for k, g in _grads(m).items()}, dal, loss.detach().clone()
+
+
 def _buffers(module):
     return {k: v.detach().clone() for k, v in module.state_dict().items() if "running" in k or "num_batches" in k}
 

@@ -127,7 +127,8 @@ def assert_report(tag, rep, tol=1e-5, slack=4.0, max_fraction=0.10, hard=32.0):
     for r in sorted(bad, reverse=True):
         print("  beyond 4x   %-70s ours %.2e ref %.2e | 2-norm ours %.2e ref %.2e | absmax %.2e" %
               (r[4], r[0], r[1], r[2], r[3], r[6]))
-    way_off = [r for r in rep if r[0] > max(tol, hard * r[1]) or r[2] > max(tol, hard * r[3])]
+    floor = tol / slack
+    way_off = [r for r in rep if r[0] > hard * max(r[1], floor) or r[2] > hard * max(r[3], floor)]
     assert not way_off, f"{tag}: {[r[4] for r in way_off]} exceed max({tol}, {hard} x the reference's own fp32 error)"
     assert len(bad) <= max_fraction * len(rep), \
         f"{tag}: {len(bad)} of {len(rep)} tensors exceed max({tol}, {slack} x the reference's own fp32 error)"

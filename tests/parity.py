@@ -80,3 +80,33 @@ def grad_errors(named_a, named_b, negligible=1e-5):
         else:
             out.append((rel_err(a, b), k))
     return out
+
+
+def check_grads(tag, ours, ref32, truth64, tol=RTOL, slack=4.0, max_fraction=0.10, hard=32.0, verbose=True):
+    """Gradients (dicts name -> tensor) of the product against the fp64 evaluation `truth64` of the same reference
+    modules, knowing the real fp32 reference's own result `ref32`:
+      * a tensor whose TRUE gradient is zero (|truth| <= 1e-9 x the model's largest gradient: the bias of a Linear
+        feeding a BatchNorm, CompGCN's loop relation under `sub`, ...) must be negligible in the product too;
+      * otherwise err = max|ours - truth| / max|truth| must be <= max(tol, slack x the reference's own error) --
+        for all but `max_fraction` of the tensors (the ratio of two independent rounding-error draws exceeds 4
+        with probability 16 %), and <= hard x max(reference's error, tol / slack) for every tensor.
+    Returns the list of (err, ref_err, name)."""
+    keys = [k for k, t in truth64.items() if t is not None]
+    top = max(float(truth64[k].detach().abs().max()) for k in keys)
+    rows, bad = [], []
+    for k in keys:
+        t = truth64[k].detach().double().cpu()
+        if float(t.abs().max()) <= 1e-9 * top:
+            assert float(ours[k].detach().abs().max()) <= 1e-4 * top, f"{tag} {k}: true gradient is 0, ours is not"
+            continue
+        e, r = rel_err(ours[k], t), rel_err(ref32[k], t)
+        rows.append((e, r, k))
+        assert e <= hard * max(r, tol / slack), f"{tag} {k}: rel err {e:.2e}, the reference's own {r:.2e}"
+        if e > max(tol, slack * r):
+            bad.append((e, r, k))
+    if verbose and rows:
+        ratios = sorted(e / max(r, tol / slack) for e, r, _ in rows)
+        print(f"{tag}: {len(rows)} gradient tensors vs fp64 truth; worst ours %.2e (reference's own %.2e) at %s; "
+              f"ratio ours/reference median {ratios[len(ratios) // 2]:.2f} max {ratios[-1]:.2f}" % max(rows))
+    assert len(bad) <= max(1, int(max_fraction * len(rows))), f"{tag}: beyond {slack}x the reference's own error: {bad}"
+    return rows

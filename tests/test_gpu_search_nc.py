@@ -19,7 +19,7 @@ def _load(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name), weights_only=False)
 
 
-from parity import grad_errors, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
+from parity import check_grads, grad_errors, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _check(name, a, b, tol=REL):
@@ -99,11 +99,9 @@ def test_search_lp_golden(golden_dir):
                        G["labels"].to(DEV))
     _check("loss", loss.view(1), G["loss"].view(1))
     loss.backward()
-    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, G["grads"]))
-    assert worst[0] <= REL, worst
-    for a, ref in zip(alphas, G["dalphas"]):
-        if ref is not None:
-            _check("dalpha", a.grad, ref)
+    check_grads("search_lp", {k: p.grad for k, p in model.named_parameters()}, G["grads"], G["grads64"])
+    check_grads("search_lp dalpha", {i: a.grad for i, a in enumerate(alphas)},
+                {i: r for i, r in enumerate(G["dalphas"])}, {i: r for i, r in enumerate(G["dalphas64"])})
 
 
 # ------------------------------------------------------------------------------ NC operators
@@ -168,8 +166,7 @@ def test_network_nc_golden(golden_dir, op_norm):
     loss = nn.CrossEntropyLoss()(logits, G["labels"].to(DEV))
     _check("loss", loss.view(1), ref["loss"].view(1))
     loss.backward()
-    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, ref["grads"]))
-    assert worst[0] <= REL, worst
+    check_grads("network_nc", {k: p.grad for k, p in model.named_parameters()}, ref["grads"], ref["grads64"])
 
 
 def test_search_nc_golden(golden_dir):
@@ -195,10 +192,9 @@ def test_search_nc_golden(golden_dir):
     _check("logits", logits, ref["logits"])
     loss = nn.CrossEntropyLoss()(logits, G["labels"].to(DEV))
     loss.backward()
-    worst = max(grad_errors({k: p.grad for k, p in model.named_parameters()}, ref["grads"]))
-    assert worst[0] <= REL, worst
-    for a, r in zip(alphas, ref["dalphas"]):
-        _check("dalpha", a.grad, r)
+    check_grads("search_nc", {k: p.grad for k, p in model.named_parameters()}, ref["grads"], ref["grads64"])
+    check_grads("search_nc dalpha", {i: a.grad for i, a in enumerate(alphas)},
+                {i: r for i, r in enumerate(ref["dalphas"])}, {i: r for i, r in enumerate(ref["dalphas64"])})
 
 
 # ------------------------------------------------------------------------------ CompGraphConv (K10)
@@ -221,8 +217,11 @@ def test_compgcn_golden(golden_dir, comp):
     _check("n_out", n_out, c["n_out"])
     _check("r_out", r_out, c["r_out"])
     ((n_out * c["c1"].to(DEV)).sum() + (r_out * c["c2"].to(DEV)).sum()).backward()
-    _check("dh", h.grad, c["dh"])
-    _check("dr", r.grad, c["dr"])
-    for k, p in layer.named_parameters():
-        if c["dparams"][k] is not None:
-            _check("d" + k, p.grad, c["dparams"][k])
+    # gradients against the fp64 run of the same reference layer (bar: max(1e-5, 4 x the fp32 reference's own
+    # error); exactly-zero true gradients -- loop_rel and W_S.bias under `sub`, any bias feeding the BatchNorm --
+    # must be negligible): tests/parity.py::check_grads
+    T = c["truth64"]
+    ours = {"dh": h.grad, "dr": r.grad, **{"d" + k: p.grad for k, p in layer.named_parameters()}}
+    ref32 = {"dh": c["dh"], "dr": c["dr"], **{"d" + k: v for k, v in c["dparams"].items()}}
+    truth = {"dh": T["dh"], "dr": T["dr"], **{"d" + k: v for k, v in T["dparams"].items()}}
+    check_grads("compgcn " + comp, ours, ref32, truth)
