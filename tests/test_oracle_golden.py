@@ -161,7 +161,7 @@ def test_oracle_matches_real_reference_at_full_c1_shape(golden_dir):
     both a_max argmax tables.  ~15 s, ~10 GB of host memory."""
     import torch
     import torch.nn as nn
-    from config_cases import c1_inputs, check_vs_truth, loss_bar, lp_args, load
+    from config_cases import assert_report, c1_inputs, check_vs_truth, loss_bar, lp_args, load
     from oracle import mrg_oracle as O
     from oracle.summary import errors, positions, sample
     from mr_gnas_b200.model_lp import Network
@@ -201,8 +201,7 @@ def test_oracle_matches_real_reference_at_full_c1_shape(golden_dir):
             assert P[k].grad is None
             continue
         check_vs_truth("grad." + k, P[k].grad, summ, T64["grads"][k], report=rep)
-    worst = max(rep)
-    print("worst sampled err vs fp64: oracle %.2e, reference's own %.2e (2-norm %.2e / %.2e) at %s" % worst)
+    assert_report("C1 oracle vs real reference", rep)
     for i, a in enumerate(args):
         got = a.reshape(-1)[positions(a.numel(), 1234 + i, 8192)]
         agree = float((got == G["arg_vals"][i]).float().mean())
