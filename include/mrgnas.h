@@ -281,12 +281,14 @@ int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t*
 /* K5 backward (sparse): gradients of a_max w.r.t. the E message-source rows (dX, edge-id order,
  * every row written once), the Linear weight (dW [D,D]) and bias (db [D]) from g = dL/d(out),
  * the encoded argmax and the (lazily activated) input rows.  Replaces the reference's two dense
- * [E,D]x[D,D] backward GEMMs with 2*N*D*D FMAs on the routed entries only.  dX / dW may be NULL. */
-size_t mrg_amax_bwd_workspace_bytes(int64_t N, int32_t D);
+ * [E,D]x[D,D] backward GEMMs with 2*N*D*D FMAs on the routed entries only.  dX / dW may be NULL.
+ * csr_dst[p] = destination of the edge at dst-CSR position p (= dst[csr_eid[p]], graph-static).  The call first
+ * turns `arg` into two bit tables over CSR positions (workspace), which both products then walk. */
+size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D);
 int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,
-                 const int32_t* csr_eid, const int32_t* chunk_first, const int32_t* chunk_seg, int64_t N, int64_t E,
-                 int64_t max_chunks, int32_t D, float* dX, float* dW, float* db, void* workspace,
-                 size_t workspace_bytes, void* stream);
+                 const int32_t* csr_eid, const int32_t* csr_dst, const int32_t* chunk_first,
+                 const int32_t* chunk_seg, int64_t N, int64_t E, int64_t max_chunks, int32_t D, float* dX, float* dW,
+                 float* db, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K8  DistMult 1-N scoring epilogue + BCE.  Replaces torch.sigmoid + nn.BCELoss

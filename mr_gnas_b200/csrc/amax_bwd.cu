@@ -11,27 +11,60 @@
 //
 // arg uses the encoded form of the forward kernels: >=0 edge id with a positive message,
 // <0 no gradient (isolated destination, or ReLU gated the maximum off).
-// Both kernels are deterministic: dX rows have one writer; dW is accumulated per CTA in shared
-// memory by a fixed warp<->row ownership and the per-CTA partials are folded in CTA order.
+//
+// Round 2: the routing is turned ONCE per call (amax_route_kernel) into two bit tables over the dst-CSR
+// positions p of the routed edges, so that neither product searches for its pairs any more:
+//   rmask[p][j]  (32-bit words, j = f / 32)      bit f % 32 set  <=>  feature f of dst(p) is routed to position p
+//   fmask[p / 64][f] (64-bit words)              bit p % 64 set  <=>  the same, indexed by (64-row window, feature)
+// dX walks rmask row by row (ascending f => fixed summation order); dW streams 64-row windows of x through
+// shared memory and each warp reads the 64-bit row sets of the features it owns.  Both are deterministic:
+// bitwise OR is order independent, dX rows have one writer, dW accumulators have one owner warp and the per-CTA
+// partials are folded in CTA order.
 #include "common.cuh"
 
 namespace mrg {
 
-constexpr int kBwdThreads = 1024;  // one CTA per SM (W / dW slice resident in smem) -> fill it with 32 warps
+constexpr int kBwdThreads = 1024;  // one CTA per SM (W resident in smem) -> fill it with 32 warps
 constexpr int kBwdWarps = kBwdThreads / 32;
+constexpr int kRW = 8;             // rmask words per position (D <= 256)
+constexpr int kWin = 64;           // rows per fmask window == rows per staged dW window
 
 // ---------------------------------------------------------------------------------------
-// dX: one warp per <=32-edge chunk of a destination's CSR row.  Lane l keeps g[n,f], arg[n,f]
-// for f = l + 32 j in registers; for every edge a ballot per 32-feature strip finds the features
-// routed to it and their W rows are accumulated from shared memory (W resident when it fits).
+// routing tables.  One thread per (destination, feature): dst-CSR position of edge arg[n,f] by binary search
+// (edge ids ascend inside a destination), then two atomic ORs.
+// ---------------------------------------------------------------------------------------
+__global__ void amax_route_kernel(const int32_t* __restrict__ arg, const int32_t* __restrict__ ptr,
+                                  const int32_t* __restrict__ eid, int64_t N, int D, uint32_t* __restrict__ rmask,
+                                  unsigned long long* __restrict__ fmask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  const int64_t n = i / D;
+  const int f = (int)(i - n * D);
+  const int32_t a = __ldg(arg + i);
+  if (a < 0) return;
+  int32_t l = __ldg(ptr + n), h = __ldg(ptr + n + 1);
+  const int32_t hi = h;
+  while (l < h) {
+    const int32_t mid = (l + h) >> 1;
+    if (__ldg(eid + mid) < a) l = mid + 1; else h = mid;
+  }
+  if (l >= hi || __ldg(eid + l) != a) return;
+  atomicOr(rmask + (size_t)l * kRW + (f >> 5), 1u << (f & 31));
+  atomicOr(fmask + (size_t)(l / kWin) * D + f, 1ull << (l % kWin));
+}
+
+// ---------------------------------------------------------------------------------------
+// dX: one warp per <=32-edge chunk of a destination's CSR row.  Lane l keeps g[n, l + 32 j] in registers and loads
+// word l of the position's rmask row; the set bits are walked in ascending feature order and the W rows are
+// accumulated from shared memory (W resident when it fits).  Rows without a routed feature are written as zeros.
 // ---------------------------------------------------------------------------------------
 template <int NJ, bool W_SMEM>
-__global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(  // NT4 = ceil(NJ / 4) float4 groups per lane
-    const float* __restrict__ g, const int32_t* __restrict__ arg, const float* __restrict__ W,
+__global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
+    const float* __restrict__ g, const uint32_t* __restrict__ rmask, const float* __restrict__ W,
     const int32_t* __restrict__ ptr, const int32_t* __restrict__ eid, const int32_t* __restrict__ chunk_first,
     const int32_t* __restrict__ chunk_seg, int64_t nseg, int D, float* __restrict__ dX) {
   extern __shared__ float smem_w[];  // [D][D] when W_SMEM
-  constexpr int NT4 = (NJ + 3) / 4;
+  constexpr int NT4 = (NJ + 3) / 4;   // float4 column groups per lane
   const int lane = threadIdx.x & 31;
   if (W_SMEM) {
     for (int i = threadIdx.x * 4; i < D * D; i += blockDim.x * 4)
@@ -39,6 +72,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(  // NT4 = 
     __syncthreads();
   }
   const float* Wp = W_SMEM ? smem_w : W;
+  const int D4 = D >> 2;
   const int64_t warp0 = (int64_t)blockIdx.x * kBwdWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kBwdWarps;
   const int64_t nchunks = chunk_first[nseg];
@@ -48,107 +82,93 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(  // NT4 = 
     const int32_t lo = p0 + (int32_t)(ch - chunk_first[n]) * MRG_CHUNK_ROWS;
     const int32_t hi = min(lo + MRG_CHUNK_ROWS, p1);
     float gr[NJ];
-    int32_t ar[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int f = lane + 32 * j;
       gr[j] = f < D ? __ldg(g + (size_t)n * D + f) : 0.f;
-      ar[j] = f < D ? __ldg(arg + (size_t)n * D + f) : -1;
     }
-    const int D4 = D >> 2;
-    int32_t e_next = __ldg(eid + lo);
+    // lane l owns position lo + l of the chunk: its edge id, and (lanes < kRW of the broadcast below) mask words
+    const int32_t my_e = lo + lane < hi ? __ldg(eid + lo + lane) : 0;
+    uint32_t w_next = lane < kRW ? __ldg(rmask + (size_t)lo * kRW + lane) : 0u;
     for (int32_t pz = lo; pz < hi; ++pz) {
-      const int32_t e = e_next;
-      if (pz + 1 < hi) e_next = __ldg(eid + pz + 1);
-      // lane owns the float4 column groups c4 = lane + 32 t: 128-bit shared-memory reads of W and 128-bit stores
+      const uint32_t w_cur = w_next;
+      if (pz + 1 < hi && lane < kRW) w_next = __ldg(rmask + (size_t)(pz + 1) * kRW + lane);
+      const int32_t e = __shfl_sync(0xffffffffu, my_e, pz - lo);
       float4 acc[NT4];
 #pragma unroll
       for (int t = 0; t < NT4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (__ballot_sync(0xffffffffu, w_cur != 0u)) {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        unsigned m = __ballot_sync(0xffffffffu, ar[j] == e);
-        while (m) {
-          const int src_lane = __ffs(m) - 1;
-          m &= m - 1;
-          const float gv = __shfl_sync(0xffffffffu, gr[j], src_lane);
-          const float* wrow = Wp + (size_t)(src_lane + 32 * j) * D;
+        for (int j = 0; j < NJ; ++j) {
+          uint32_t m = __shfl_sync(0xffffffffu, w_cur, j);
+          while (m) {
+            const int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            const float gv = __shfl_sync(0xffffffffu, gr[j], src_lane);
+            const float* wrow = Wp + (src_lane + 32 * j) * D + 4 * lane;
 #pragma unroll
-          for (int t = 0; t < NT4; ++t) {
-            const int c4 = lane + 32 * t;
-            if (c4 < D4) {
-              const float4 w = W_SMEM ? *reinterpret_cast<const float4*>(wrow + 4 * c4) : ldg4(wrow + 4 * c4);
-              acc[t].x = fmaf(gv, w.x, acc[t].x); acc[t].y = fmaf(gv, w.y, acc[t].y);
-              acc[t].z = fmaf(gv, w.z, acc[t].z); acc[t].w = fmaf(gv, w.w, acc[t].w);
+            for (int t = 0; t < NT4; ++t) {
+              if (lane + 32 * t < D4) {
+                const float4 w = W_SMEM ? *reinterpret_cast<const float4*>(wrow + 128 * t) : ldg4(wrow + 128 * t);
+                acc[t].x = fmaf(gv, w.x, acc[t].x); acc[t].y = fmaf(gv, w.y, acc[t].y);
+                acc[t].z = fmaf(gv, w.z, acc[t].z); acc[t].w = fmaf(gv, w.w, acc[t].w);
+              }
             }
           }
         }
       }
-      float* out = dX + (size_t)e * D;
+      float* out = dX + (size_t)e * D + 4 * lane;
 #pragma unroll
-      for (int t = 0; t < NT4; ++t) {
-        const int c4 = lane + 32 * t;
-        if (c4 < D4) st_stream4(out + 4 * c4, acc[t]);
-      }
+      for (int t = 0; t < NT4; ++t)
+        if (lane + 32 * t < D4) st_stream4(out + 128 * t, acc[t]);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // dW / db.  Every (destination, feature) pair routes g[n,f] to ONE edge row, so dW^T is a sum of
-// N*D rank-1 contributions g[n,f] * x(arg[n,f],:).  Gathering an 800-byte x row per pair would move
-// N*D*b bytes (5x the edge tensor at C1); instead each CTA owns a contiguous range of dst-CSR
-// positions, streams the x rows of that range ONCE into shared memory (cp.async, 3-stage ring of
-// kDwCap-row windows, lazy BatchNorm+ReLU applied in place when a window lands) and resolves every
-// pair against the staged window by a binary search of its edge id in the window's (ascending) edge
-// list.  Warp w owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS
-// (acc[u][t]: feature w*NF+u, column k0 + lane + 32 t): no shared-memory read-modify-write, no atomics,
-// a fixed accumulation order -> deterministic.  Destinations that straddle windows / CTAs are simply
-// seen by both; each pair is counted where its edge position falls.
+// N*D rank-1 contributions g[n,f] * x(arg[n,f],:).  Each CTA owns a contiguous range of 64-row windows of
+// dst-CSR positions, streams the x rows of that range ONCE into shared memory (cp.async, 3-stage ring; the
+// window's fmask row and destination ids ride along; lazy BatchNorm+ReLU applied in place when a window lands).
+// Warp w owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS (acc[u][t]: feature w*NF+u,
+// column k0 + lane + 32 t): lane u reads the 64-bit row set of its feature, the warp pops up to kPop rows per
+// feature into a small shared list, fetches their g values in one parallel round (one exposed L2 latency per
+// window instead of one per destination) and then accumulates feature by feature in ascending row order.
+// No shared-memory read-modify-write, no atomics, fixed order -> deterministic.
 // Partials: part[cta][D][KW] (+ db in part_b[group][D]), folded in CTA order.
 // ---------------------------------------------------------------------------------------
 constexpr int kDwThreads = 512;
 constexpr int kDwWarps = kDwThreads / 32;
-constexpr int kDwCap = 64;      // edge rows per staged window
 constexpr int kDwStages = 3;
+constexpr int kPop = 8;         // rows popped per feature and batch
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// pos[n,f] = dst-CSR position of edge arg[n,f] (edge ids ascend inside a destination), -1 when no gradient flows
-__global__ void amax_pos_kernel(const int32_t* __restrict__ arg, const int32_t* __restrict__ ptr,
-                                const int32_t* __restrict__ eid, int64_t N, int D, int32_t* __restrict__ pos) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * D) return;
-  const int64_t n = i / D;
-  const int32_t a = __ldg(arg + i);
-  int32_t r = -1;
-  if (a >= 0) {
-    int32_t l = __ldg(ptr + n), h = __ldg(ptr + n + 1);
-    const int32_t hi = h;
-    while (l < h) {
-      const int32_t mid = (l + h) >> 1;
-      if (__ldg(eid + mid) < a) l = mid + 1; else h = mid;
-    }
-    if (l < hi && __ldg(eid + l) == a) r = l;
-  }
-  pos[i] = r;
-}
-
 template <int NF, int NT>
 __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
-    const float* __restrict__ g, const int32_t* __restrict__ pos, mrg_act x, const int32_t* __restrict__ ptr,
-    const int32_t* __restrict__ eid, int64_t N, int64_t E, int D, int KW, int kslices, float* __restrict__ part,
-    float* __restrict__ part_b) {
-  extern __shared__ float smem[];
-  // layout: xs[kDwStages][kDwCap][KW] | pad[32] | sc[KW] | sh[KW]
-  float* xs = smem;
-  float* sc_s = xs + (size_t)kDwStages * kDwCap * KW + 32;
+    const float* __restrict__ g, const unsigned long long* __restrict__ fmask, mrg_act x,
+    const int32_t* __restrict__ eid, const int32_t* __restrict__ csr_dst, int64_t E, int D, int KW, int kslices,
+    float* __restrict__ part, float* __restrict__ part_b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | sc[KW] | sh[KW] |
+  //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32
+  float* xs = reinterpret_cast<float*>(smem_raw);
+  unsigned long long* fm = reinterpret_cast<unsigned long long*>(xs + (size_t)kDwStages * kWin * KW);
+  int32_t* wd = reinterpret_cast<int32_t*>(fm + (size_t)kDwStages * D);
+  float* sc_s = reinterpret_cast<float*>(wd + kDwStages * kWin);
   float* sh_s = sc_s + KW;
+  int32_t* lr = reinterpret_cast<int32_t*>(sh_s + KW);
+  float* lg = reinterpret_cast<float*>(lr + kDwWarps * NF * kPop);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x % kslices, group = blockIdx.x / kslices, ngroups = gridDim.x / kslices;
   const int k0 = slice * KW;
@@ -160,8 +180,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
       sc_s[c] = x.scale[k0 + c];
       sh_s[c] = x.shift[k0 + c];
     }
-  const int64_t P0 = E * group / ngroups, P1 = E * (group + 1) / ngroups;
-  const int nb = (int)((P1 - P0 + kDwCap - 1) / kDwCap);
+  const int64_t nwin = (E + kWin - 1) / kWin;
+  const int64_t W0 = nwin * group / ngroups, W1 = nwin * (group + 1) / ngroups;
+  const int nb = (int)(W1 - W0);
 
   float acc[NF][NT];
 #pragma unroll
@@ -169,19 +190,24 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[u][t] = 0.f;
   float db_acc = 0.f;
-  const int f_l = warp * NF + lane;                 // the feature whose (pos, g) this lane fetches
+  const int f_l = warp * NF + lane;                 // the feature whose row set this lane pops
   const bool f_ok = lane < NF && f_l < D;
-  const float* xs_lane = xs + lane;
+  int32_t* lr_w = lr + warp * NF * kPop;
+  float* lg_w = lg + warp * NF * kPop;
 
-  auto issue = [&](int b) {   // warp w copies rows w, w+16, ... of window b
-    const int64_t w_lo = P0 + (int64_t)b * kDwCap;
-    const int nrows = (int)min((int64_t)kDwCap, P1 - w_lo);
-    float* st = xs + (size_t)(b % kDwStages) * kDwCap * KW;
+  auto issue = [&](int b) {   // warp w copies rows w, w+16, ... of window b; the first warps also fmask / dst ids
+    const int64_t w_lo = (W0 + b) * kWin;
+    const int nrows = (int)min((int64_t)kWin, E - w_lo);
+    const int s = b % kDwStages;
+    float* st = xs + (size_t)s * kWin * KW;
     for (int r = warp; r < nrows; r += kDwWarps) {
       const int32_t e = __ldg(eid + w_lo + r);
       const float* src = x.data + (size_t)e * D + k0;
       for (int c4 = lane; c4 < kw4; c4 += 32) cp_async16(st + (size_t)r * KW + 4 * c4, src + 4 * c4);
     }
+    const unsigned long long* fsrc = fmask + (size_t)(W0 + b) * D;
+    for (int c = threadIdx.x; c < D / 2; c += kDwThreads) cp_async16(fm + (size_t)s * D + 2 * c, fsrc + 2 * c);
+    if (threadIdx.x < nrows) cp_async4(wd + s * kWin + threadIdx.x, csr_dst + w_lo + threadIdx.x);
   };
 
   if (nb > 0) issue(0);
@@ -189,36 +215,20 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
   if (nb > 1) issue(1);
   cp_async_commit();
 
-  // first destination whose CSR row reaches past P0: largest n with ptr[n] <= P0 (empty rows skipped below)
-  int64_t n_cur = 0;
-  {
-    int64_t lo = 0, hi = N;   // invariant: ptr[lo] <= P0, answer in [lo, hi)
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (__ldg(ptr + mid) <= P0) lo = mid; else hi = mid;
-    }
-    n_cur = lo;
-  }
-  // (pos, g) of destination n_pf, fetched one destination ahead of use
-  int64_t n_pf = n_cur;
-  int32_t p_pf = f_ok ? __ldg(pos + (size_t)n_pf * D + f_l) : -1;
-  float g_pf = f_ok ? __ldg(g + (size_t)n_pf * D + f_l) : 0.f;
-
   for (int b = 0; b < nb; ++b) {
     cp_async_wait<1>();
-    const int64_t w_lo = P0 + (int64_t)b * kDwCap;
-    const int64_t w_hi = min(w_lo + kDwCap, P1);
-    const int nrows = (int)(w_hi - w_lo);
-    const int stage_off = (b % kDwStages) * kDwCap * KW;
+    const int64_t w_lo = (W0 + b) * kWin;
+    const int nrows = (int)min((int64_t)kWin, E - w_lo);
+    const int s = b % kDwStages;
     if (affine || relu) {     // each thread post-processes exactly the 16-byte pieces it copied
-      float* st = xs + stage_off;
+      float* st = xs + (size_t)s * kWin * KW;
       for (int r = warp; r < nrows; r += kDwWarps)
         for (int c4 = lane; c4 < kw4; c4 += 32) {
           float4 v = *reinterpret_cast<float4*>(st + (size_t)r * KW + 4 * c4);
           if (affine) {
             const float4 a = *reinterpret_cast<const float4*>(sc_s + 4 * c4);
-            const float4 s = *reinterpret_cast<const float4*>(sh_s + 4 * c4);
-            v.x = fmaf(a.x, v.x, s.x); v.y = fmaf(a.y, v.y, s.y); v.z = fmaf(a.z, v.z, s.z); v.w = fmaf(a.w, v.w, s.w);
+            const float4 sh = *reinterpret_cast<const float4*>(sh_s + 4 * c4);
+            v.x = fmaf(a.x, v.x, sh.x); v.y = fmaf(a.y, v.y, sh.y); v.z = fmaf(a.z, v.z, sh.z); v.w = fmaf(a.w, v.w, sh.w);
           }
           if (relu) {
             v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
@@ -230,46 +240,47 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     __syncthreads();          // window b complete for everyone; everyone finished computing window b-1
     if (b + 2 < nb) issue(b + 2);
     cp_async_commit();
-    const float* st_lane = xs_lane + stage_off;
+    const float* st_lane = xs + (size_t)s * kWin * KW + lane;
+    const int32_t* wd_s = wd + s * kWin;
 
-    int64_t n = n_cur;
-    while (n < N) {
-      const int32_t p0 = __ldg(ptr + n), p1 = __ldg(ptr + n + 1);
-      if (p0 >= w_hi) break;
-      if (p1 > w_lo && p1 > p0) {
-        int32_t pp;
-        float gv;
-        if (n == n_pf) {
-          pp = p_pf; gv = g_pf;
-        } else {
-          pp = f_ok ? __ldg(pos + (size_t)n * D + f_l) : -1;
-          gv = f_ok ? __ldg(g + (size_t)n * D + f_l) : 0.f;
-        }
-        if (n + 1 < N && n_pf != n + 1) {   // next destination's routing, in flight while this one is processed
-          n_pf = n + 1;
-          p_pf = f_ok ? __ldg(pos + (size_t)(n + 1) * D + f_l) : -1;
-          g_pf = f_ok ? __ldg(g + (size_t)(n + 1) * D + f_l) : 0.f;
-        }
-        const int r = (pp >= w_lo && pp < w_hi) ? (int)(pp - w_lo) : -1;
-        if (r >= 0) db_acc += gv;
-        const unsigned mask = __ballot_sync(0xffffffffu, r >= 0);
-        if (mask) {
+    unsigned long long m = f_ok ? fm[(size_t)s * D + f_l] : 0ull;
+    while (__ballot_sync(0xffffffffu, m != 0ull)) {
+      // pop up to kPop rows of my feature (ascending) and fetch their g values: all loads of the batch in flight
+      int cnt = 0;
+      float gq[kPop];
+      int rq[kPop];
 #pragma unroll
-          for (int u = 0; u < NF; ++u) {
-            if (mask & (1u << u)) {      // warp-uniform
-              const int ru = __shfl_sync(0xffffffffu, r, u);
-              const float gu = __shfl_sync(0xffffffffu, gv, u);
-              const float* row = st_lane + ru * KW;
-#pragma unroll
-              for (int t = 0; t < NT; ++t) acc[u][t] = fmaf(gu, row[32 * t], acc[u][t]);
-            }
-          }
+      for (int q = 0; q < kPop; ++q) {
+        rq[q] = 0;
+        gq[q] = 0.f;
+        if (m) {
+          rq[q] = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          gq[q] = __ldg(g + (size_t)wd_s[rq[q]] * D + f_l);
+          ++cnt;
         }
       }
-      if (p1 > w_hi) break;     // this destination continues in the next window
-      ++n;
+      if (lane < NF) {
+#pragma unroll
+        for (int q = 0; q < kPop; ++q) {
+          lr_w[lane * kPop + q] = rq[q] * KW;
+          lg_w[lane * kPop + q] = gq[q];
+          db_acc += gq[q];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < NF; ++u) {
+        const int cu = __shfl_sync(0xffffffffu, cnt, u);
+        for (int q = 0; q < cu; ++q) {
+          const float gu = lg_w[u * kPop + q];
+          const float* row = st_lane + lr_w[u * kPop + q];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) acc[u][t] = fmaf(gu, row[32 * t], acc[u][t]);
+        }
+      }
+      __syncwarp();
     }
-    n_cur = n;
   }
   cp_async_wait<0>();
   float* p = part + (size_t)blockIdx.x * D * KW;
@@ -316,41 +327,56 @@ static inline int dw_grid(int D) {
   const int ks = dw_kslices(D);
   return kNumSMs / ks * ks;
 }
-static inline size_t dw_smem(int KW) { return ((size_t)kDwStages * kDwCap * KW + 32) * 4 + 2 * (size_t)KW * 4; }
+static inline size_t dw_smem(int D, int KW, int NF) {
+  return (size_t)kDwStages * kWin * KW * 4 + (size_t)kDwStages * D * 8 + (size_t)kDwStages * kWin * 4 +
+         2 * (size_t)KW * 4 + (size_t)kDwWarps * NF * kPop * 8;
+}
+static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 static inline size_t dw_part_bytes(int D) {
   const int ks = dw_kslices(D), KW = dw_kw(D, ks);
-  return ((size_t)dw_grid(D) * D * KW * sizeof(float) + (size_t)dw_grid(D) * D * sizeof(float) + 255) / 256 * 256;
+  return align256((size_t)dw_grid(D) * D * KW * sizeof(float) + (size_t)dw_grid(D) * D * sizeof(float));
+}
+static inline size_t rmask_bytes(int64_t E) { return align256((size_t)(E > 0 ? E : 1) * kRW * sizeof(uint32_t)); }
+static inline size_t fmask_bytes(int64_t E, int D) {
+  return align256((size_t)((E + kWin - 1) / kWin + 1) * D * sizeof(unsigned long long));
 }
 
-extern "C" size_t mrg_amax_bwd_workspace_bytes(int64_t N, int32_t D) {
-  return dw_part_bytes(D) + (size_t)N * D * sizeof(int32_t) + 256;   // per-CTA dW partials | pos[N,D]
+extern "C" size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D) {
+  (void)N;
+  return dw_part_bytes(D) + rmask_bytes(E) + fmask_bytes(E, D) + 256;   // dW partials | rmask | fmask
 }
 
 extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,
-                            const int32_t* csr_eid, const int32_t* chunk_first, const int32_t* chunk_seg, int64_t N,
-                            int64_t E, int64_t max_chunks, int32_t D, float* dX, float* dW, float* db, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            const int32_t* csr_eid, const int32_t* csr_dst, const int32_t* chunk_first,
+                            const int32_t* chunk_seg, int64_t N, int64_t E, int64_t max_chunks, int32_t D, float* dX,
+                            float* dW, float* db, void* workspace, size_t workspace_bytes, void* stream) {
   MRG_CHECK_ARG(g && arg && x.data && W && csr_ptr && chunk_first && chunk_seg && workspace, "amax_bwd: null pointer");
-  MRG_CHECK_ARG(E == 0 || csr_eid, "amax_bwd: null csr_eid");
+  MRG_CHECK_ARG(E == 0 || (csr_eid && csr_dst), "amax_bwd: null csr_eid / csr_dst");
   MRG_CHECK_ARG(valid_D(D) && D <= 256, "amax_bwd: D must be a multiple of 4 and <= 256");
-  if (workspace_bytes < mrg_amax_bwd_workspace_bytes(N, D)) {
+  if (workspace_bytes < mrg_amax_bwd_workspace_bytes(N, E, D)) {
     set_error("amax_bwd: workspace too small");
     return MRG_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
+  (void)max_chunks;
+  uint32_t* rmask = (uint32_t*)((char*)workspace + dw_part_bytes(D));
+  unsigned long long* fmask = (unsigned long long*)((char*)rmask + rmask_bytes(E));
+  e = cudaMemsetAsync(rmask, 0, rmask_bytes(E) + fmask_bytes(E, D), st);
+  if (e != cudaSuccess) return cuda_fail(e, "amax_bwd memset");
+  if (N > 0 && E > 0)
+    amax_route_kernel<<<(unsigned)((N * D + 255) / 256), 256, 0, st>>>(arg, csr_ptr, csr_eid, N, D, rmask, fmask);
   if (dX && E > 0) {
     const bool w_smem = (size_t)D * D * 4 <= 200 * 1024;
     const size_t smem = w_smem ? (size_t)D * D * 4 : 0;
     const int grid = kNumSMs;  // persistent: one 32-warp CTA per SM walks the chunk list
-    (void)max_chunks;
 #define LDX(NJ, WS)                                                                                              \
   do {                                                                                                           \
     if (smem > 48 * 1024) {                                                                                      \
       e = cudaFuncSetAttribute(amax_bwd_dx_kernel<NJ, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dx smem attr");                                        \
     }                                                                                                            \
-    amax_bwd_dx_kernel<NJ, WS><<<grid, kBwdThreads, smem, st>>>(g, arg, W, csr_ptr, csr_eid, chunk_first, chunk_seg, N, D, dX); \
+    amax_bwd_dx_kernel<NJ, WS><<<grid, kBwdThreads, smem, st>>>(g, rmask, W, csr_ptr, csr_eid, chunk_first, chunk_seg, N, D, dX); \
   } while (0)
     const int nj = (D + 31) / 32;
     if (nj <= 2) { if (w_smem) LDX(2, true); else LDX(2, false); }
@@ -363,15 +389,13 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
     const int ks = dw_kslices(D), KW = dw_kw(D, ks), grid = dw_grid(D);
     float* part = (float*)workspace;
     float* part_b = part + (size_t)grid * D * KW;
-    const size_t smem = dw_smem(KW);
     const int nf = (D + kDwWarps - 1) / kDwWarps, nt = (KW + 31) / 32;
-    int32_t* pos = (int32_t*)((char*)workspace + dw_part_bytes(D));
-    if (N > 0) amax_pos_kernel<<<(unsigned)((N * D + 255) / 256), 256, 0, st>>>(arg, csr_ptr, csr_eid, N, D, pos);
 #define LDW(NF, NT)                                                                                               \
   do {                                                                                                            \
+    const size_t smem = dw_smem(D, KW, NF);                                                                       \
     e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw smem attr");                                           \
-    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, pos, x, csr_ptr, csr_eid, N, E, D, KW, ks, part, \
+    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, fmask, x, csr_eid, csr_dst, E, D, KW, ks, part,  \
                                                                part_b);                                           \
   } while (0)
     if (nf <= 4 && nt <= 2) LDW(4, 2);

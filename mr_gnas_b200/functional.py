@@ -481,15 +481,18 @@ def amax_backward(g, gout, arg, x_act, weight, rows, has_residual, need_dx=True,
     D = gout.shape[1]
     dev = gout.device
     E = g.E
-    key = (g.N, D, str(dev))
+    key = (g.N, E, D, str(dev))
     if key not in _bwd_ws:
-        _bwd_ws[key] = torch.empty(int(_lib.load().mrg_amax_bwd_workspace_bytes(g.N, D)), dtype=torch.uint8, device=dev)
+        _bwd_ws[key] = torch.empty(int(_lib.load().mrg_amax_bwd_workspace_bytes(g.N, E, D)), dtype=torch.uint8,
+                                   device=dev)
     ws = _bwd_ws[key]
+    if getattr(g, 'csr_dst', None) is None:      # destination of every dst-CSR position (graph-static)
+        g.csr_dst = g.dst[g.csr.idx[:E].long()].contiguous() if E > 0 else g.dst
     if need_dx and dx is None:
         dx = torch.empty(rows, D, dtype=torch.float32, device=dev)
     dw = torch.empty(D, D, dtype=torch.float32, device=dev)
     db = torch.empty(D, dtype=torch.float32, device=dev)
-    call("mrg_amax_bwd", ptr(gout), ptr(arg), x_act, ptr(weight), ptr(g.csr.ptr), ptr(g.csr.idx),
+    call("mrg_amax_bwd", ptr(gout), ptr(arg), x_act, ptr(weight), ptr(g.csr.ptr), ptr(g.csr.idx), ptr(g.csr_dst),
          ptr(g.csr.chunk_first), ptr(g.csr.chunk_seg), g.N, E, g.csr.max_chunks, D, ptr(dx) if need_dx else None,
          ptr(dw), ptr(db), ptr(ws), ws.numel(), stream(), nbytes=2 * E * 4 * D + 2 * g.N * 4 * D)
     if need_dx and has_residual:
