@@ -291,6 +291,18 @@ int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, 
                  float* db, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * TransE 1-N scoring.  Replaces sf_TransE_op.forward (operations_lp.py:101-112):
+ *   logit[b,n] = gamma - || query[b,:] - ent[n,:] ||_1 ,  query = sub_emb + rel_emb;  score = sigmoid(logit)
+ * without the reference's [B, N, D] broadcast (2.98 GB at C1).  Backward: dquery[b,k] = -sum_n dlogit[b,n] *
+ * sgn(query[b,k] - ent[n,k]), dent[n,k] = +sum_b (same), sgn(0) = 0; either output may be NULL.  D % 4 == 0.
+ * ---------------------------------------------------------------------------------- */
+int mrg_transe_fwd(const float* query, const float* ent, int64_t B, int64_t N, int32_t D, float gamma, float* logit,
+                   void* stream);
+size_t mrg_transe_bwd_workspace_bytes(int64_t B, int64_t N, int32_t D);
+int mrg_transe_bwd(const float* dlogit, const float* query, const float* ent, int64_t B, int64_t N, int32_t D,
+                   float* dquery, float* dent, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K8  DistMult 1-N scoring epilogue + BCE.  Replaces torch.sigmoid + nn.BCELoss
  * (operations_lp.py:121-127; train/mr_lp_train.py:116,235): loss = mean over n elements of
  * -(y*max(log p,-100) + (1-y)*max(log(1-p),-100)), p = sigmoid(logit).

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmrgnas.so")
-SOURCES = ["rowops.cu", "segreduce.cu", "graph.cu", "gemm_tc.cu", "amax_bwd.cu", "gate_pipe.cu"]
+SOURCES = ["rowops.cu", "segreduce.cu", "graph.cu", "gemm_tc.cu", "amax_bwd.cu", "gate_pipe.cu", "score.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

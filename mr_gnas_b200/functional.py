@@ -647,6 +647,43 @@ class DistMultBCE(torch.autograd.Function):
         return dent, dq * rel_emb, dq * sub_emb, None
 
 
+_te_ws = {}
+
+
+class TransELogits(torch.autograd.Function):
+    """logit[b,n] = gamma - ||query[b] - all_ent[n]||_1 (sf_TransE_op, operations_lp.py:101-112) without the
+    reference's [B, N, D] broadcast: mrg_transe_fwd / mrg_transe_bwd."""
+
+    @staticmethod
+    def forward(ctx, all_ent, query, gamma):
+        all_ent, query = _f32c(all_ent), _f32c(query)
+        B, D = query.shape
+        N = all_ent.shape[0]
+        logit = torch.empty(B, N, dtype=torch.float32, device=all_ent.device)
+        call("mrg_transe_fwd", ptr(query), ptr(all_ent), B, N, D, float(gamma), ptr(logit), stream(),
+             nbytes=N * D * 4 + B * N * 4)
+        ctx.save_for_backward(all_ent, query)
+        return logit
+
+    @staticmethod
+    def backward(ctx, dl):
+        all_ent, query = ctx.saved_tensors
+        dl = _f32c(dl)
+        B, D = query.shape
+        N = all_ent.shape[0]
+        dev = dl.device
+        key = (B, N, D, str(dev))
+        if key not in _te_ws:
+            _te_ws[key] = torch.empty(int(_lib.load().mrg_transe_bwd_workspace_bytes(B, N, D)), dtype=torch.uint8,
+                                      device=dev)
+        ws = _te_ws[key]
+        dq = torch.empty_like(query) if ctx.needs_input_grad[1] else None
+        de = torch.empty_like(all_ent) if ctx.needs_input_grad[0] else None
+        call("mrg_transe_bwd", ptr(dl), ptr(query), ptr(all_ent), B, N, D, ptr(dq), ptr(de), ptr(ws), ws.numel(),
+             stream(), nbytes=2 * B * N * 4)
+        return de, dq, None
+
+
 def distmult_bce_supported(D):
     return bool(_lib.load().mrg_distmult_bce_supported(int(D)))
 

@@ -23,7 +23,7 @@ class OpModule(nn.Module):
         self.activate = nn.ReLU()
 
     def forward(self, g, h, h_in):
-        h = self.linear(self.op(g, h, h_in))
+        h = K.linear(self.linear, self.op(g, h, h_in))     # tcgen05 (3xTF32) on full-graph / large blocks
         if self.args.op_norm:
             return K.bn_act(h, self.batchnorm_h, relu=True)
         return K.ReluAct.apply(h)
@@ -53,7 +53,7 @@ class Cell(nn.Module):
         for n in range(1, self._nb_nodes):
             hs = [self._ops[n][i][0](g, states[i], zero_out) for i in range(n + 1) if len(self._ops[n][i]) > 0]
             states.append(hs[0] if len(hs) == 1 else sum(hs))
-        h = self.concat(torch.cat([states[idx] for idx in self._concat_node], dim=1))
+        h = K.linear(self.concat, torch.cat([states[idx] for idx in self._concat_node], dim=1))
         return K.bn_act(h, self.batchnorm_h, relu=True)
 
 
@@ -81,7 +81,7 @@ class mean_aggre(nn.Module):
         self.linear = nn.Linear(feature_dim, feature_dim)
 
     def forward(self, block, src_emb):
-        return K.SegReduce.apply(self.linear(src_emb), None, block, 1, True)
+        return K.SegReduce.apply(K.linear(self.linear, src_emb), None, block, 1, True)
 
 
 def block_inputs(trip_index, blocks):

@@ -48,7 +48,7 @@ class a_max_op(nn.Module):
     def forward(self, block, src_emb, src_emb_in):
         if self.kind == 2 and lp.USE_TENSOR_CORES and K.amax_tc_supported(src_emb.shape[1]):
             return K.AMaxTC.apply(src_emb, self.linear.weight, self.linear.bias, block, False)
-        return K.SegReduce.apply(self.linear(src_emb), None, block, self.kind, True)
+        return K.SegReduce.apply(K.linear(self.linear, src_emb), None, block, self.kind, True)
 
 
 class a_mean_op(a_max_op):

@@ -102,7 +102,7 @@ class a_max_op(nn.Module):
         E = block.num_edges()
         if self.kind == 2 and USE_TENSOR_CORES and K.amax_tc_supported(src_emb.shape[1]):
             return K.AMaxTC.apply(src_emb, self.linear.weight, self.linear.bias, block, True)
-        m_pre = self.linear(src_emb[:E, :])  # edge-tile GEMM (bias fused); ReLU is applied on load by the reducer
+        m_pre = K.linear(self.linear, src_emb[:E, :])  # edge-tile GEMM (tcgen05, bias fused); ReLU applied on load by the reducer
         return K.SegReduce.apply(m_pre, src_emb[E:, :], block, self.kind, True)
 
 
@@ -190,10 +190,9 @@ class f_sparse_op_last(nn.Module):
 
 # ------------------------------------------------------------------ dense gates (K4)
 def _seg_linear(W, x, xin, lo, hi):
-    """W [x, xin] (+b) on rows [lo,hi) without materialising the [rows,2D] concat."""
-    D = x.shape[1]
-    z = x[lo:hi] @ W.weight[:, :D].t() + xin[lo:hi] @ W.weight[:, D:].t()
-    return z + W.bias if W.bias is not None else z
+    """W [x, xin] (+b) on rows [lo,hi): the edge-tile GEMM of the dense candidates (operations_lp.py:275-283,
+    366-384) on the tcgen05 main loop (3xTF32, K = 2D) when the tile is large enough, else the library GEMM."""
+    return K.linear(W, torch.cat([x[lo:hi], xin[lo:hi]], 1))
 
 
 class f_dense_op_comp(nn.Module):
@@ -259,7 +258,7 @@ class f_dense_op_last(nn.Module):
 
     def forward(self, g, src_emb, src_emb_in):
         rows = src_emb.shape[0]
-        y, stats = K.DenseGate.apply(self.W(src_emb), src_emb, True, None, 0, (1.0,), [(0, rows)])
+        y, stats = K.DenseGate.apply(K.linear(self.W, src_emb), src_emb, True, None, 0, (1.0,), [(0, rows)])
         return _with_stats(y, stats)
 
 
@@ -284,15 +283,24 @@ class sf_DisMult_op(nn.Module):
 
 
 class sf_TransE_op(nn.Module):
-    """reference: operations_lp.py:101-112 (selectable by genotype; SURVEY.md 8f rank 4, plain torch)."""
+    """reference: operations_lp.py:101-112 (selectable by genotype):
+    sigmoid(gamma - ||sub_emb + rel_emb - all_ent||_1) as a fused L1-distance kernel (csrc/score.cu) instead of the
+    reference's [B, N, D] broadcast; `loss` feeds the logits to the fused sigmoid+BCE kernel like sf_DisMult."""
 
     def __init__(self, args):
         super().__init__()
         self.gamma = args.get('gamma', 40)
 
+    def logits(self, all_ent, sub_emb, rel_emb):
+        if all_ent.is_cuda and all_ent.shape[1] % 4 == 0:
+            return K.TransELogits.apply(all_ent, sub_emb + rel_emb, self.gamma)
+        raise RuntimeError("sf_TransE runs on the CUDA path only (feature dim must be a multiple of 4)")
+
     def forward(self, all_ent, sub_emb, rel_emb):
-        obj_emb = sub_emb + rel_emb
-        return torch.sigmoid(self.gamma - torch.cdist(obj_emb, all_ent, p=1))
+        return torch.sigmoid(self.logits(all_ent, sub_emb, rel_emb))
+
+    def loss(self, all_ent, sub_emb, rel_emb, label):
+        return K.SigmoidBCE.apply(self.logits(all_ent, sub_emb, rel_emb), label)
 
 
 class sf_ConvE_op(nn.Module):

@@ -33,7 +33,7 @@ class MixedOp(nn.Module):
         for stack in self._ops:
             y = stack[0](g, h, h_in)
             if self._with_linear:
-                y = stack[1](y.float())
+                y = K.linear(stack[1], y.float())
             ys.append(y)
             bns.append(stack[-2])
         return K.mixed_sum(weights, ys, bns)

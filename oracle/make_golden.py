@@ -612,6 +612,31 @@ def gen_config_c2():
     torch.save(out, os.path.join(OUT, "config_c2.pt"))
 
 
+def gen_score_transe():
+    """sf_TransE_op (operations_lp.py:101-112) from the REAL reference: probabilities, BCE loss and gradients for
+    two shapes (ragged tile edges; exact-zero differences so that sign(0) = 0 matters), fp32 + fp64."""
+    cases = {}
+    for tag, (B, N, D, gamma, seed) in {"small": (5, 37, 8, 9.0, 3), "ragged": (70, 333, 72, 40.0, 4)}.items():
+        torch.manual_seed(seed)
+        op = ref_lp.MIXED_OPS_sf['sf_TransE']({'gamma': gamma})
+        ent = torch.randn(N, D)
+        sub, rel = torch.randn(B, D), torch.randn(B, D)
+        ent[3] = sub[1] + rel[1]                     # a zero distance: every |.| has a zero argument
+        ent[5, :4] = (sub[2] + rel[2])[:4]
+        label = (torch.rand(B, N) < 0.05).float() * 0.9 + 1.0 / N
+        out = {}
+        for dt in (torch.float32, torch.float64):
+            e, s_, r_ = (t.detach().clone().to(dt).requires_grad_(True) for t in (ent, sub, rel))
+            pred = op(e, s_, r_)
+            loss = nn.BCELoss()(pred, label.to(dt))
+            loss.backward()
+            out[dt] = {"pred": pred.detach(), "loss": loss.detach(), "dent": e.grad.clone(), "dsub": s_.grad.clone(),
+                       "drel": r_.grad.clone()}
+        cases[tag] = {"B": B, "N": N, "D": D, "gamma": gamma, "ent": ent, "sub": sub, "rel": rel, "label": label,
+                      "f32": out[torch.float32], "f64": out[torch.float64]}
+    torch.save(cases, os.path.join(OUT, "score_transe.pt"))
+
+
 def gen_labels():
     """1-N training items and their dense smoothed label rows from the REAL process() (utils/process_data.py:4-31)
     and TrainDataset (utils/data_set.py:6-33): the fixture behind the host-side batch builders and the device-side
@@ -671,7 +696,7 @@ def gen_predict():
 
 
 if __name__ == "__main__":
-    single = {"predict": gen_predict, "labels": gen_labels, "config_c1": gen_config_c1, "config_c2": gen_config_c2,
+    single = {"predict": gen_predict, "labels": gen_labels, "score_transe": gen_score_transe, "config_c1": gen_config_c1, "config_c2": gen_config_c2,
               "config_c3": gen_config_c3}
     if len(sys.argv) > 1 and sys.argv[1] in single:
         for name in sys.argv[1:]:
@@ -687,6 +712,7 @@ if __name__ == "__main__":
     gen_network_nc()
     gen_predict()
     gen_labels()
+    gen_score_transe()
     gen_config_c2()
     gen_config_c3()
     gen_config_c1()

@@ -4,7 +4,6 @@ mrg_graph_build_part, the sharded scorer and the statistics plumbing; world=2 ru
 the box has 2 GPUs and otherwise BOTH ranks on the one GPU with a gloo group (dist.py stages the collectives
 through the host there) -- the partition arithmetic is the same, so the 2-rank path is never skipped."""
 import os
-import socket
 import types
 from collections import namedtuple
 
@@ -23,11 +22,12 @@ CELL = Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('f_spar
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    return port
+    """A rendezvous FILE (not a TCP port: a freshly released port can still be in TIME_WAIT -> EADDRINUSE)."""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="mrg_rdzv_")
+    os.close(fd)
+    os.unlink(path)
+    return path
 
 
 def _args(D):
@@ -86,14 +86,14 @@ def _compare(rank, world, n_cells, dev_index=None):
 
 def _init(rank, world, port):
     """-> device index of this rank.  One GPU per rank + NCCL when possible, else a shared GPU + gloo."""
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
+    init = f"file://{port}"
     if torch.cuda.device_count() >= world:
         torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        dist.init_process_group("nccl", init_method=init, rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
         return rank
     torch.cuda.set_device(0)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
     return 0
 
 
