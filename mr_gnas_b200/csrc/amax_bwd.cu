@@ -62,7 +62,8 @@ template <int NJ, bool W_SMEM>
 __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
     const float* __restrict__ g, const uint32_t* __restrict__ rmask, const float* __restrict__ W,
     const int32_t* __restrict__ ptr, const int32_t* __restrict__ eid, const int32_t* __restrict__ chunk_first,
-    const int32_t* __restrict__ chunk_seg, int64_t nseg, int D, float* __restrict__ dX) {
+    const int32_t* __restrict__ chunk_seg, int64_t nseg, int D, float* __restrict__ dX,
+    unsigned int* __restrict__ next_chunk) {
   extern __shared__ float smem_w[];  // [D][D] when W_SMEM
   constexpr int NT4 = (NJ + 3) / 4;   // float4 column groups per lane
   const int lane = threadIdx.x & 31;
@@ -73,10 +74,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
   }
   const float* Wp = W_SMEM ? smem_w : W;
   const int D4 = D >> 2;
-  const int64_t warp0 = (int64_t)blockIdx.x * kBwdWarps + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kBwdWarps;
+  // Chunks cost between ~30 (a hub's rows, hardly any routed feature) and ~3,500 (the single edge of a
+  // degree-1 destination carries all D features) instructions: a static round-robin left the SM sub-partitions
+  // between 24 % and 76 % busy (ncu, round 2).  Warps now draw chunks from a global counter; every dX row still
+  // has exactly one writer and a fixed summation order, so the result does not depend on who draws what.
   const int64_t nchunks = chunk_first[nseg];
-  for (int64_t ch = warp0; ch < nchunks; ch += nwarps) {
+  for (;;) {
+    unsigned int ch_u = 0;
+    if (lane == 0) ch_u = atomicAdd(next_chunk, 1u);
+    const int64_t ch = __shfl_sync(0xffffffffu, ch_u, 0);
+    if (ch >= nchunks) break;
     const int64_t n = chunk_seg[ch];
     const int32_t p0 = ptr[n], p1 = ptr[n + 1];
     const int32_t lo = p0 + (int32_t)(ch - chunk_first[n]) * MRG_CHUNK_ROWS;
@@ -343,7 +350,7 @@ static inline size_t fmask_bytes(int64_t E, int D) {
 
 extern "C" size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D) {
   (void)N;
-  return dw_part_bytes(D) + rmask_bytes(E) + fmask_bytes(E, D) + 256;   // dW partials | rmask | fmask
+  return dw_part_bytes(D) + rmask_bytes(E) + fmask_bytes(E, D) + 512;   // dW partials | rmask | fmask | counter
 }
 
 extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,
@@ -362,7 +369,8 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
   (void)max_chunks;
   uint32_t* rmask = (uint32_t*)((char*)workspace + dw_part_bytes(D));
   unsigned long long* fmask = (unsigned long long*)((char*)rmask + rmask_bytes(E));
-  e = cudaMemsetAsync(rmask, 0, rmask_bytes(E) + fmask_bytes(E, D), st);
+  unsigned int* counter = (unsigned int*)((char*)fmask + fmask_bytes(E, D));     // dX chunk counter (zeroed with the tables)
+  e = cudaMemsetAsync(rmask, 0, rmask_bytes(E) + fmask_bytes(E, D) + 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "amax_bwd memset");
   if (N > 0 && E > 0)
     amax_route_kernel<<<(unsigned)((N * D + 255) / 256), 256, 0, st>>>(arg, csr_ptr, csr_eid, N, D, rmask, fmask);
@@ -376,7 +384,7 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
       e = cudaFuncSetAttribute(amax_bwd_dx_kernel<NJ, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dx smem attr");                                        \
     }                                                                                                            \
-    amax_bwd_dx_kernel<NJ, WS><<<grid, kBwdThreads, smem, st>>>(g, rmask, W, csr_ptr, csr_eid, chunk_first, chunk_seg, N, D, dX); \
+    amax_bwd_dx_kernel<NJ, WS><<<grid, kBwdThreads, smem, st>>>(g, rmask, W, csr_ptr, csr_eid, chunk_first, chunk_seg, N, D, dX, counter); \
   } while (0)
     const int nj = (D + 31) / 32;
     if (nj <= 2) { if (w_smem) LDX(2, true); else LDX(2, false); }

@@ -110,3 +110,18 @@ def check_grads(tag, ours, ref32, truth64, tol=RTOL, slack=4.0, max_fraction=0.1
               f"ratio ours/reference median {ratios[len(ratios) // 2]:.2f} max {ratios[-1]:.2f}" % max(rows))
     assert len(bad) <= max(1, int(max_fraction * len(rows))), f"{tag}: beyond {slack}x the reference's own error: {bad}"
     return rows
+
+
+def check_grads_pair(tag, named_a, named_b, tol=2e-5, max_fraction=0.10, hard=2e-3):
+    """Two fp32 evaluations of the SAME step that differ only in summation order (e.g. destination-partitioned vs
+    single GPU) -- no fp64 truth at hand.  Per tensor max|a-b| / max|b|: well-conditioned tensors agree to `tol`;
+    gradients that are small differences of large sums (the W.bias of a sparse gate: the real fp32 reference is
+    itself up to 5e-4 from its fp64 value there, see tests/golden/network_nc.pt) move with the order of the sum.
+    So: at most `max_fraction` of the tensors beyond `tol`, none beyond `hard`; zero-true-gradient tensors are
+    handled as in grad_errors."""
+    errs = grad_errors(named_a, named_b)
+    beyond = [(e, k) for e, k in errs if e > tol]
+    worst = max(errs)
+    print(f"{tag}: {len(errs)} gradient tensors, worst rel err {worst[0]:.2e} at {worst[1]}, {len(beyond)} beyond {tol:.0e}")
+    assert worst[0] <= hard, (tag, worst)
+    assert len(beyond) <= max(1, int(max_fraction * len(errs))), (tag, sorted(beyond, reverse=True))

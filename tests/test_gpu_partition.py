@@ -35,7 +35,7 @@ def _args(D):
                                  conve_hid_drop=0.0, feat_drop=0.0, num_filt=4, ker_sz=3, k_w=4, k_h=D // 4)
 
 
-from parity import grad_errors, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
+from parity import check_grads_pair, rel_err as _err  # max|a-b| / max|b|: relative to the tensor's own scale, no absolute floor
 
 
 def _compare(rank, world, n_cells, dev_index=None):
@@ -72,9 +72,8 @@ def _compare(rank, world, n_cells, dev_index=None):
     loss.backward()
     D_.allreduce_grads_sum(list(par.parameters()), g.part)
     assert _err(loss, loss_ref) <= 1e-5, (float(loss), float(loss_ref))
-    worst = max(grad_errors({k: p.grad for k, p in par.named_parameters()},
-                            {k: q.grad for k, q in ref.named_parameters()}))
-    assert worst[0] <= 2e-5, worst
+    check_grads_pair(f"LP partition world {world}", {k: p.grad for k, p in par.named_parameters()},
+                     {k: q.grad for k, q in ref.named_parameters()})
     for (k, a), b in zip(par.named_buffers(), ref.buffers()):
         if a.dtype.is_floating_point:
             assert _err(a, b) <= 1e-5, k
@@ -160,9 +159,8 @@ def _compare_nc(rank, world, dev_index=None):
     loss.backward()
     D_.allreduce_grads_sum(list(par.parameters()), part)
     assert _err(loss, loss_ref) <= 1e-5, (float(loss), float(loss_ref))
-    worst = max(grad_errors({k: p.grad for k, p in par.named_parameters()},
-                            {k: q.grad for k, q in ref.named_parameters() if dict(par.named_parameters())[k].grad is not None}))
-    assert worst[0] <= 2e-5, worst
+    check_grads_pair(f"NC partition world {world}", {k: p.grad for k, p in par.named_parameters()},
+                     {k: q.grad for k, q in ref.named_parameters() if dict(par.named_parameters())[k].grad is not None})
 
 
 def _worker_nc(rank, world, port):

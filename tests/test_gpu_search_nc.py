@@ -225,3 +225,43 @@ def test_compgcn_golden(golden_dir, comp):
     ref32 = {"dh": c["dh"], "dr": c["dr"], **{"d" + k: v for k, v in c["dparams"].items()}}
     truth = {"dh": T["dh"], "dr": T["dr"], **{"d" + k: v for k, v in T["dparams"].items()}}
     check_grads("compgcn " + comp, ours, ref32, truth)
+
+
+# ------------------------------------------------------------------------------ search-script graph pipeline (8f rank 3)
+@pytest.mark.parametrize("N,R,T,S", [(500, 5, 3000, 400), (40943, 11, 86835, 30000)], ids=["small", "c3"])
+def test_device_sampler_reproduces_reference_pipeline(N, R, T, S):
+    """utils_rgcn.sample_search_graph (device: torch.unique relabel, vectorised negative sampling, packed-key radix
+    sort by (rel, dst, src), K0 graph build) against the oracle restatement of generate_sampled_graph_and_labels --
+    itself pinned draw-for-draw to the REAL utils/utils_rgcn.py:79-204 (tests/golden/config_c3.pt checksums) -- on
+    the SAME random draws: every array must be bit-identical (integer graph arrays, fp32 norms, samples, labels)."""
+    from mr_gnas_b200.utils_rgcn import sample_search_graph
+    from oracle.mrg_oracle import sample_search_graph as oracle_sampler, synth_kg
+    trip = synth_kg(N, R, T, seed=0)
+    neg_rate, split_size = 10, 0.5
+    np.random.seed(0)
+    ref = oracle_sampler(trip, S, split_size, R, neg_rate)
+    # the same draws, taken in the reference's order from the same numpy stream
+    np.random.seed(0)
+    edges = np.random.choice(np.arange(T), S, replace=False)
+    n = len(np.unique((trip[edges, 0], trip[edges, 2])))
+    values = np.random.randint(n, size=S * neg_rate)
+    choices = np.random.uniform(size=S * neg_rate)
+    keep = np.random.choice(np.arange(S), size=int(S * split_size), replace=False)
+    d = sample_search_graph(trip, S, split_size, R, neg_rate, device=DEV,
+                            draws={"edges": edges, "values": values, "choices": choices, "keep": keep})
+    for key in ("uniq_v", "src", "dst", "etype", "samples"):
+        assert np.array_equal(d[key].cpu().numpy(), ref[key]), key
+    assert np.array_equal(d["labels"].cpu().numpy(), ref["labels"])
+    assert np.array_equal(d["node_norm"].cpu().numpy(), ref["node_norm"])
+    assert np.array_equal(d["norm"].cpu().numpy(), ref["norm"])
+    g = d["g"]
+    assert g.N == ref["num_nodes"] and g.E == len(ref["src"]) and tuple(g.edata['norm'].shape) == (g.E, 1)
+    # its own generator: structurally valid sample (sizes, label counts, relabelling is a bijection onto [0, n))
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    d2 = sample_search_graph(trip, S, split_size, R, neg_rate, device=DEV, generator=gen)
+    assert d2["samples"].shape == (S * (neg_rate + 1), 3) and int(d2["labels"].sum()) == S
+    assert d2["g"].E == 2 * int(S * split_size) and int(d2["src"].max()) < d2["g"].N
+    uv = d2["uniq_v"].cpu().numpy()
+    assert np.all(np.diff(uv) > 0) and uv.max() < N
+    key = (d2["etype"] * d2["g"].N + d2["dst"]) * d2["g"].N + d2["src"]
+    assert bool((key[1:] >= key[:-1]).all())          # ordered by (rel, dst, src)
