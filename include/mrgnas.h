@@ -282,7 +282,8 @@ int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t*
  * every row written once), the Linear weight (dW [D,D]) and bias (db [D]) from g = dL/d(out),
  * the encoded argmax and the (lazily activated) input rows.  Replaces the reference's two dense
  * [E,D]x[D,D] backward GEMMs with 2*N*D*D FMAs on the routed entries only.  dX / dW may be NULL.
- * csr_dst[p] = destination of the edge at dst-CSR position p (= dst[csr_eid[p]], graph-static).  The call first
+ * csr_dst[p] = destination of the edge at dst-CSR position p (= dst[csr_eid[p]], graph-static), allocated with 64
+ * extra entries (whole 64-row windows are bulk-copied).  The call first
  * turns `arg` into two bit tables over CSR positions (workspace), which both products then walk. */
 size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D);
 int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,

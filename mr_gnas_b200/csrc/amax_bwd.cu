@@ -21,6 +21,7 @@
 // bitwise OR is order independent, dX rows have one writer, dW accumulators have one owner warp and the per-CTA
 // partials are folded in CTA order.
 #include "common.cuh"
+#include "pipe.cuh"
 
 namespace mrg {
 
@@ -135,46 +136,37 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
 // ---------------------------------------------------------------------------------------
 // dW / db.  Every (destination, feature) pair routes g[n,f] to ONE edge row, so dW^T is a sum of
 // N*D rank-1 contributions g[n,f] * x(arg[n,f],:).  Each CTA owns a contiguous range of 64-row windows of
-// dst-CSR positions, streams the x rows of that range ONCE into shared memory (cp.async, 3-stage ring; the
-// window's fmask row and destination ids ride along; lazy BatchNorm+ReLU applied in place when a window lands).
-// Warp w owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS (acc[u][t]: feature w*NF+u,
-// column k0 + lane + 32 t): lane u reads the 64-bit row set of its feature, the warp pops up to kPop rows per
-// feature into a small shared list, fetches their g values in one parallel round (one exposed L2 latency per
-// window instead of one per destination) and then accumulates feature by feature in ascending row order.
+// dst-CSR positions and streams the x rows of that range ONCE through a 3-stage shared-memory ring:
+//   * warp 0 issues one cp.async.bulk per row (800 B at D=200; edge ids prefetched one window ahead, so the issue
+//     never waits on a load) plus the window's fmask row and destination ids; completion by mbarrier expect_tx.
+//     Round-2 profile of the per-thread cp.async version: 15 % of the instructions and 29 % of the stall samples sat
+//     in the copy loop (address arithmetic, waiting for the edge ids);
+//   * lazy BatchNorm + ReLU is applied in place by all threads, one float4 column group per thread (scale / shift
+//     in registers), then one __syncthreads;
+//   * warp w owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS (acc[u][t]: feature w*NF+u,
+//     column k0 + lane + 32 t): lane u reads the 64-bit row set of its feature, the warp pops rows (ascending) into
+//     a small shared list, fetches their g values in one parallel round and accumulates feature by feature.
 // No shared-memory read-modify-write, no atomics, fixed order -> deterministic.
 // Partials: part[cta][D][KW] (+ db in part_b[group][D]), folded in CTA order.
 // ---------------------------------------------------------------------------------------
 constexpr int kDwThreads = 512;
 constexpr int kDwWarps = kDwThreads / 32;
 constexpr int kDwStages = 3;
-constexpr int kPop = 8;         // rows popped per feature and batch
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int kPop = 3;         // rows popped per feature and batch
 
 template <int NF, int NT>
 __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     const float* __restrict__ g, const unsigned long long* __restrict__ fmask, mrg_act x,
     const int32_t* __restrict__ eid, const int32_t* __restrict__ csr_dst, int64_t E, int D, int KW, int kslices,
     float* __restrict__ part, float* __restrict__ part_b) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | sc[KW] | sh[KW] |
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | full[kDwStages] u64 |
   //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32
   float* xs = reinterpret_cast<float*>(smem_raw);
   unsigned long long* fm = reinterpret_cast<unsigned long long*>(xs + (size_t)kDwStages * kWin * KW);
   int32_t* wd = reinterpret_cast<int32_t*>(fm + (size_t)kDwStages * D);
-  float* sc_s = reinterpret_cast<float*>(wd + kDwStages * kWin);
-  float* sh_s = sc_s + KW;
-  int32_t* lr = reinterpret_cast<int32_t*>(sh_s + KW);
+  uint64_t* full = reinterpret_cast<uint64_t*>(wd + kDwStages * kWin);
+  int32_t* lr = reinterpret_cast<int32_t*>(full + kDwStages);
   float* lg = reinterpret_cast<float*>(lr + kDwWarps * NF * kPop);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x % kslices, group = blockIdx.x / kslices, ngroups = gridDim.x / kslices;
@@ -182,14 +174,21 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
   const int kw = min(KW, D - k0);   // valid columns of this slice (multiple of 4)
   const int kw4 = kw >> 2;
   const bool affine = x.scale != nullptr, relu = x.relu != 0;
-  if (affine)
-    for (int c = threadIdx.x; c < kw; c += blockDim.x) {
-      sc_s[c] = x.scale[k0 + c];
-      sh_s[c] = x.shift[k0 + c];
-    }
   const int64_t nwin = (E + kWin - 1) / kWin;
   const int64_t W0 = nwin * group / ngroups, W1 = nwin * (group + 1) / ngroups;
   const int nb = (int)(W1 - W0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) pipe::mbar_init(full + s, 1);
+    pipe::fence_barrier_init();
+  }
+  // in-place activation: thread t owns float4 column group t % 64 (when < kw4) of rows t / 64 + 8 i
+  const int my_c4 = threadIdx.x & 63, my_r0 = threadIdx.x >> 6;
+  float4 my_sc = make_float4(1.f, 1.f, 1.f, 1.f), my_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (affine && my_c4 < kw4) {
+    my_sc = ldg4(x.scale + k0 + 4 * my_c4);
+    my_sh = ldg4(x.shift + k0 + 4 * my_c4);
+  }
 
   float acc[NF][NT];
 #pragma unroll
@@ -201,52 +200,67 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
   const bool f_ok = lane < NF && f_l < D;
   int32_t* lr_w = lr + warp * NF * kPop;
   float* lg_w = lg + warp * NF * kPop;
+  __syncthreads();
 
-  auto issue = [&](int b) {   // warp w copies rows w, w+16, ... of window b; the first warps also fmask / dst ids
+  // ---- producer state (warp 0): edge ids of rows lane, lane + 32 of the NEXT window to issue
+  int32_t e_pf0 = 0, e_pf1 = 0;
+  auto prefetch_eids = [&](int b) {
+    if (b < nb) {
+      const int64_t w_lo = (W0 + b) * kWin;
+      e_pf0 = w_lo + lane < E ? __ldg(eid + w_lo + lane) : 0;
+      e_pf1 = w_lo + lane + 32 < E ? __ldg(eid + w_lo + lane + 32) : 0;
+    }
+  };
+  auto issue = [&](int b) {     // warp 0 only; the stage must have been released by a __syncthreads
     const int64_t w_lo = (W0 + b) * kWin;
     const int nrows = (int)min((int64_t)kWin, E - w_lo);
     const int s = b % kDwStages;
     float* st = xs + (size_t)s * kWin * KW;
-    for (int r = warp; r < nrows; r += kDwWarps) {
-      const int32_t e = __ldg(eid + w_lo + r);
-      const float* src = x.data + (size_t)e * D + k0;
-      for (int c4 = lane; c4 < kw4; c4 += 32) cp_async16(st + (size_t)r * KW + 4 * c4, src + 4 * c4);
+    const uint32_t row_bytes = (uint32_t)kw * 4u;
+    if (lane == 0) {
+      pipe::mbar_expect_tx(full + s, (uint32_t)nrows * row_bytes + (uint32_t)D * 8u + (uint32_t)kWin * 4u);
+      pipe::bulk_g2s(fm + (size_t)s * D, fmask + (size_t)(W0 + b) * D, (uint32_t)D * 8u, full + s);
+      pipe::bulk_g2s(wd + s * kWin, csr_dst + w_lo, (uint32_t)kWin * 4u, full + s);   // csr_dst is padded by kWin entries
     }
-    const unsigned long long* fsrc = fmask + (size_t)(W0 + b) * D;
-    for (int c = threadIdx.x; c < D / 2; c += kDwThreads) cp_async16(fm + (size_t)s * D + 2 * c, fsrc + 2 * c);
-    if (threadIdx.x < nrows) cp_async4(wd + s * kWin + threadIdx.x, csr_dst + w_lo + threadIdx.x);
+    if (lane < nrows) pipe::bulk_g2s(st + (size_t)lane * KW, x.data + (size_t)e_pf0 * D + k0, row_bytes, full + s);
+    if (lane + 32 < nrows)
+      pipe::bulk_g2s(st + (size_t)(lane + 32) * KW, x.data + (size_t)e_pf1 * D + k0, row_bytes, full + s);
   };
-
-  if (nb > 0) issue(0);
-  cp_async_commit();
-  if (nb > 1) issue(1);
-  cp_async_commit();
+  if (warp == 0) {
+    prefetch_eids(0);
+    if (nb > 0) issue(0);
+    prefetch_eids(1);
+    if (nb > 1) issue(1);
+    prefetch_eids(2);
+  }
 
   for (int b = 0; b < nb; ++b) {
-    cp_async_wait<1>();
     const int64_t w_lo = (W0 + b) * kWin;
     const int nrows = (int)min((int64_t)kWin, E - w_lo);
     const int s = b % kDwStages;
-    if (affine || relu) {     // each thread post-processes exactly the 16-byte pieces it copied
-      float* st = xs + (size_t)s * kWin * KW;
-      for (int r = warp; r < nrows; r += kDwWarps)
-        for (int c4 = lane; c4 < kw4; c4 += 32) {
-          float4 v = *reinterpret_cast<float4*>(st + (size_t)r * KW + 4 * c4);
-          if (affine) {
-            const float4 a = *reinterpret_cast<const float4*>(sc_s + 4 * c4);
-            const float4 sh = *reinterpret_cast<const float4*>(sh_s + 4 * c4);
-            v.x = fmaf(a.x, v.x, sh.x); v.y = fmaf(a.y, v.y, sh.y); v.z = fmaf(a.z, v.z, sh.z); v.w = fmaf(a.w, v.w, sh.w);
-          }
-          if (relu) {
-            v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
-            v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
-          }
-          *reinterpret_cast<float4*>(st + (size_t)r * KW + 4 * c4) = v;
+    pipe::mbar_wait(full + s, (uint32_t)(b / kDwStages) & 1u);
+    if ((affine || relu) && my_c4 < kw4) {
+      float* col = xs + (size_t)s * kWin * KW + 4 * my_c4;
+      for (int r = my_r0; r < nrows; r += kDwThreads / 64) {
+        float4 v = *reinterpret_cast<float4*>(col + (size_t)r * KW);
+        if (affine) {
+          v.x = fmaf(my_sc.x, v.x, my_sh.x); v.y = fmaf(my_sc.y, v.y, my_sh.y);
+          v.z = fmaf(my_sc.z, v.z, my_sh.z); v.w = fmaf(my_sc.w, v.w, my_sh.w);
         }
+        if (relu) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(col + (size_t)r * KW) = v;
+      }
     }
-    __syncthreads();          // window b complete for everyone; everyone finished computing window b-1
-    if (b + 2 < nb) issue(b + 2);
-    cp_async_commit();
+    // generic-proxy writes of this window (and reads of window b-1) are ordered before the bulk copies that will
+    // overwrite the ring: proxy fence by every thread, then the CTA barrier, then warp 0 issues window b+2
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0 && b + 2 < nb) {
+      issue(b + 2);              // into the stage of window b-1, which everyone has left
+      prefetch_eids(b + 3);
+    }
     const float* st_lane = xs + (size_t)s * kWin * KW + lane;
     const int32_t* wd_s = wd + s * kWin;
 
@@ -260,6 +274,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
       for (int q = 0; q < kPop; ++q) {
         rq[q] = 0;
         gq[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < kPop; ++q) {
+        if (!__ballot_sync(0xffffffffu, m != 0ull)) break;     // warp-uniform: most features have 1-3 rows here
         if (m) {
           rq[q] = __ffsll((long long)m) - 1;
           m &= m - 1;
@@ -289,7 +307,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
       __syncwarp();
     }
   }
-  cp_async_wait<0>();
   float* p = part + (size_t)blockIdx.x * D * KW;
 #pragma unroll
   for (int u = 0; u < NF; ++u) {
@@ -336,7 +353,7 @@ static inline int dw_grid(int D) {
 }
 static inline size_t dw_smem(int D, int KW, int NF) {
   return (size_t)kDwStages * kWin * KW * 4 + (size_t)kDwStages * D * 8 + (size_t)kDwStages * kWin * 4 +
-         2 * (size_t)KW * 4 + (size_t)kDwWarps * NF * kPop * 8;
+         (size_t)kDwStages * 8 + (size_t)kDwWarps * NF * kPop * 8 + 128;
 }
 static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 static inline size_t dw_part_bytes(int D) {

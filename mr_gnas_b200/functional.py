@@ -486,8 +486,9 @@ def amax_backward(g, gout, arg, x_act, weight, rows, has_residual, need_dx=True,
         _bwd_ws[key] = torch.empty(int(_lib.load().mrg_amax_bwd_workspace_bytes(g.N, E, D)), dtype=torch.uint8,
                                    device=dev)
     ws = _bwd_ws[key]
-    if getattr(g, 'csr_dst', None) is None:      # destination of every dst-CSR position (graph-static)
-        g.csr_dst = g.dst[g.csr.idx[:E].long()].contiguous() if E > 0 else g.dst
+    if getattr(g, 'csr_dst', None) is None:      # destination of every dst-CSR position (graph-static), padded by
+        pad = torch.zeros(64, dtype=torch.int32, device=dev)          # one 64-row window for the bulk copies
+        g.csr_dst = torch.cat([g.dst[g.csr.idx[:E].long()], pad]).contiguous() if E > 0 else pad
     if need_dx and dx is None:
         dx = torch.empty(rows, D, dtype=torch.float32, device=dev)
     dw = torch.empty(D, D, dtype=torch.float32, device=dev)
