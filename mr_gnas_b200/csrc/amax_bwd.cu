@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
 // No shared-memory read-modify-write, no atomics, fixed order -> deterministic.
 // Partials: part[cta][D][KW] (+ db in part_b[group][D]), folded in CTA order.
 // ---------------------------------------------------------------------------------------
-constexpr int kDwThreads = 512;
+// 32 warps per SM: the kernel is latency bound (round-2 ncu: 0.44 instructions per cycle and scheduler with 16
+// warps), so the column range is split in two slices per destination range above D = 104 -- 4 accumulator
+// registers per owned feature instead of 7 -- which lets 1,024 threads fit in the register file.
+constexpr int kDwThreads = 1024;
 constexpr int kDwWarps = kDwThreads / 32;
-constexpr int kDwStages = 3;
+constexpr int kDwStages = 4;
 constexpr int kPop = 3;         // rows popped per feature and batch
 
 template <int NF, int NT>
@@ -345,7 +348,7 @@ __global__ void amax_bwd_dw_fold_kernel(const float* __restrict__ part, const fl
 
 using namespace mrg;
 
-static inline int dw_kslices(int D) { return D > 208 ? 2 : 1; }
+static inline int dw_kslices(int D) { return D > 104 ? 2 : 1; }
 static inline int dw_kw(int D, int ks) { return ((D + ks - 1) / ks + 3) / 4 * 4; }
 static inline int dw_grid(int D) {
   const int ks = dw_kslices(D);
@@ -424,9 +427,8 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
                                                                part_b);                                           \
   } while (0)
     if (nf <= 4 && nt <= 2) LDW(4, 2);
-    else if (nf <= 8 && nt <= 4) LDW(8, 4);
-    else if (nf <= 13 && nt <= 7) LDW(13, 7);
-    else LDW(16, 4);
+    else if (nf <= 7 && nt <= 4) LDW(7, 4);
+    else LDW(8, 4);
 #undef LDW
     const int n = D * D + D;
     amax_bwd_dw_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, part_b, grid, ks, D, KW, dW, db);

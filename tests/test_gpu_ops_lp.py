@@ -150,6 +150,19 @@ def test_lp_op_oracle_seeded(dev, name, D):
         x = torch.relu(x)
     xin = torch.randn(rows, D)
     cot = torch.randn(N if (name.startswith("a_") or name.endswith("_last")) else M, D)
+    if name == "a_mean":
+        # ReLU'(m) is discontinuous at m = 0: a pre-activation within GEMM rounding distance of zero (the edge-tile
+        # GEMM runs as 3xTF32 on the tensor cores, ~1e-6 relative to MKL's fp32) may be gated differently by the
+        # two implementations and moves a whole gradient row.  Re-draw the few message rows that have such an
+        # entry so that the comparison is about arithmetic, not about which side of zero a rounding error fell.
+        W0, b0 = op.linear.weight.detach(), op.linear.bias.detach()
+        for _ in range(20):
+            m0 = torch.nn.functional.linear(x[:E], W0, b0)
+            bad = (m0.abs() < 1e-4 * float(m0.abs().max())).any(1).nonzero().view(-1)
+            if bad.numel() == 0:
+                break
+            x[bad] = torch.relu(torch.randn(bad.numel(), D))
+        assert bad.numel() == 0
     # oracle (CPU fp32)
     P = {"op." + k: v.detach().clone().requires_grad_(True) for k, v in op.state_dict().items()}
     xo, xino = x.clone().requires_grad_(True), xin.clone().requires_grad_(True)
