@@ -149,10 +149,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
 // No shared-memory read-modify-write, no atomics, fixed order -> deterministic.
 // Partials: part[cta][D][KW] (+ db in part_b[group][D]), folded in CTA order.
 // ---------------------------------------------------------------------------------------
-// 32 warps per SM: the kernel is latency bound (round-2 ncu: 0.44 instructions per cycle and scheduler with 16
-// warps), so the column range is split in two slices per destination range above D = 104 -- 4 accumulator
-// registers per owned feature instead of 7 -- which lets 1,024 threads fit in the register file.
-constexpr int kDwThreads = 1024;
+// Measured (round 2): the time of this kernel is (windows per CTA) x (a fixed ~7 us per window), whatever the
+// instruction count -- 32 warps with two column slices (twice the windows per CTA) took 650 us against 413 us.
+// The fixed cost was the exposed L2 latency of the g gather (one dependent round per pop batch, inside the
+// per-window barrier).  The first batch of window b+1 is therefore popped and its g loads issued BEFORE window b
+// is accumulated; the ring is 4 deep so that waiting for window b+1 early still leaves two windows in flight.
+constexpr int kDwThreads = 512;
 constexpr int kDwWarps = kDwThreads / 32;
 constexpr int kDwStages = 4;
 constexpr int kPop = 3;         // rows popped per feature and batch
@@ -164,13 +166,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     float* __restrict__ part, float* __restrict__ part_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | full[kDwStages] u64 |
-  //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32
+  //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32 | sc[KW] | sh[KW]
   float* xs = reinterpret_cast<float*>(smem_raw);
   unsigned long long* fm = reinterpret_cast<unsigned long long*>(xs + (size_t)kDwStages * kWin * KW);
   int32_t* wd = reinterpret_cast<int32_t*>(fm + (size_t)kDwStages * D);
   uint64_t* full = reinterpret_cast<uint64_t*>(wd + kDwStages * kWin);
   int32_t* lr = reinterpret_cast<int32_t*>(full + kDwStages);
   float* lg = reinterpret_cast<float*>(lr + kDwWarps * NF * kPop);
+  float* sc_s = lg + kDwWarps * NF * kPop + ((kDwWarps * NF * kPop) & 1 ? 1 : 0) + 2;   // keep 16-byte alignment
+  sc_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sc_s) + 15) & ~(uintptr_t)15);
+  float* sh_s = sc_s + KW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x % kslices, group = blockIdx.x / kslices, ngroups = gridDim.x / kslices;
   const int k0 = slice * KW;
@@ -187,11 +192,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
   }
   // in-place activation: thread t owns float4 column group t % 64 (when < kw4) of rows t / 64 + 8 i
   const int my_c4 = threadIdx.x & 63, my_r0 = threadIdx.x >> 6;
-  float4 my_sc = make_float4(1.f, 1.f, 1.f, 1.f), my_sh = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (affine && my_c4 < kw4) {
-    my_sc = ldg4(x.scale + k0 + 4 * my_c4);
-    my_sh = ldg4(x.shift + k0 + 4 * my_c4);
-  }
+  if (affine)
+    for (int c = threadIdx.x; c < kw; c += blockDim.x) {
+      sc_s[c] = x.scale[k0 + c];
+      sh_s[c] = x.shift[k0 + c];
+    }
 
   float acc[NF][NT];
 #pragma unroll
@@ -235,15 +240,59 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     prefetch_eids(1);
     if (nb > 1) issue(1);
     prefetch_eids(2);
+    if (nb > 2) issue(2);
+    prefetch_eids(3);
+  }
+
+  // pop up to kPop rows (ascending) of this lane's feature from row set `m` of the window in stage `s` and issue
+  // the loads of their g values; nothing is consumed here, so the L2 latency overlaps whatever follows
+  unsigned long long mA = 0ull, mB = 0ull;
+  int cntA = 0, cntB = 0;
+  float gA[kPop], gB[kPop];
+  int rA[kPop], rB[kPop];
+  auto pop = [&](unsigned long long& m, int s, int& cnt, int* rq, float* gq) {
+    const int32_t* wd_s = wd + s * kWin;
+    cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kPop; ++q) {
+      rq[q] = 0;
+      gq[q] = 0.f;
+      if (m) {
+        rq[q] = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        gq[q] = __ldg(g + (size_t)wd_s[rq[q]] * D + f_l);
+        ++cnt;
+      }
+    }
+  };
+  auto publish = [&](const int* rq, const float* gq) {     // lanes < NF: my batch -> the warp's shared list
+    if (lane < NF) {
+#pragma unroll
+      for (int q = 0; q < kPop; ++q) {
+        lr_w[lane * kPop + q] = rq[q] * KW;
+        lg_w[lane * kPop + q] = gq[q];
+        db_acc += gq[q];
+      }
+    }
+    __syncwarp();
+  };
+  if (nb > 0) {
+    pipe::mbar_wait(full + 0, 0u);
+    mA = f_ok ? fm[f_l] : 0ull;
+    pop(mA, 0, cntA, rA, gA);
   }
 
   for (int b = 0; b < nb; ++b) {
     const int64_t w_lo = (W0 + b) * kWin;
     const int nrows = (int)min((int64_t)kWin, E - w_lo);
-    const int s = b % kDwStages;
-    pipe::mbar_wait(full + s, (uint32_t)(b / kDwStages) & 1u);
+    const int s = b % kDwStages;          // landed: waited for in the previous iteration / the prologue
     if ((affine || relu) && my_c4 < kw4) {
       float* col = xs + (size_t)s * kWin * KW + 4 * my_c4;
+      float4 my_sc = make_float4(1.f, 1.f, 1.f, 1.f), my_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (affine) {
+        my_sc = *reinterpret_cast<const float4*>(sc_s + 4 * my_c4);
+        my_sh = *reinterpret_cast<const float4*>(sh_s + 4 * my_c4);
+      }
       for (int r = my_r0; r < nrows; r += kDwThreads / 64) {
         float4 v = *reinterpret_cast<float4*>(col + (size_t)r * KW);
         if (affine) {
@@ -257,46 +306,23 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
       }
     }
     // generic-proxy writes of this window (and reads of window b-1) are ordered before the bulk copies that will
-    // overwrite the ring: proxy fence by every thread, then the CTA barrier, then warp 0 issues window b+2
+    // overwrite the ring: proxy fence by every thread, then the CTA barrier, then warp 0 issues window b+3
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (warp == 0 && b + 2 < nb) {
-      issue(b + 2);              // into the stage of window b-1, which everyone has left
-      prefetch_eids(b + 3);
+    if (warp == 0 && b + 3 < nb) {
+      issue(b + 3);              // into the stage of window b-1, which everyone has left
+      prefetch_eids(b + 4);
     }
     const float* st_lane = xs + (size_t)s * kWin * KW + lane;
-    const int32_t* wd_s = wd + s * kWin;
-
-    unsigned long long m = f_ok ? fm[(size_t)s * D + f_l] : 0ull;
-    while (__ballot_sync(0xffffffffu, m != 0ull)) {
-      // pop up to kPop rows of my feature (ascending) and fetch their g values: all loads of the batch in flight
-      int cnt = 0;
-      float gq[kPop];
-      int rq[kPop];
-#pragma unroll
-      for (int q = 0; q < kPop; ++q) {
-        rq[q] = 0;
-        gq[q] = 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < kPop; ++q) {
-        if (!__ballot_sync(0xffffffffu, m != 0ull)) break;     // warp-uniform: most features have 1-3 rows here
-        if (m) {
-          rq[q] = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          gq[q] = __ldg(g + (size_t)wd_s[rq[q]] * D + f_l);
-          ++cnt;
-        }
-      }
-      if (lane < NF) {
-#pragma unroll
-        for (int q = 0; q < kPop; ++q) {
-          lr_w[lane * kPop + q] = rq[q] * KW;
-          lg_w[lane * kPop + q] = gq[q];
-          db_acc += gq[q];
-        }
-      }
-      __syncwarp();
+    publish(rA, gA);                                   // first batch of window b (its g loads were issued a window ago)
+    if (b + 1 < nb) {                                  // first batch of window b+1: loads in flight during the FMAs
+      const int s1 = (b + 1) % kDwStages;
+      pipe::mbar_wait(full + s1, (uint32_t)((b + 1) / kDwStages) & 1u);
+      mB = f_ok ? fm[(size_t)s1 * D + f_l] : 0ull;
+      pop(mB, s1, cntB, rB, gB);
+    }
+    int cnt = cntA;
+    for (;;) {
 #pragma unroll
       for (int u = 0; u < NF; ++u) {
         const int cu = __shfl_sync(0xffffffffu, cnt, u);
@@ -308,6 +334,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
         }
       }
       __syncwarp();
+      if (!__ballot_sync(0xffffffffu, mA != 0ull)) break;
+      pop(mA, s, cnt, rA, gA);                         // features with more than kPop rows in this window (rare)
+      publish(rA, gA);
+    }
+    mA = mB;
+    cntA = cntB;
+#pragma unroll
+    for (int q = 0; q < kPop; ++q) {
+      rA[q] = rB[q];
+      gA[q] = gB[q];
     }
   }
   float* p = part + (size_t)blockIdx.x * D * KW;
@@ -348,7 +384,7 @@ __global__ void amax_bwd_dw_fold_kernel(const float* __restrict__ part, const fl
 
 using namespace mrg;
 
-static inline int dw_kslices(int D) { return D > 104 ? 2 : 1; }
+static inline int dw_kslices(int D) { return D > 208 ? 2 : 1; }
 static inline int dw_kw(int D, int ks) { return ((D + ks - 1) / ks + 3) / 4 * 4; }
 static inline int dw_grid(int D) {
   const int ks = dw_kslices(D);
@@ -356,7 +392,7 @@ static inline int dw_grid(int D) {
 }
 static inline size_t dw_smem(int D, int KW, int NF) {
   return (size_t)kDwStages * kWin * KW * 4 + (size_t)kDwStages * D * 8 + (size_t)kDwStages * kWin * 4 +
-         (size_t)kDwStages * 8 + (size_t)kDwWarps * NF * kPop * 8 + 128;
+         (size_t)kDwStages * 8 + (size_t)kDwWarps * NF * kPop * 8 + 2 * (size_t)KW * 4 + 256;
 }
 static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 static inline size_t dw_part_bytes(int D) {
@@ -427,8 +463,9 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
                                                                part_b);                                           \
   } while (0)
     if (nf <= 4 && nt <= 2) LDW(4, 2);
-    else if (nf <= 7 && nt <= 4) LDW(7, 4);
-    else LDW(8, 4);
+    else if (nf <= 8 && nt <= 4) LDW(8, 4);
+    else if (nf <= 13 && nt <= 7) LDW(13, 7);
+    else LDW(16, 4);
 #undef LDW
     const int n = D * D + D;
     amax_bwd_dw_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, part_b, grid, ks, D, KW, dW, db);
