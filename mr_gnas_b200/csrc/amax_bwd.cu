@@ -163,8 +163,12 @@ template <int NF, int NT>
 __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     const float* __restrict__ g, const unsigned long long* __restrict__ fmask, mrg_act x,
     const int32_t* __restrict__ eid, const int32_t* __restrict__ csr_dst, int64_t E, int D, int KW, int kslices,
-    float* __restrict__ part, float* __restrict__ part_b) {
+    float* __restrict__ part, float* __restrict__ part_b, long long* __restrict__ prof) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // optional phase timing (mrg_debug_set_dw_prof): cycles of warp 1 lane 0 per phase, summed over CTAs
+  long long t_aff = 0, t_bar = 0, t_pub = 0, t_wait = 0, t_acc = 0, t_mark = 0;
+  const bool do_prof = prof != nullptr && threadIdx.x == 32;
+#define DW_MARK(var) do { if (do_prof) { const long long now_ = clock64(); var += now_ - t_mark; t_mark = now_; } } while (0)
   // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | full[kDwStages] u64 |
   //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32 | sc[KW] | sh[KW]
   float* xs = reinterpret_cast<float*>(smem_raw);
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     pop(mA, 0, cntA, rA, gA);
   }
 
+  if (do_prof) t_mark = clock64();
   for (int b = 0; b < nb; ++b) {
     const int64_t w_lo = (W0 + b) * kWin;
     const int nrows = (int)min((int64_t)kWin, E - w_lo);
@@ -307,17 +312,21 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     }
     // generic-proxy writes of this window (and reads of window b-1) are ordered before the bulk copies that will
     // overwrite the ring: proxy fence by every thread, then the CTA barrier, then warp 0 issues window b+3
+    DW_MARK(t_aff);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    DW_MARK(t_bar);
     if (warp == 0 && b + 3 < nb) {
       issue(b + 3);              // into the stage of window b-1, which everyone has left
       prefetch_eids(b + 4);
     }
     const float* st_lane = xs + (size_t)s * kWin * KW + lane;
     publish(rA, gA);                                   // first batch of window b (its g loads were issued a window ago)
+    DW_MARK(t_pub);
     if (b + 1 < nb) {                                  // first batch of window b+1: loads in flight during the FMAs
       const int s1 = (b + 1) % kDwStages;
       pipe::mbar_wait(full + s1, (uint32_t)((b + 1) / kDwStages) & 1u);
+      DW_MARK(t_wait);
       mB = f_ok ? fm[(size_t)s1 * D + f_l] : 0ull;
       pop(mB, s1, cntB, rB, gB);
     }
@@ -345,7 +354,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
       rA[q] = rB[q];
       gA[q] = gB[q];
     }
+    DW_MARK(t_acc);
   }
+  if (do_prof) {
+    atomicAdd((unsigned long long*)prof + 0, (unsigned long long)t_aff);
+    atomicAdd((unsigned long long*)prof + 1, (unsigned long long)t_bar);
+    atomicAdd((unsigned long long*)prof + 2, (unsigned long long)t_pub);
+    atomicAdd((unsigned long long*)prof + 3, (unsigned long long)t_wait);
+    atomicAdd((unsigned long long*)prof + 4, (unsigned long long)t_acc);
+    atomicAdd((unsigned long long*)prof + 5, (unsigned long long)nb);
+  }
+#undef DW_MARK
   float* p = part + (size_t)blockIdx.x * D * KW;
 #pragma unroll
   for (int u = 0; u < NF; ++u) {
@@ -404,6 +423,14 @@ static inline size_t fmask_bytes(int64_t E, int D) {
   return align256((size_t)((E + kWin - 1) / kWin + 1) * D * sizeof(unsigned long long));
 }
 
+static long long* g_dw_prof = nullptr;
+/* debugging aid (not part of the data path): device buffer of 8 int64 that the dW kernel adds its per-phase cycle
+ * counts to (in-place activation, barrier, list publish, wait for the next window, accumulate, windows) */
+extern "C" int mrg_debug_set_dw_prof(long long* dev_buf) {
+  g_dw_prof = dev_buf;
+  return MRG_OK;
+}
+
 extern "C" size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D) {
   (void)N;
   return dw_part_bytes(D) + rmask_bytes(E) + fmask_bytes(E, D) + 512;   // dW partials | rmask | fmask | counter
@@ -460,7 +487,7 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
     e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw smem attr");                                           \
     amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, fmask, x, csr_eid, csr_dst, E, D, KW, ks, part,  \
-                                                               part_b);                                           \
+                                                               part_b, g_dw_prof);                                \
   } while (0)
     if (nf <= 4 && nt <= 2) LDW(4, 2);
     else if (nf <= 8 && nt <= 4) LDW(8, 4);
