@@ -166,9 +166,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     float* __restrict__ part, float* __restrict__ part_b, long long* __restrict__ prof) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // optional phase timing (mrg_debug_set_dw_prof): cycles of warp 1 lane 0 per phase, summed over CTAs
+  // (compiled in only with -DMRG_DW_PROF: the counters cost registers)
+#ifdef MRG_DW_PROF
   long long t_aff = 0, t_bar = 0, t_pub = 0, t_wait = 0, t_acc = 0, t_mark = 0;
   const bool do_prof = prof != nullptr && threadIdx.x == 32;
 #define DW_MARK(var) do { if (do_prof) { const long long now_ = clock64(); var += now_ - t_mark; t_mark = now_; } } while (0)
+#else
+  (void)prof;
+#define DW_MARK(var) do { } while (0)
+#endif
   // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | full[kDwStages] u64 |
   //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32 | sc[KW] | sh[KW]
   float* xs = reinterpret_cast<float*>(smem_raw);
@@ -286,7 +292,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     pop(mA, 0, cntA, rA, gA);
   }
 
+#ifdef MRG_DW_PROF
   if (do_prof) t_mark = clock64();
+#endif
   for (int b = 0; b < nb; ++b) {
     const int64_t w_lo = (W0 + b) * kWin;
     const int nrows = (int)min((int64_t)kWin, E - w_lo);
@@ -356,6 +364,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     }
     DW_MARK(t_acc);
   }
+#ifdef MRG_DW_PROF
   if (do_prof) {
     atomicAdd((unsigned long long*)prof + 0, (unsigned long long)t_aff);
     atomicAdd((unsigned long long*)prof + 1, (unsigned long long)t_bar);
@@ -364,6 +373,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     atomicAdd((unsigned long long*)prof + 4, (unsigned long long)t_acc);
     atomicAdd((unsigned long long*)prof + 5, (unsigned long long)nb);
   }
+#endif
 #undef DW_MARK
   float* p = part + (size_t)blockIdx.x * D * KW;
 #pragma unroll
