@@ -220,39 +220,40 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
   float* lg_w = lg + warp * NF * kPop;
   __syncthreads();
 
-  // ---- producer state (warp 0): edge ids of rows lane, lane + 32 of the NEXT window to issue
-  int32_t e_pf0 = 0, e_pf1 = 0;
+  // ---- copy issue, spread over all warps (a single issuing warp arrived late at every window barrier and the
+  // other 15 waited for it: 31 % of the stall samples): warp w copies rows w, w+16, w+32, w+48 of a window, one
+  // cp.async.bulk per lane 0..3; their edge ids are prefetched one window ahead
+  int32_t e_pf = 0;
+  const int my_row = warp + kDwWarps * lane;          // lanes < kWin / kDwWarps
   auto prefetch_eids = [&](int b) {
-    if (b < nb) {
-      const int64_t w_lo = (W0 + b) * kWin;
-      e_pf0 = w_lo + lane < E ? __ldg(eid + w_lo + lane) : 0;
-      e_pf1 = w_lo + lane + 32 < E ? __ldg(eid + w_lo + lane + 32) : 0;
+    if (b < nb && lane < kWin / kDwWarps) {
+      const int64_t p = (W0 + b) * kWin + my_row;
+      e_pf = p < E ? __ldg(eid + p) : 0;
     }
   };
-  auto issue = [&](int b) {     // warp 0 only; the stage must have been released by a __syncthreads
+  auto issue = [&](int b) {     // every warp; the stage must have been released by a __syncthreads
     const int64_t w_lo = (W0 + b) * kWin;
     const int nrows = (int)min((int64_t)kWin, E - w_lo);
     const int s = b % kDwStages;
     float* st = xs + (size_t)s * kWin * KW;
     const uint32_t row_bytes = (uint32_t)kw * 4u;
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
+      // (a row copy of another warp may complete before this expect_tx: the transaction count of an mbarrier is
+      //  signed, the phase cannot complete before this arrival)
       pipe::mbar_expect_tx(full + s, (uint32_t)nrows * row_bytes + (uint32_t)D * 8u + (uint32_t)kWin * 4u);
       pipe::bulk_g2s(fm + (size_t)s * D, fmask + (size_t)(W0 + b) * D, (uint32_t)D * 8u, full + s);
       pipe::bulk_g2s(wd + s * kWin, csr_dst + w_lo, (uint32_t)kWin * 4u, full + s);   // csr_dst is padded by kWin entries
     }
-    if (lane < nrows) pipe::bulk_g2s(st + (size_t)lane * KW, x.data + (size_t)e_pf0 * D + k0, row_bytes, full + s);
-    if (lane + 32 < nrows)
-      pipe::bulk_g2s(st + (size_t)(lane + 32) * KW, x.data + (size_t)e_pf1 * D + k0, row_bytes, full + s);
+    if (lane < kWin / kDwWarps && my_row < nrows)
+      pipe::bulk_g2s(st + (size_t)my_row * KW, x.data + (size_t)e_pf * D + k0, row_bytes, full + s);
   };
-  if (warp == 0) {
-    prefetch_eids(0);
-    if (nb > 0) issue(0);
-    prefetch_eids(1);
-    if (nb > 1) issue(1);
-    prefetch_eids(2);
-    if (nb > 2) issue(2);
-    prefetch_eids(3);
-  }
+  prefetch_eids(0);
+  if (nb > 0) issue(0);
+  prefetch_eids(1);
+  if (nb > 1) issue(1);
+  prefetch_eids(2);
+  if (nb > 2) issue(2);
+  prefetch_eids(3);
 
   // pop up to kPop rows (ascending) of this lane's feature from row set `m` of the window in stage `s` and issue
   // the loads of their g values; nothing is consumed here, so the L2 latency overlaps whatever follows
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     DW_MARK(t_bar);
-    if (warp == 0 && b + 3 < nb) {
+    if (b + 3 < nb) {
       issue(b + 3);              // into the stage of window b-1, which everyone has left
       prefetch_eids(b + 4);
     }
