@@ -269,8 +269,8 @@ def main():
     ap.add_argument("--partition", action="store_true", help="same as --mode partition")
     ap.add_argument("--dp", action="store_true", help="same as --mode dp")
     ap.add_argument("--strong", action="store_true",
-                    help="partition mode: keep the C1 graph at every N (strong scaling) instead of growing entities "
-                         "and triples with N (weak scaling, the default: per-GPU edge work stays that of C1)")
+                    help="partition mode: keep the C1 graph at every N (strong scaling) instead of growing the "
+                         "triples with N (weak scaling, the default: per-GPU edge work stays that of C1)")
     ap.add_argument("--no-c4", action="store_true", help="skip the AM-shaped NC partition sub-record (c4_partition)")
     ap.add_argument("--c4-scale", type=float, default=1.0)
     ap.add_argument("--c4-steps", type=int, default=3)
@@ -300,7 +300,9 @@ def main():
     part_mode = world > 1 and mode in ("auto", "partition")
     grow = world if (part_mode and not args.strong) else 1
     N0, R, T0, D = CONFIGS[args.workload]
-    N, T = N0 * grow, T0 * grow          # weak scaling: the C1 degree law on `grow` x the entities and triples
+    # weak scaling: `grow` x the C1 triples over the C1 entity set (same generator law), so every GPU's edge-level
+    # work is that of C1 while the replicated entity table does not grow with the GPU count
+    N, T = N0, T0 * grow
     trip = synth_kg(N, R, T, seed=0)
     E, M, B = 2 * T, 2 * T + N, args.batch
     if part_mode:
@@ -537,7 +539,7 @@ def main():
 
     if rank == 0:
         scal = "strong scaling on the C1 graph" if args.strong else \
-            f"weak scaling: C1 degree law on {grow}x entities and triples"
+            f"weak scaling: {grow}x the C1 triples over the C1 entities (per-GPU edge work = C1's)"
         par = "none (one device)" if world == 1 else (
             f"dst-partition x{world}: 1-D destination ranges balanced by in-edges, NCCL halo all-gather, global "
             f"BatchNorm statistics, entity-sharded 1-N scoring, one shared query batch; {scal}" if part_mode else
