@@ -601,6 +601,14 @@ class LinearTC(torch.autograd.Function):
         return dx, dw, db
 
 
+def linear_fn(x, weight, bias):
+    """x @ weight.T (+ bias): tcgen05 (3xTF32) for large tiles, the library GEMM for small ones."""
+    if USE_TC_LINEAR and x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 \
+            and x.shape[0] >= 1024:
+        return LinearTC.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 def linear(module, x):
     """module(x) for an nn.Linear, on the tensor-core path when the shapes allow it."""
     if USE_TC_LINEAR and x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0 and module.weight.shape[0] % 8 == 0 \
