@@ -286,6 +286,8 @@ int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t*
  * extra entries (whole 64-row windows are bulk-copied).  The call first
  * turns `arg` into two bit tables over CSR positions (workspace), which both products then walk. */
 size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D);
+/* debugging aid: 8 x int64 device buffer receiving the dW kernel's per-phase cycle counts (NULL switches it off) */
+int mrg_debug_set_dw_prof(long long* dev_buf);
 int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const float* W, const int32_t* csr_ptr,
                  const int32_t* csr_eid, const int32_t* csr_dst, const int32_t* chunk_first,
                  const int32_t* chunk_seg, int64_t N, int64_t E, int64_t max_chunks, int32_t D, float* dX, float* dW,

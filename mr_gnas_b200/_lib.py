@@ -78,6 +78,7 @@ _SIGNATURES = {
     "mrg_amax_tc_fwd": (I32, [MrgAct, P, P, P, P, I64, I64, I32, MrgAct, P, P, P, SZ, P]),
     "mrg_amax_bwd_workspace_bytes": (SZ, [I64, I64, I32]),
     "mrg_amax_bwd": (I32, [P, P, MrgAct, P, P, P, P, P, P, I64, I64, I64, I32, P, P, P, P, SZ, P]),
+    "mrg_debug_set_dw_prof": (I32, [P]),
     "mrg_labels_from_csr": (I32, [P, P, I64, I64, I64, F32, F32, P, P]),
     "mrg_filtered_rank": (I32, [P, P, P, I64, I64, P, P]),
     "mrg_distmult_bce_supported": (I32, [I32]),

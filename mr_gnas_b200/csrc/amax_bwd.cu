@@ -135,106 +135,247 @@ __global__ void __launch_bounds__(kBwdThreads, 1) amax_bwd_dx_kernel(
 
 // ---------------------------------------------------------------------------------------
 // dW / db.  Every (destination, feature) pair routes g[n,f] to ONE edge row, so dW^T is a sum of
-// N*D rank-1 contributions g[n,f] * x(arg[n,f],:).
-//
-// Warp w of a CTA owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS (acc[u][t]: feature
-// w*NF+u, column k0 + lane + 32 t); the CTA owns a contiguous range of 64-row windows of dst-CSR positions.  For
-// every window lane u reads the 64-bit row set of its feature (fmask) and the warp walks the set bits: the x row
-// of a pair is read STRAIGHT from global memory through L1 (7 coalesced 128-byte requests at D = 200), activated
-// in registers (lazy BatchNorm + ReLU) and accumulated.  The 16 warps of a CTA sweep the same window range, so a
-// row is fetched from HBM once and the ~5 further features routed to it hit L1/L2; the rows of the NEXT window are
-// prefetched to L2 while the current one is processed.
-//
-// Round-2 history (profiles/r02_ncu_top_kernels.md): the shared-memory staged versions -- per-thread cp.async,
-// then cp.async.bulk + mbarrier rings, with the routing prefetched a window ahead -- all sat at ~7 us per window
-// whatever their instruction count: one CTA-wide barrier per window made every window cost what its slowest warp
-// cost (31 % of the stall samples on that barrier, 0.44 instructions per cycle and scheduler).  Without a staging
-// buffer there is nothing to hand over and no barrier: warps run independently.
-// No atomics, one owner per accumulator, fixed order (windows ascending, rows ascending) -> deterministic.
+// N*D rank-1 contributions g[n,f] * x(arg[n,f],:).  Each CTA owns a contiguous range of 64-row windows of
+// dst-CSR positions and streams the x rows of that range ONCE through a 3-stage shared-memory ring:
+//   * warp 0 issues one cp.async.bulk per row (800 B at D=200; edge ids prefetched one window ahead, so the issue
+//     never waits on a load) plus the window's fmask row and destination ids; completion by mbarrier expect_tx.
+//     Round-2 profile of the per-thread cp.async version: 15 % of the instructions and 29 % of the stall samples sat
+//     in the copy loop (address arithmetic, waiting for the edge ids);
+//   * lazy BatchNorm + ReLU is applied in place by all threads, one float4 column group per thread (scale / shift
+//     in registers), then one __syncthreads;
+//   * warp w owns the dW rows f in [w*NF, (w+1)*NF) with the accumulators in REGISTERS (acc[u][t]: feature w*NF+u,
+//     column k0 + lane + 32 t): lane u reads the 64-bit row set of its feature, the warp pops rows (ascending) into
+//     a small shared list, fetches their g values in one parallel round and accumulates feature by feature.
+// No shared-memory read-modify-write, no atomics, fixed order -> deterministic.
 // Partials: part[cta][D][KW] (+ db in part_b[group][D]), folded in CTA order.
 // ---------------------------------------------------------------------------------------
+// Measured (round 2): the time of this kernel is (windows per CTA) x (a fixed ~7 us per window), whatever the
+// instruction count -- 32 warps with two column slices (twice the windows per CTA) took 650 us against 413 us.
+// The fixed cost was the exposed L2 latency of the g gather (one dependent round per pop batch, inside the
+// per-window barrier).  The first batch of window b+1 is therefore popped and its g loads issued BEFORE window b
+// is accumulated; the ring is 4 deep so that waiting for window b+1 early still leaves two windows in flight.
 constexpr int kDwThreads = 512;
 constexpr int kDwWarps = kDwThreads / 32;
+constexpr int kDwStages = 4;
+constexpr int kPop = 3;         // rows popped per feature and batch
 
 template <int NF, int NT>
 __global__ void __launch_bounds__(kDwThreads, 1) amax_bwd_dw_kernel(
     const float* __restrict__ g, const unsigned long long* __restrict__ fmask, mrg_act x,
     const int32_t* __restrict__ eid, const int32_t* __restrict__ csr_dst, int64_t E, int D, int KW, int kslices,
-    float* __restrict__ part, float* __restrict__ part_b) {
+    float* __restrict__ part, float* __restrict__ part_b, long long* __restrict__ prof) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // optional phase timing (mrg_debug_set_dw_prof): cycles of warp 1 lane 0 per phase, summed over CTAs
+  // (compiled in only with -DMRG_DW_PROF: the counters cost registers)
+#ifdef MRG_DW_PROF
+  long long t_aff = 0, t_bar = 0, t_pub = 0, t_wait = 0, t_acc = 0, t_mark = 0;
+  const bool do_prof = prof != nullptr && threadIdx.x == 32;
+#define DW_MARK(var) do { if (do_prof) { const long long now_ = clock64(); var += now_ - t_mark; t_mark = now_; } } while (0)
+#else
+  (void)prof;
+#define DW_MARK(var) do { } while (0)
+#endif
+  // layout: xs[kDwStages][kWin][KW] f32 | fm[kDwStages][D] u64 | wd[kDwStages][kWin] i32 | full[kDwStages] u64 |
+  //         lr[warps][NF][kPop] i32 | lg[warps][NF][kPop] f32 | sc[KW] | sh[KW]
+  float* xs = reinterpret_cast<float*>(smem_raw);
+  unsigned long long* fm = reinterpret_cast<unsigned long long*>(xs + (size_t)kDwStages * kWin * KW);
+  int32_t* wd = reinterpret_cast<int32_t*>(fm + (size_t)kDwStages * D);
+  uint64_t* full = reinterpret_cast<uint64_t*>(wd + kDwStages * kWin);
+  int32_t* lr = reinterpret_cast<int32_t*>(full + kDwStages);
+  float* lg = reinterpret_cast<float*>(lr + kDwWarps * NF * kPop);
+  float* sc_s = lg + kDwWarps * NF * kPop + ((kDwWarps * NF * kPop) & 1 ? 1 : 0) + 2;   // keep 16-byte alignment
+  sc_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sc_s) + 15) & ~(uintptr_t)15);
+  float* sh_s = sc_s + KW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x % kslices, group = blockIdx.x / kslices, ngroups = gridDim.x / kslices;
   const int k0 = slice * KW;
-  const int kw = min(KW, D - k0);   // valid columns of this slice
+  const int kw = min(KW, D - k0);   // valid columns of this slice (multiple of 4)
+  const int kw4 = kw >> 2;
   const bool affine = x.scale != nullptr, relu = x.relu != 0;
   const int64_t nwin = (E + kWin - 1) / kWin;
   const int64_t W0 = nwin * group / ngroups, W1 = nwin * (group + 1) / ngroups;
+  const int nb = (int)(W1 - W0);
 
-  float acc[NF][NT], sc[NT], sh[NT];
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const int k = lane + 32 * t;
-    sc[t] = (affine && k < kw) ? __ldg(x.scale + k0 + k) : 1.f;
-    sh[t] = (affine && k < kw) ? __ldg(x.shift + k0 + k) : 0.f;
-#pragma unroll
-    for (int u = 0; u < NF; ++u) acc[u][t] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) pipe::mbar_init(full + s, 1);
+    pipe::fence_barrier_init();
   }
-  float db_acc = 0.f;
-  const int f_l = warp * NF + lane;                 // the feature whose row set this lane holds
-  const bool f_ok = lane < NF && f_l < D;
-  const float* xcol = x.data + k0 + lane;
-  const float* gcol = g + warp * NF;
+  // in-place activation: thread t owns float4 column group t % 64 (when < kw4) of rows t / 64 + 8 i
+  const int my_c4 = threadIdx.x & 63, my_r0 = threadIdx.x >> 6;
+  if (affine)
+    for (int c = threadIdx.x; c < kw; c += blockDim.x) {
+      sc_s[c] = x.scale[k0 + c];
+      sh_s[c] = x.shift[k0 + c];
+    }
 
-  // per-window state, loaded one window ahead: row set of my feature, edge id + destination of rows lane, lane + 32
-  unsigned long long m_n = 0ull;
-  int32_t e0_n = 0, e1_n = 0, d0_n = 0, d1_n = 0;
-  auto load_window = [&](int64_t w) {
-    m_n = 0ull;
-    if (w < W1) {
-      const int64_t p0 = w * kWin + lane, p1 = p0 + 32;
-      if (f_ok) m_n = __ldg(fmask + (size_t)w * D + f_l);
-      e0_n = p0 < E ? __ldg(eid + p0) : 0;
-      e1_n = p1 < E ? __ldg(eid + p1) : 0;
-      d0_n = __ldg(csr_dst + p0);            // csr_dst is padded by one window
-      d1_n = __ldg(csr_dst + p1);
+  float acc[NF][NT];
+#pragma unroll
+  for (int u = 0; u < NF; ++u)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[u][t] = 0.f;
+  float db_acc = 0.f;
+  const int f_l = warp * NF + lane;                 // the feature whose row set this lane pops
+  const bool f_ok = lane < NF && f_l < D;
+  int32_t* lr_w = lr + warp * NF * kPop;
+  float* lg_w = lg + warp * NF * kPop;
+  __syncthreads();
+
+  // ---- copy issue, spread over all warps (a single issuing warp arrived late at every window barrier and the
+  // other 15 waited for it: 31 % of the stall samples): warp w copies rows w, w+16, w+32, w+48 of a window, one
+  // cp.async.bulk per lane 0..3; their edge ids are prefetched one window ahead
+  int32_t e_pf = 0;
+  const int my_row = warp + kDwWarps * lane;          // lanes < kWin / kDwWarps
+  auto prefetch_eids = [&](int b) {
+    if (b < nb && lane < kWin / kDwWarps) {
+      const int64_t p = (W0 + b) * kWin + my_row;
+      e_pf = p < E ? __ldg(eid + p) : 0;
     }
   };
-  load_window(W0);
-  for (int64_t w = W0; w < W1; ++w) {
-    const unsigned long long m = m_n;
-    const int32_t e0 = e0_n, e1 = e1_n, d0 = d0_n, d1 = d1_n;
-    load_window(w + 1);
-    // rows of the next window towards L2 / L1 while this one is processed: warp w takes rows w, w+16, w+32, w+48
-    if (w + 1 < W1) {
+  auto issue = [&](int b) {     // every warp; the stage must have been released by a __syncthreads
+    const int64_t w_lo = (W0 + b) * kWin;
+    const int nrows = (int)min((int64_t)kWin, E - w_lo);
+    const int s = b % kDwStages;
+    float* st = xs + (size_t)s * kWin * KW;
+    const uint32_t row_bytes = (uint32_t)kw * 4u;
+    if (threadIdx.x == 0) {
+      // (a row copy of another warp may complete before this expect_tx: the transaction count of an mbarrier is
+      //  signed, the phase cannot complete before this arrival)
+      pipe::mbar_expect_tx(full + s, (uint32_t)nrows * row_bytes + (uint32_t)D * 8u + (uint32_t)kWin * 4u);
+      pipe::bulk_g2s(fm + (size_t)s * D, fmask + (size_t)(W0 + b) * D, (uint32_t)D * 8u, full + s);
+      pipe::bulk_g2s(wd + s * kWin, csr_dst + w_lo, (uint32_t)kWin * 4u, full + s);   // csr_dst is padded by kWin entries
+    }
+    if (lane < kWin / kDwWarps && my_row < nrows)
+      pipe::bulk_g2s(st + (size_t)my_row * KW, x.data + (size_t)e_pf * D + k0, row_bytes, full + s);
+  };
+  prefetch_eids(0);
+  if (nb > 0) issue(0);
+  prefetch_eids(1);
+  if (nb > 1) issue(1);
+  prefetch_eids(2);
+  if (nb > 2) issue(2);
+  prefetch_eids(3);
+
+  // pop up to kPop rows (ascending) of this lane's feature from row set `m` of the window in stage `s` and issue
+  // the loads of their g values; nothing is consumed here, so the L2 latency overlaps whatever follows
+  unsigned long long mA = 0ull, mB = 0ull;
+  int cntA = 0, cntB = 0;
+  float gA[kPop], gB[kPop];
+  int rA[kPop], rB[kPop];
+  auto pop = [&](unsigned long long& m, int s, int& cnt, int* rq, float* gq) {
+    const int32_t* wd_s = wd + s * kWin;
+    cnt = 0;
 #pragma unroll
-      for (int i = 0; i < kWin / kDwWarps; ++i) {
-        const int r = warp + kDwWarps * i;
-        const int32_t e = __shfl_sync(0xffffffffu, r < 32 ? e0_n : e1_n, r & 31);
-        if (lane < NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(xcol - lane + (size_t)e * D + 32 * lane));
+    for (int q = 0; q < kPop; ++q) {
+      rq[q] = 0;
+      gq[q] = 0.f;
+      if (m) {
+        rq[q] = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        gq[q] = __ldg(g + (size_t)wd_s[rq[q]] * D + f_l);
+        ++cnt;
       }
     }
+  };
+  auto publish = [&](const int* rq, const float* gq) {     // lanes < NF: my batch -> the warp's shared list
+    if (lane < NF) {
 #pragma unroll
-    for (int u = 0; u < NF; ++u) {
-      unsigned long long mu = __shfl_sync(0xffffffffu, m, u);
-      while (mu) {
-        const int r = __ffsll((long long)mu) - 1;
-        mu &= mu - 1;
-        const int32_t e = __shfl_sync(0xffffffffu, r < 32 ? e0 : e1, r & 31);
-        const int32_t n = __shfl_sync(0xffffffffu, r < 32 ? d0 : d1, r & 31);
-        const float gv = __ldg(gcol + (size_t)n * D + u);
-        const float* row = xcol + (size_t)e * D;
-        float v[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) v[t] = (lane + 32 * t < kw) ? __ldg(row + 32 * t) : 0.f;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          float a = fmaf(sc[t], v[t], sh[t]);
-          if (relu) a = fmaxf(a, 0.f);
-          acc[u][t] = fmaf(gv, a, acc[u][t]);
-        }
-        if (lane == u) db_acc += gv;
+      for (int q = 0; q < kPop; ++q) {
+        lr_w[lane * kPop + q] = rq[q] * KW;
+        lg_w[lane * kPop + q] = gq[q];
+        db_acc += gq[q];
       }
     }
+    __syncwarp();
+  };
+  if (nb > 0) {
+    pipe::mbar_wait(full + 0, 0u);
+    mA = f_ok ? fm[f_l] : 0ull;
+    pop(mA, 0, cntA, rA, gA);
   }
+
+#ifdef MRG_DW_PROF
+  if (do_prof) t_mark = clock64();
+#endif
+  for (int b = 0; b < nb; ++b) {
+    const int64_t w_lo = (W0 + b) * kWin;
+    const int nrows = (int)min((int64_t)kWin, E - w_lo);
+    const int s = b % kDwStages;          // landed: waited for in the previous iteration / the prologue
+    if ((affine || relu) && my_c4 < kw4) {
+      float* col = xs + (size_t)s * kWin * KW + 4 * my_c4;
+      float4 my_sc = make_float4(1.f, 1.f, 1.f, 1.f), my_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (affine) {
+        my_sc = *reinterpret_cast<const float4*>(sc_s + 4 * my_c4);
+        my_sh = *reinterpret_cast<const float4*>(sh_s + 4 * my_c4);
+      }
+      for (int r = my_r0; r < nrows; r += kDwThreads / 64) {
+        float4 v = *reinterpret_cast<float4*>(col + (size_t)r * KW);
+        if (affine) {
+          v.x = fmaf(my_sc.x, v.x, my_sh.x); v.y = fmaf(my_sc.y, v.y, my_sh.y);
+          v.z = fmaf(my_sc.z, v.z, my_sh.z); v.w = fmaf(my_sc.w, v.w, my_sh.w);
+        }
+        if (relu) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(col + (size_t)r * KW) = v;
+      }
+    }
+    // generic-proxy writes of this window (and reads of window b-1) are ordered before the bulk copies that will
+    // overwrite the ring: proxy fence by every thread, then the CTA barrier, then warp 0 issues window b+3
+    DW_MARK(t_aff);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    DW_MARK(t_bar);
+    if (b + 3 < nb) {
+      issue(b + 3);              // into the stage of window b-1, which everyone has left
+      prefetch_eids(b + 4);
+    }
+    const float* st_lane = xs + (size_t)s * kWin * KW + lane;
+    publish(rA, gA);                                   // first batch of window b (its g loads were issued a window ago)
+    DW_MARK(t_pub);
+    if (b + 1 < nb) {                                  // first batch of window b+1: loads in flight during the FMAs
+      const int s1 = (b + 1) % kDwStages;
+      pipe::mbar_wait(full + s1, (uint32_t)((b + 1) / kDwStages) & 1u);
+      DW_MARK(t_wait);
+      mB = f_ok ? fm[(size_t)s1 * D + f_l] : 0ull;
+      pop(mB, s1, cntB, rB, gB);
+    }
+    int cnt = cntA;
+    for (;;) {
+#pragma unroll
+      for (int u = 0; u < NF; ++u) {
+        const int cu = __shfl_sync(0xffffffffu, cnt, u);
+        for (int q = 0; q < cu; ++q) {
+          const float gu = lg_w[u * kPop + q];
+          const float* row = st_lane + lr_w[u * kPop + q];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) acc[u][t] = fmaf(gu, row[32 * t], acc[u][t]);
+        }
+      }
+      __syncwarp();
+      if (!__ballot_sync(0xffffffffu, mA != 0ull)) break;
+      pop(mA, s, cnt, rA, gA);                         // features with more than kPop rows in this window (rare)
+      publish(rA, gA);
+    }
+    mA = mB;
+    cntA = cntB;
+#pragma unroll
+    for (int q = 0; q < kPop; ++q) {
+      rA[q] = rB[q];
+      gA[q] = gB[q];
+    }
+    DW_MARK(t_acc);
+  }
+#ifdef MRG_DW_PROF
+  if (do_prof) {
+    atomicAdd((unsigned long long*)prof + 0, (unsigned long long)t_aff);
+    atomicAdd((unsigned long long*)prof + 1, (unsigned long long)t_bar);
+    atomicAdd((unsigned long long*)prof + 2, (unsigned long long)t_pub);
+    atomicAdd((unsigned long long*)prof + 3, (unsigned long long)t_wait);
+    atomicAdd((unsigned long long*)prof + 4, (unsigned long long)t_acc);
+    atomicAdd((unsigned long long*)prof + 5, (unsigned long long)nb);
+  }
+#endif
+#undef DW_MARK
   float* p = part + (size_t)blockIdx.x * D * KW;
 #pragma unroll
   for (int u = 0; u < NF; ++u) {
@@ -279,6 +420,10 @@ static inline int dw_grid(int D) {
   const int ks = dw_kslices(D);
   return kNumSMs / ks * ks;
 }
+static inline size_t dw_smem(int D, int KW, int NF) {
+  return (size_t)kDwStages * kWin * KW * 4 + (size_t)kDwStages * D * 8 + (size_t)kDwStages * kWin * 4 +
+         (size_t)kDwStages * 8 + (size_t)kDwWarps * NF * kPop * 8 + 2 * (size_t)KW * 4 + 256;
+}
 static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 static inline size_t dw_part_bytes(int D) {
   const int ks = dw_kslices(D), KW = dw_kw(D, ks);
@@ -287,6 +432,14 @@ static inline size_t dw_part_bytes(int D) {
 static inline size_t rmask_bytes(int64_t E) { return align256((size_t)(E > 0 ? E : 1) * kRW * sizeof(uint32_t)); }
 static inline size_t fmask_bytes(int64_t E, int D) {
   return align256((size_t)((E + kWin - 1) / kWin + 1) * D * sizeof(unsigned long long));
+}
+
+static long long* g_dw_prof = nullptr;
+/* debugging aid (not part of the data path): device buffer of 8 int64 that the dW kernel adds its per-phase cycle
+ * counts to (in-place activation, barrier, list publish, wait for the next window, accumulate, windows) */
+extern "C" int mrg_debug_set_dw_prof(long long* dev_buf) {
+  g_dw_prof = dev_buf;
+  return MRG_OK;
 }
 
 extern "C" size_t mrg_amax_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D) {
@@ -341,10 +494,11 @@ extern "C" int mrg_amax_bwd(const float* g, const int32_t* arg, mrg_act x, const
     const int nf = (D + kDwWarps - 1) / kDwWarps, nt = (KW + 31) / 32;
 #define LDW(NF, NT)                                                                                               \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NF, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);      \
-    if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw carveout attr");                                       \
-    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, 0, st>>>(g, fmask, x, csr_eid, csr_dst, E, D, KW, ks, part,     \
-                                                            part_b);                                              \
+    const size_t smem = dw_smem(D, KW, NF);                                                                       \
+    e = cudaFuncSetAttribute(amax_bwd_dw_kernel<NF, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return cuda_fail(e, "amax_bwd dw smem attr");                                           \
+    amax_bwd_dw_kernel<NF, NT><<<grid, kDwThreads, smem, st>>>(g, fmask, x, csr_eid, csr_dst, E, D, KW, ks, part,  \
+                                                               part_b, g_dw_prof);                                \
   } while (0)
     if (nf <= 4 && nt <= 2) LDW(4, 2);
     else if (nf <= 8 && nt <= 4) LDW(8, 4);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""CUDA-event timing of mrg_amax_bwd at the C1 shape (with and without the dX product): a quick harness for
-iterating on the a_max backward kernels outside the full training step."""
+"""Phase timing of the a_max backward kernels at C1 (debugging aid): runs the README-genotype step eagerly with
+mrg_debug_set_dw_prof armed and prints the dW kernel's per-phase cycle shares, plus CUDA-event times of the
+dX-only and dW-only calls."""
 import os, sys, types
 import torch, torch.nn as nn
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,6 +21,7 @@ out = K.AMaxTC.apply(x, lin.weight, lin.bias, g, True)
 arg = g.last_arg
 gout = torch.randn(N, D, device=dev)
 lib = _lib.load()
+prof = torch.zeros(8, dtype=torch.int64, device=dev)
 def run(need_dx, need_dw, n=5):
     ts = []
     for _ in range(n):
@@ -30,3 +32,12 @@ def run(need_dx, need_dw, n=5):
     return min(ts)
 print("full call (route + dX + dW + fold): %.3f ms" % run(True, True))
 print("without dX:                          %.3f ms" % run(False, True))
+lib.mrg_debug_set_dw_prof(prof.data_ptr())
+prof.zero_()
+run(False, True, n=1)
+lib.mrg_debug_set_dw_prof(None)
+p = prof.cpu().tolist()
+tot = sum(p[:5])
+print("dW phases (cycles of warp 1 summed over %d CTAs, %d windows): " % (148, p[5]))
+for name, v in zip(("in-place activation", "fence+barrier", "publish list", "wait next window", "prefetch+accumulate"), p[:5]):
+    print("  %-22s %6.1f %%   %8.0f cycles / window" % (name, 100 * v / tot, v / max(p[5], 1)))
