@@ -171,3 +171,57 @@ def test_batch_builders_match_real_reference_dataset(golden_dir):
         for b in range(len(items)):
             dense[b, idx[ptr[b]:ptr[b + 1]].long()] = pos
         assert torch.equal(dense, y_ref)
+
+
+def test_shim_lets_the_reference_scripts_import_this_package():
+    """mr_gnas_b200.shim: with the aliases installed the reference's own train/mr_lp_train.py and
+    search/mr_lp_search.py import UNCHANGED (their `models.*`, `dgl`, `utils.process_data`, `utils.utils_rgcn`,
+    `configs.genotypes` resolve to this package, `utils.utils` / `utils.data_set` / `models.architect_lp` to the
+    reference's files) and their own helper code builds the network and the 1-N items.  Needs the reference
+    checkout (build container only)."""
+    import importlib.util
+    import subprocess
+    import sys
+    ref = os.environ.get("MRG_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    code = r'''
+import sys, importlib.util, types
+import numpy as np, torch
+from mr_gnas_b200 import shim
+ref = shim.install(sys.argv[1])
+for rel in ("train/mr_lp_train.py", "search/mr_lp_search.py"):
+    spec = importlib.util.spec_from_file_location("ref_script", ref + "/" + rel)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                     # module scope only: imports + function definitions
+    import mr_gnas_b200
+    assert mod.Network.__module__.startswith("mr_gnas_b200."), mod.Network.__module__
+    assert mod.process.__module__ == "mr_gnas_b200.process_data"
+import models.operations_lp, models.architect_lp, utils.utils, configs.genotypes, dgl
+assert models.operations_lp.__name__ == "mr_gnas_b200.operations_lp"
+assert models.architect_lp.__file__.startswith(ref)          # the reference's own file
+assert utils.utils.__file__.startswith(ref)
+from mr_gnas_b200.graph import MRGraph
+assert dgl.DGLGraph is MRGraph
+# the script's own model construction path (mr_lp_train.py:101-129) on a small synthetic KG, on the host
+spec = importlib.util.spec_from_file_location("ref_train", ref + "/train/mr_lp_train.py")
+tr = importlib.util.module_from_spec(spec); spec.loader.exec_module(tr)
+genotype = eval("[Genotype(alpha_cell=[('pre_sub', 1, 0), ('f_sparse_comp', 2, 1), ('a_max', 3, 2)], concat_node=[3], score_func='sf_DisMult')]",
+                {"Genotype": configs.genotypes.Genotype})
+args = types.SimpleNamespace(feature_dim=16, drop_aggr=0.1, drop_op=0.0, gamma=40, embed_dim=16, conve_hid_drop=0.3,
+                             feat_drop=0.2, num_filt=4, ker_sz=3, k_w=4, k_h=4)
+m = tr.Network('cpu', genotype, 50, 3, 16, 16, 7, torch.nn.BCELoss(), 0.3, args)
+m.apply(tr.weights_init)
+assert tr.count_parameters_in_MB(m) > 0
+d = dgl.contrib.data.load_data("FB15k-237")
+assert d.num_nodes == 14541 and d.train.shape == (272115, 3)
+items = tr.process({'train': d.train[:500], 'valid': d.valid[:10], 'test': d.test[:10]}, d.num_rels)
+ds = tr.TrainDataset(items['train'], d.num_nodes, types.SimpleNamespace(lbl_smooth=0.1))
+t, y = ds[0]
+assert y.shape == (14541,)
+print("shim ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code, ref], capture_output=True, text=True, cwd=root,
+                         env={**os.environ, "PYTHONPATH": root})
+    assert out.returncode == 0 and "shim ok" in out.stdout, out.stderr[-2000:]
