@@ -214,7 +214,7 @@ def algo_bytes(key, M, E, N, D):
 
 # C-ABI call -> the kernels it launches that move HBM data (ncu names, template arguments dropped)
 CALL_KERNELS = {
-    "mrg_amax_bwd": ["amax_bwd_dw_kernel", "amax_bwd_dx_kernel"],
+    "mrg_amax_bwd": ["amax_bwd_dw_kernel", "amax_bwd_dx_kernel", "amax_route_kernel"],
     "mrg_amax_tc_fwd": ["tc::amax_tc_kernel"],
     "mrg_sparse_gate_bwd_fused": ["gate_bwd_pipe_kernel"],
     "mrg_sparse_gate_fwd": ["sparse_gate_fwd_kernel"],
