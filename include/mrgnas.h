@@ -237,6 +237,12 @@ int mrg_dense_gate_bwd(const float* dy, const float* z, mrg_act x, int64_t rows,
  * pass over the rows.  The backward reuses mrg_bn_bwd_reduce/apply per candidate (ds_k = w_k*dout).
  * ---------------------------------------------------------------------------------- */
 int mrg_mixed_sum_fwd(mrg_act_list ys, const float* w, int64_t rows, int32_t D, float* out, void* stream);
+/* MixedOp backward, candidate k, after mrg_bn_bwd_finalize of its BatchNorm: dw[k] = sum(dout * relu(a y + b)) from
+ * the finalized statistics, then coef / dgamma / dbeta are scaled by w[k] in place (training = 0: coef = [0,0,a w_k]).
+ * One launch instead of ~12 elementwise / reduction launches per candidate. */
+int mrg_mixed_bwd_scale(float* coef, float* dgamma, float* dbeta, const float* a, const float* b, const float* mean,
+                        const float* invstd, const float* w, int32_t k, float* dw, int32_t D, int32_t training,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K5/K11  segmented reduction of gathered rows.  One kernel family serves

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mrg_dense_gate_fwd": (I32, [P, MrgAct, I64, I32, I32, P, F32, P, P, P]),
     "mrg_dense_gate_bwd": (I32, [P, P, MrgAct, I64, I32, I32, P, F32, P, P, I32, P]),
     "mrg_mixed_sum_fwd": (I32, [MrgActList, P, I64, I32, P, P]),
+    "mrg_mixed_bwd_scale": (I32, [P, P, P, P, P, P, P, P, I32, P, I32, I32, P]),
     "mrg_seg_reduce_workspace_bytes": (SZ, [I64, I32, I32]),
     "mrg_seg_reduce_fwd": (I32, [I32, MrgAct, P, P, P, P, I64, I64, I32, P, P, F32, MrgAct, I32, P, P, P, SZ, P]),
     "mrg_seg_reduce_bwd": (I32, [I32, P, P, P, MrgAct, P, P, I64, I64, I32, P, I32, P]),
@@ -138,7 +139,15 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream.  (torch.cuda.current_stream() costs ~16 us of Python per call --
+    measured: 11 ms of a 51 ms launch-bound supernet step -- the raw getter is a single C call.)"""
+    if _raw_stream is not None and _cur_device is not None:
+        return c_void_p(_raw_stream(_cur_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -293,6 +293,45 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int npa
   coef[2 * D + c] = (float)c2;
 }
 
+// MixedOp backward, per candidate k (cell_lp.py:25-33): after bn_bwd_finalize, ONE block
+//   dw[k]   = sum_c a_c * S2_c + b_c * S1_c      (= sum(dout * relu(a y + b)); S1 = dbeta, S2 = dgamma / invstd + mean S1)
+//   coef, dgamma, dbeta *= w[k]                   (eval mode: coef = [0, 0, a * w[k]])
+// replaces a dozen tiny elementwise / reduction launches per candidate (the supernet step is launch bound).
+__global__ void mixed_bwd_scale_kernel(float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       const float* __restrict__ a, const float* __restrict__ b,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ w, int k, float* __restrict__ dw, int D,
+                                       int training) {
+  __shared__ double red[32];
+  const float wk = w[k];
+  double t = 0.0;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const double s1 = dbeta[c];
+    const double s2 = (double)dgamma[c] / (double)invstd[c] + (double)mean[c] * s1;
+    t += (double)a[c] * s2 + (double)b[c] * s1;
+    if (training) {
+      coef[c] *= wk;
+      coef[D + c] *= wk;
+      coef[2 * D + c] *= wk;
+    } else {
+      coef[c] = 0.f;
+      coef[D + c] = 0.f;
+      coef[2 * D + c] = a[c] * wk;
+    }
+    dgamma[c] *= wk;
+    dbeta[c] *= wk;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];     // fixed order
+    dw[k] = (float)s;
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __restrict__ ds, mrg_act y,
                                                                 const float* __restrict__ coef, int64_t rows, int D,
@@ -1006,6 +1045,17 @@ extern "C" int mrg_bn_bwd_finalize(const double* bwd_stats, int32_t nparts, int6
   bn_bwd_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, kFinCols * kFinLanes, 0, (cudaStream_t)stream>>>(bwd_stats, nparts, rows, D, gamma, mean,
                                                                             invstd, dgamma, dbeta, coef);
   MRG_LAUNCH_CHECK("bn_bwd_finalize");
+  return MRG_OK;
+}
+
+extern "C" int mrg_mixed_bwd_scale(float* coef, float* dgamma, float* dbeta, const float* a, const float* b,
+                                   const float* mean, const float* invstd, const float* w, int32_t k, float* dw,
+                                   int32_t D, int32_t training, void* stream) {
+  MRG_CHECK_ARG(coef && dgamma && dbeta && a && b && mean && invstd && w && dw && D > 0 && k >= 0,
+                "mixed_bwd_scale: arguments");
+  mixed_bwd_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(coef, dgamma, dbeta, a, b, mean, invstd, w, k, dw, D,
+                                                             training);
+  MRG_LAUNCH_CHECK("mixed_bwd_scale");
   return MRG_OK;
 }
 

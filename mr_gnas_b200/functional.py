@@ -789,16 +789,13 @@ class MixedSum(torch.autograd.Function):
             coef = torch.empty(3 * D, dtype=torch.float32, device=dev)
             call("mrg_bn_bwd_finalize", ptr(bst), nparts, rows, D, ptr(gamma), ptr(mean), ptr(invstd), ptr(dgamma),
                  ptr(dbeta), ptr(coef), stream())
-            # sum(dout * s_k) = sum_c a_c * S2_c + b_c * S1_c  with S1 = dbeta, S2 = dgamma/invstd + mean*S1
-            s1 = dbeta
-            s2 = dgamma / invstd + mean * s1
-            dw[k] = (a * s2 + b * s1).sum()
-            if not ctx.training:  # eval: no statistics path -> dy = w_k * a * dz
-                coef = torch.cat([torch.zeros(2 * D, device=dev), a]).contiguous()
-            coef = (coef * w[k]).contiguous()
+            # dw[k] = sum(dout * s_k) = sum_c a_c * S2_c + b_c * S1_c (S1 = dbeta, S2 = dgamma/invstd + mean*S1), then
+            # coef / dgamma / dbeta scaled by w[k] (eval: dy = w_k * a * dz) -- one launch
+            call("mrg_mixed_bwd_scale", ptr(coef), ptr(dgamma), ptr(dbeta), ptr(a), ptr(b), ptr(mean), ptr(invstd),
+                 ptr(w), k, ptr(dw), D, 1 if ctx.training else 0, stream())
             dy = torch.empty_like(y)
             call("mrg_bn_bwd_apply", ptr(dout), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
-            grads += [dy, dgamma * w[k], dbeta * w[k]]
+            grads += [dy, dgamma, dbeta]
         return (dw, None, None, None, None, None, *grads)
 
 

@@ -44,7 +44,7 @@ def main():
     model._device = dev
     for a in model.arch_parameters():
         a.data = a.data.to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
     gen = torch.Generator(device=dev).manual_seed(0)
     for size in [int(s) for s in args.sizes.split(",")]:
         t_samp = t_model = 0.0
