@@ -271,6 +271,9 @@ def main():
     ap.add_argument("--strong", action="store_true",
                     help="partition mode: keep the C1 graph at every N (strong scaling) instead of growing the "
                          "triples with N (weak scaling, the default: per-GPU edge work stays that of C1)")
+    ap.add_argument("--amax-bf16", action="store_true",
+                    help="run the fused a_max forward in its bf16 variant (mrg_amax_tc_fwd_bf16; tolerance class 2e-2, "
+                         "not the fp32 parity path) -- reported as dtype 'f32 + bf16 a_max operands'")
     ap.add_argument("--no-c4", action="store_true", help="skip the AM-shaped NC partition sub-record (c4_partition)")
     ap.add_argument("--c4-scale", type=float, default=1.0)
     ap.add_argument("--c4-steps", type=int, default=3)
@@ -295,6 +298,9 @@ def main():
     from mr_gnas_b200.synth import CONFIGS, synth_kg
     from mr_gnas_b200.utils import weights_init
     _lib.load()  # fails loudly if the CUDA extension is missing
+    if args.amax_bf16:
+        from mr_gnas_b200 import functional as _K
+        _K.AMAX_PRECISION = "bf16"
 
     mode = "dp" if args.dp else ("partition" if args.partition else args.mode)
     part_mode = world > 1 and mode in ("auto", "partition")
@@ -553,7 +559,8 @@ def main():
                           if args.sparse_labels else "dense smoothed [B,N] fp32 matrix per step")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong" if (part_mode and args.strong) else "weak", "vs_baseline": None, "dtype": "f32",
+                "scaling": "strong" if (part_mode and args.strong) else "weak", "vs_baseline": None,
+                "dtype": "f32 + bf16 a_max operands" if args.amax_bf16 else "f32",
                 "data": "synthetic", "config": cfg, "run": run,
                 "triples_per_s": q_units * B / (ms / 1e3),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

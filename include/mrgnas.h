@@ -283,6 +283,13 @@ size_t mrg_amax_tc_workspace_bytes(int64_t N, int32_t D);
 int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid, const int32_t* dst,
                     int64_t E, int64_t N, int32_t D, mrg_act residual, float* out, int32_t* arg, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* Reduced-precision variant of the same call (north_star "bf16 variants"): the activated message rows and W are
+ * rounded to bf16 on the way into shared memory, ONE tcgen05 kind::f16 MMA per K step accumulates in fp32 TMEM
+ * (a third of the tensor work of the 3xTF32 path, three times the X stages).  Same outputs, same argmax encoding;
+ * stated tolerance: |out - out_fp32| <= 2e-2 * max|out| (tests/test_gpu_ops_lp.py::test_amax_bf16_variant). */
+int mrg_amax_tc_fwd_bf16(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid, const int32_t* dst,
+                         int64_t E, int64_t N, int32_t D, mrg_act residual, float* out, int32_t* arg, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* K5 backward (sparse): gradients of a_max w.r.t. the E message-source rows (dX, edge-id order,
  * every row written once), the Linear weight (dW [D,D]) and bias (db [D]) from g = dL/d(out),

@@ -109,6 +109,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// kind::f16 with bf16 operands, fp32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -144,6 +157,26 @@ __global__ void tf32_split_kernel(const float* __restrict__ W, int Dout, int Din
     const int64_t off = (int64_t)(rr >> 3) * 256 + (rr & 7) * 32 + ((j ^ (rr & 7)) << 2) + e;  // floats within a tile
     img[c * per_chunk + (int64_t)h * 4096 + off] = hi;
     img[c * per_chunk + (int64_t)(MH + h) * 4096 + off] = tf32_rna(x - hi);
+  }
+}
+
+// W [Dout, Din] fp32 -> bf16 shared-memory image: per K chunk of 64 elements MH tiles of 128 rows x 128 bytes,
+// K-major, 128B-swizzled (16-byte unit j of row r at unit j ^ (r & 7)), zero padded.
+__global__ void bf16_image_kernel(const float* __restrict__ W, int Dout, int Din, int MH, int nchunks,
+                                  unsigned short* __restrict__ img) {
+  const int64_t per_chunk = (int64_t)MH * 128 * 64;  // bf16 elements
+  const int64_t n = (int64_t)nchunks * per_chunk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % 64);
+    const int row = (int)((i / 64) % (MH * 128));
+    const int c = (int)(i / per_chunk);
+    const int k = c * 64 + kk;
+    const float x = (row < Dout && k < Din) ? W[(size_t)row * Din + k] : 0.f;
+    unsigned short b;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(b) : "f"(x));
+    const int h = row >> 7, rr = row & 127, j = kk >> 3, e = kk & 7;
+    const int64_t off = (int64_t)(rr >> 3) * 512 + (rr & 7) * 64 + ((j ^ (rr & 7)) << 3) + e;  // bf16 within a tile
+    img[c * per_chunk + (int64_t)h * 8192 + off] = b;
   }
 }
 
@@ -192,12 +225,19 @@ __device__ __forceinline__ Item item_of(int q, int nchunks, int full_pairs) {
 }
 
 // dynamic smem (1024-B aligned): W ring [WS][Whi MH tiles | Wlo MH tiles], X ring [XS][Xhi | Xlo], small arrays
-template <int MH, int EPI>
+// PREC: 0 = 3xTF32 (fp32-class accuracy: hi/lo operand pairs, three MMAs per K step);
+//       2 = BF16 (operands rounded to bf16, ONE kind::f16 MMA per K step, K chunk = 64 elements per 128-byte row):
+//           a third of the tensor work, half the operand bytes per K and 3x the X stages -- the reduced-precision
+//           variant of the north_star, with its own stated tolerance (tests/test_gpu_ops_lp.py::test_amax_bf16_variant)
+template <int MH, int EPI, int PREC = 0>
 __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t WSTAGE = 2 * MH * TILE_BYTES;
-  constexpr uint32_t XSTAGE = 2 * TILE_BYTES;
-  constexpr int XS = MH == 1 ? 4 : 2;
+  constexpr bool BF = PREC == 2;
+  constexpr int KC = BF ? 64 : KCH;                       // operand elements per K chunk (one 128-byte row)
+  constexpr int STAGES = BF ? 3 : tc::STAGES;             // W ring depth (shadows the namespace constant)
+  constexpr uint32_t WSTAGE = (BF ? 1 : 2) * MH * TILE_BYTES;
+  constexpr uint32_t XSTAGE = (BF ? 1 : 2) * TILE_BYTES;
+  constexpr int XS = BF ? 6 : (MH == 1 ? 4 : 2);
   // align with pointer arithmetic on the __shared__ symbol (an integer round-trip would demote every access
   // below to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -288,10 +328,16 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     const float* xrow0 = nullptr;   // load cursor's row per slot (null: past the last edge)
     const float* xrow1 = nullptr;
     bool cvalid0 = false, cvalid1 = false;   // consume cursor's row validity per slot
-    float4 buf[PD][NU];
+    constexpr int NB = BF ? 2 * NU : NU;     // float4 pieces per item and thread (a bf16 unit packs two float4)
+    constexpr int PDP = BF ? 2 : PD;         // items in flight per producer thread
+    float4 buf[PDP][NB];
     Cur lc = {0, 0, 0}, cc = {0, 0, 0};
     int lq = 0;
-    auto load = [&](float4(&b)[NU]) {
+    if (BF) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) ucol[j] *= 2;          // a 16-byte bf16 unit covers 8 columns
+    }
+    auto load = [&](float4(&b)[NB]) {
       if (lc.c == 0) {
         const int64_t pos = tile_of(lc.pair, lc.slot) * TILE_E + r;
         const float* v = pos < p.E ? p.x.data + (size_t)(p.csr_eid ? __ldg(p.csr_eid + pos) : (int32_t)pos) * D
@@ -300,25 +346,61 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         else xrow0 = v;
       }
       const float* xr = lc.slot ? xrow1 : xrow0;
-      const int c0 = lc.c * KCH;
+      const int c0 = lc.c * KC;
+      if (BF) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j)
-        b[j] = (xr && c0 + ucol[j] < D) ? ld_stream4(xr + c0 + ucol[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NU; ++j) {
+          const int col = c0 + ucol[j];
+          b[2 * j] = (xr && col < D) ? ld_stream4(xr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[2 * j + 1] = (xr && col + 4 < D) ? ld_stream4(xr + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NU; ++j)
+          b[j] = (xr && c0 + ucol[j] < D) ? ld_stream4(xr + c0 + ucol[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       advance(lc);
     };
-    auto consume = [&](float4(&b)[NU], int q) {
+    auto activate = [&](float4 v, int col, bool valid) {     // lazy BN affine + ReLU of 4 columns
+      if (valid && col < D) {
+        if (affine) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + col);
+          v.x = fmaf(sc.x, v.x, sh.x); v.y = fmaf(sc.y, v.y, sh.y);
+          v.z = fmaf(sc.z, v.z, sh.z); v.w = fmaf(sc.w, v.w, sh.w);
+        }
+        if (relu) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+      }
+      return v;
+    };
+    auto consume = [&](float4(&b)[NB], int q) {
       if (cc.c == 0) {
         const bool ok = tile_of(cc.pair, cc.slot) * TILE_E + r < p.E;
         if (cc.slot) cvalid1 = ok;
         else cvalid0 = ok;
       }
       const bool valid = cc.slot ? cvalid1 : cvalid0;
-      const int c0 = cc.c * KCH;
+      const int c0 = cc.c * KC;
       const int s = q % XS;
       const uint32_t ph = (q / XS) & 1;
       mbar_wait(&xempty_bar[s], ph ^ 1);
       uint8_t* xhi = smem_x + (size_t)s * XSTAGE;
       uint8_t* xlo = xhi + TILE_BYTES;
+      if (BF) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          const int col = c0 + ucol[j];
+          const float4 a = activate(b[2 * j], col, valid), c4 = activate(b[2 * j + 1], col + 4, valid);
+          uint4 pk;      // 8 bf16: cvt.rn.bf16x2 packs (hi operand -> upper half)
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(a.y), "f"(a.x));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(a.w), "f"(a.z));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.z) : "f"(c4.y), "f"(c4.x));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.w) : "f"(c4.w), "f"(c4.z));
+          *reinterpret_cast<uint4*>(xhi + uoff[j]) = pk;
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
         const int col = c0 + ucol[j];
@@ -344,18 +426,19 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         *reinterpret_cast<float4*>(xhi + uoff[j]) = hi;
         *reinterpret_cast<float4*>(xlo + uoff[j]) = lo;
       }
+      }
       fence_proxy_async();
       mbar_arrive(&xfull_bar[s]);
       advance(cc);
     };
 #pragma unroll
-    for (int u = 0; u < PD; ++u) {
+    for (int u = 0; u < PDP; ++u) {
       if (lq < total) load(buf[u]);
       ++lq;
     }
-    for (int q = 0; q < total; q += PD) {
+    for (int q = 0; q < total; q += PDP) {
 #pragma unroll
-      for (int u = 0; u < PD; ++u) {
+      for (int u = 0; u < PDP; ++u) {
         if (q + u < total) {
           consume(buf[u], q + u);
           if (lq < total) load(buf[u]);
@@ -380,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA ISSUER ================================
-    const uint32_t idesc = umma_idesc(128, TILE_E);
+    const uint32_t idesc = BF ? umma_idesc_bf16(128, TILE_E) : umma_idesc(128, TILE_E);
     int q = 0, wq = 0;
     for (int pr = 0; pr < npairs; ++pr) {
       const int ntp = min(2, my_tiles - 2 * pr);
@@ -390,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         const int ws = wq % STAGES;
         mbar_wait(&wfull_bar[ws], (wq / STAGES) & 1);
         const uint32_t wbase = smem_u32(smem_w + (size_t)ws * WSTAGE);
-        const int ksteps = min(KCH, D - c * KCH) / 8;
+        const int ksteps = BF ? (min(KC, D - c * KC) + 15) / 16 : min(KCH, D - c * KCH) / 8;   // zero padded
         for (int ts = 0; ts < ntp; ++ts, ++q) {
           const int xs = q % XS;
           mbar_wait(&xfull_bar[xs], (q / XS) & 1);
@@ -401,11 +484,15 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
               const uint32_t whi = wbase + h * TILE_BYTES, wlo = wbase + (MH + h) * TILE_BYTES;
               const uint32_t d_tmem = tmem_base + ts * (MH * TILE_E) + h * TILE_E;
               for (int k = 0; k < ksteps; ++k) {
-                const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the swizzled 128B row
+                const uint32_t ko = k * 32;  // 8 tf32 / 16 bf16 = 32 bytes inside the swizzled 128B row
                 const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-                umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);  // small terms first
-                umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
-                umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+                if (BF) {
+                  umma_bf16(d_tmem, umma_desc(wbase + h * TILE_BYTES + ko), umma_desc(xhi + ko), idesc, acc);
+                } else {
+                  umma_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);  // small terms first
+                  umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
+                  umma_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+                }
               }
             }
             umma_commit(&xempty_bar[xs]);                          // X stage free when these MMAs retire
@@ -635,9 +722,9 @@ extern "C" size_t mrg_amax_tc_workspace_bytes(int64_t N, int32_t D) {
 
 extern "C" int mrg_amax_tc_supported(int32_t D) { return (D % 8 == 0 && D >= 8 && D <= 256) ? 1 : 0; }
 
-extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid,
-                               const int32_t* dst, int64_t E, int64_t N, int32_t D, mrg_act residual, float* out,
-                               int32_t* arg, void* workspace, size_t workspace_bytes, void* stream) {
+static int amax_tc_fwd_impl(int prec, mrg_act x, const float* W, const float* bias, const int32_t* csr_eid,
+                            const int32_t* dst, int64_t E, int64_t N, int32_t D, mrg_act residual, float* out,
+                            int32_t* arg, void* workspace, size_t workspace_bytes, void* stream) {
   MRG_CHECK_ARG(x.data && W && out && workspace, "amax_tc_fwd: null pointer");
   MRG_CHECK_ARG(E == 0 || (csr_eid && dst), "amax_tc_fwd: null graph arrays");
   MRG_CHECK_ARG(mrg_amax_tc_supported(D), "amax_tc_fwd: D must be a multiple of 8 and <= 256");
@@ -647,13 +734,15 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int MH = D <= 128 ? 1 : 2;
-  const int Kp = (D + tc::KCH - 1) / tc::KCH * tc::KCH;
+  const int kch = prec == 2 ? 64 : tc::KCH;
+  const int Kp = (D + kch - 1) / kch * kch;
   unsigned long long* packed = (unsigned long long*)workspace;
   const size_t packed_bytes = ((size_t)N * D * sizeof(unsigned long long) + 255) / 256 * 256;
   float* wsplit = (float*)((char*)workspace + packed_bytes);
   cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)N * D * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd memset");
-  tc::tf32_split_kernel<<<64, 256, 0, st>>>(W, D, D, MH, Kp / tc::KCH, wsplit);
+  if (prec == 2) tc::bf16_image_kernel<<<64, 256, 0, st>>>(W, D, D, MH, Kp / kch, (unsigned short*)wsplit);
+  else tc::tf32_split_kernel<<<64, 256, 0, st>>>(W, D, D, MH, Kp / kch, wsplit);
   tc::AmaxParams p;
   p.x = x;
   p.csr_eid = csr_eid;
@@ -665,7 +754,7 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   p.D = D;
   p.MH = MH;
   p.Kp = Kp;
-  p.nchunks = Kp / tc::KCH;
+  p.nchunks = Kp / kch;
   p.num_tiles = (int)((E + tc::TILE_E - 1) / tc::TILE_E);
   p.Dout = D;
   p.label = nullptr;
@@ -675,10 +764,20 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
   p.store = nullptr;
   p.lds = 0;
   if (p.num_tiles > 0) {
-    const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
-                        1024 /*align*/ + 8192 /*tail*/;
+    const size_t smem = prec == 2
+        ? (size_t)3 * MH * tc::TILE_BYTES + (size_t)6 * tc::TILE_BYTES + 1024 + 8192
+        : (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
+              1024 /*align*/ + 8192 /*tail*/;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    if (MH == 1) {
+    if (prec == 2 && MH == 1) {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<1, tc::EPI_AMAX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+      tc::amax_tc_kernel<1, tc::EPI_AMAX, 2><<<grid, tc::THREADS, smem, st>>>(p);
+    } else if (prec == 2) {
+      e = cudaFuncSetAttribute(tc::amax_tc_kernel<2, tc::EPI_AMAX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+      tc::amax_tc_kernel<2, tc::EPI_AMAX, 2><<<grid, tc::THREADS, smem, st>>>(p);
+    } else if (MH == 1) {
       e = cudaFuncSetAttribute(tc::amax_tc_kernel<1, tc::EPI_AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
       tc::amax_tc_kernel<1, tc::EPI_AMAX><<<grid, tc::THREADS, smem, st>>>(p);
@@ -693,6 +792,19 @@ extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, con
                                                                                                   out, arg);
   MRG_LAUNCH_CHECK("amax_tc_fwd");
   return MRG_OK;
+}
+
+extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid,
+                               const int32_t* dst, int64_t E, int64_t N, int32_t D, mrg_act residual, float* out,
+                               int32_t* arg, void* workspace, size_t workspace_bytes, void* stream) {
+  return amax_tc_fwd_impl(0, x, W, bias, csr_eid, dst, E, N, D, residual, out, arg, workspace, workspace_bytes, stream);
+}
+
+/* bf16 variant: operands (activated x rows, W) rounded to bf16, fp32 accumulation in TMEM, one MMA per K step */
+extern "C" int mrg_amax_tc_fwd_bf16(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid,
+                                    const int32_t* dst, int64_t E, int64_t N, int32_t D, mrg_act residual, float* out,
+                                    int32_t* arg, void* workspace, size_t workspace_bytes, void* stream) {
+  return amax_tc_fwd_impl(2, x, W, bias, csr_eid, dst, E, N, D, residual, out, arg, workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -430,6 +430,15 @@ def amax_tc_supported(D):
     return bool(_lib.load().mrg_amax_tc_supported(int(D)))
 
 
+AMAX_PRECISION = "fp32"     # "bf16": the reduced-precision variant of the fused a_max forward (mrg_amax_tc_fwd_bf16)
+
+
+def amax_tc_call():
+    if AMAX_PRECISION not in ("fp32", "bf16"):
+        raise ValueError(f"AMAX_PRECISION must be 'fp32' or 'bf16', got {AMAX_PRECISION!r}")
+    return "mrg_amax_tc_fwd_bf16" if AMAX_PRECISION == "bf16" else "mrg_amax_tc_fwd"
+
+
 _tc_ws = {}
 
 
@@ -455,7 +464,7 @@ class AMaxTC(torch.autograd.Function):
         arg = torch.empty(N, D, dtype=torch.int32, device=x.device)
         ws = _tc_workspace(N, D, x.device)
         res = act(x[E:]) if has_residual else act(None)
-        call("mrg_amax_tc_fwd", act(x), ptr(weight), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, res, ptr(out),
+        call(amax_tc_call(), act(x), ptr(weight), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, res, ptr(out),
              ptr(arg), ptr(ws), ws.numel(), stream())
         ctx.g, ctx.has_residual = g, has_residual
         ctx.save_for_backward(x, weight, arg)

@@ -134,7 +134,7 @@ class EdgeChain(torch.autograd.Function):
                 agg_params[node] = (W, bias)
                 arg = torch.empty(N, D, dtype=torch.int32, device=dev)
                 ws = K._tc_workspace(N, D, dev)
-                call("mrg_amax_tc_fwd", view(i), ptr(W), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, view(i, E, M),
+                call(K.amax_tc_call(), view(i), ptr(W), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, view(i, E, M),
                      ptr(out), ptr(arg), ptr(ws), ws.numel(), stream(), nbytes=E * (b + 8) + 3 * N * b)
                 ARG[node] = arg
                 g.last_arg = arg

@@ -460,3 +460,53 @@ def test_linear_tc_vs_fp64(dev, rows, K, F):
     _check("dx", x.grad, x64.grad.float())
     _check("dw", lin.weight.grad, w64.grad.float())
     _check("db", lin.bias.grad, b64.grad.float())
+
+
+@pytest.mark.parametrize("D", [64, 200, 256])
+def test_amax_bf16_variant(dev, D):
+    """Reduced-precision variant of the fused a_max forward (mrg_amax_tc_fwd_bf16: activated rows and W rounded to
+    bf16, fp32 accumulation) against the fp32-class 3xTF32 kernel on the same inputs.
+    STATED TOLERANCE (bf16 class): max|out_bf16 - out_fp32| <= 2e-2 * max|out_fp32| and 2-norm error <= 1e-2; the
+    routing (argmax edge per destination and feature) must agree on >= 90 % of the pairs (a bf16-rounded message
+    may pick another near-maximal edge); isolated destinations and ReLU-gated maxima are encoded identically.
+    The backward is the fp32 sparse kernel fed with the routing the forward reported, so gradients are exact for
+    that routing (checked against CPU autograd through it)."""
+    from mr_gnas_b200 import functional as K
+    from mr_gnas_b200 import operations_lp as ops
+    from mr_gnas_b200.graph import MRGraph
+    from parity import norm_err, rel_err
+    N, R, T = 3000, 9, 20000
+    trip = O.synth_kg(N, R, T, seed=D)
+    g = MRGraph.from_triples(N, trip, R, device=dev)
+    E = 2 * T
+    torch.manual_seed(D)
+    op = ops.MIXED_OPS['a_max']({'feature_dim': D, 'drop_aggr': 0.0}).to(dev)
+    x = torch.relu(torch.randn(E + N, D, device=dev))
+    cot = torch.randn(N, D, device=dev)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        K.AMAX_PRECISION = prec
+        try:
+            xg = x.clone().requires_grad_(True)
+            op.zero_grad()
+            out = op(g, xg, xg)
+            out.backward(cot)
+            res[prec] = (out.detach(), K.decode_arg(g.last_arg).clone(), g.last_arg.clone(), xg.grad.clone(),
+                         op.linear.weight.grad.clone(), op.linear.bias.grad.clone())
+        finally:
+            K.AMAX_PRECISION = "fp32"
+    o32, a32, enc32 = res["fp32"][:3]
+    o16, a16, enc16 = res["bf16"][:3]
+    e_max, e_nrm = rel_err(o16, o32), norm_err(o16, o32)
+    agree = float((a16 == a32).float().mean())
+    print(f"bf16 a_max D={D}: max-norm rel err {e_max:.2e}, 2-norm rel err {e_nrm:.2e}, routing agreement {agree:.4f}")
+    assert e_max <= 2e-2 and e_nrm <= 1e-2
+    assert agree >= 0.90
+    assert torch.equal(enc16 == -1, enc32 == -1)                      # isolated destinations
+    # gradients are exact for the routing the bf16 forward reported
+    W, b = op.linear.weight.detach().cpu(), op.linear.bias.detach().cpu()
+    exp = _amax_expected_grads(x.cpu(), W, b, torch.where(enc16 >= 0, enc16, torch.full_like(enc16, -1)).cpu().long(),
+                               E, cot.cpu())
+    _check("dx", res["bf16"][3], exp[0])
+    _check("dW", res["bf16"][4], exp[1])
+    _check("db", res["bf16"][5], exp[2])
