@@ -503,10 +503,16 @@ def test_amax_bf16_variant(dev, D):
     assert e_max <= 2e-2 and e_nrm <= 1e-2
     assert agree >= 0.90
     assert torch.equal(enc16 == -1, enc32 == -1)                      # isolated destinations
-    # gradients are exact for the routing the bf16 forward reported
-    W, b = op.linear.weight.detach().cpu(), op.linear.bias.detach().cpu()
-    exp = _amax_expected_grads(x.cpu(), W, b, torch.where(enc16 >= 0, enc16, torch.full_like(enc16, -1)).cpu().long(),
-                               E, cot.cpu())
-    _check("dx", res["bf16"][3], exp[0])
-    _check("dW", res["bf16"][4], exp[1])
-    _check("db", res["bf16"][5], exp[2])
+    # gradients are exact for the routing AND the ReLU gating the bf16 forward reported (enc >= 0: the routed
+    # message was positive in bf16 arithmetic): CPU autograd through out[n,f] = (W x_e + b)[enc[n,f], f] + x[E+n, f]
+    xo = x.cpu().clone().requires_grad_(True)
+    Wo = op.linear.weight.detach().cpu().clone().requires_grad_(True)
+    bo = op.linear.bias.detach().cpu().clone().requires_grad_(True)
+    m = torch.nn.functional.linear(xo[:E], Wo, bo)
+    enc = enc16.cpu().long()
+    cols = torch.arange(D).view(1, -1).expand(N, D)
+    picked = torch.where(enc >= 0, m[enc.clamp(min=0), cols], torch.zeros(N, D))
+    (picked + xo[E:]).backward(cot.cpu())
+    _check("dx", res["bf16"][3], xo.grad)
+    _check("dW", res["bf16"][4], Wo.grad)
+    _check("db", res["bf16"][5], bo.grad)
