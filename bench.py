@@ -311,6 +311,7 @@ def main():
     N, T = N0, T0 * grow
     trip = synth_kg(N, R, T, seed=0)
     E, M, B = 2 * T, 2 * T + N, args.batch
+    torch.cuda.set_per_process_memory_fraction(0.92)       # a Python OOM, never a dead box
     if part_mode:
         from mr_gnas_b200.dist import lp_partition
         g = lp_partition(trip, N, R, rank, world, device=dev)
@@ -325,7 +326,8 @@ def main():
     nb = args.steps + args.warmup
     rng = np.random.RandomState(100 + (0 if (part_mode or world == 1) else rank))
     n_queries = train_items(trip, R, select=[])[1]
-    sels = [rng.choice(n_queries, size=B, replace=False) for _ in range(min(nb, 8))]
+    n_host_batches = 2 if N * B * 4 > (1 << 28) else 8      # dense [B, N] label rows are pinned on the host
+    sels = [rng.choice(n_queries, size=B, replace=False) for _ in range(min(nb, n_host_batches))]
     flat_items, _ = train_items(trip, R, select=np.concatenate(sels))
     host_batches, sparse_batches = [], []
     for i in range(len(sels)):

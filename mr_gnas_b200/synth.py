@@ -8,6 +8,11 @@ CONFIGS = {
     "c1_fb15k237": (14541, 237, 272115, 200),
     "c3_wn18rr": (40943, 11, 86835, 200),
     "tiny": (500, 7, 4000, 64),
+    # BASELINE configs[4] (C5: 10 M entities, 1 k relations, 200 M directed edges = 100 M triples, D = 256) scaled down
+    # in entities and triples alike (same relation count and feature dim); the full size needs the entity table and
+    # its optimiser state sharded
+    "c5_64th": (156_250, 1000, 1_562_500, 256),
+    "c5_eighth": (1_250_000, 1000, 12_500_000, 256),
 }
 
 
