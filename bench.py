@@ -546,7 +546,7 @@ def main():
             c4 = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank == 0:
-        scal = "strong scaling on the C1 graph" if args.strong else \
+        scal = "strong scaling on the named workload" if args.strong else \
             f"weak scaling: {grow}x the C1 triples over the C1 entities (per-GPU edge work = C1's)"
         par = "none (one device)" if world == 1 else (
             f"dst-partition x{world}: 1-D destination ranges balanced by in-edges, NCCL halo all-gather, global "
