@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--amax-bf16", action="store_true",
                     help="run the fused a_max forward in its bf16 variant (mrg_amax_tc_fwd_bf16; tolerance class 2e-2, "
                          "not the fp32 parity path) -- reported as dtype 'f32 + bf16 a_max operands'")
+    ap.add_argument("--no-bf16-variant", action="store_true", help="skip the bf16_variant sub-record")
     ap.add_argument("--no-c4", action="store_true", help="skip the AM-shaped NC partition sub-record (c4_partition)")
     ap.add_argument("--c4-scale", type=float, default=1.0)
     ap.add_argument("--c4-steps", type=int, default=3)
@@ -532,6 +533,31 @@ def main():
                           "this init); tests/test_gpu_config_parity.py holds every tensor to max(1e-5, 4 x the "
                           "reference's own error) against the fp64 truth"}
 
+    # ---- the same step with the bf16 variant of the fused a_max forward: its own CUDA graph,
+    # same model / optimiser / batches, timed like `value`; reported beside the fp32 number, never instead of it
+    bf16_variant = None
+    if not args.amax_bf16 and not args.no_graph and not args.sparse_labels and not args.no_bf16_variant:
+        from mr_gnas_b200 import functional as _K
+        _K.AMAX_PRECISION = "bf16"
+        try:
+            runner16 = GraphedTrainStep(model, g, opt, B, label_cols, grad_sync=lambda ps: allreduce_grads())
+            trip_d, y_d = dev_batches[0]
+            runner16.load(trip_d[:, 0], trip_d[:, 1], y_d)
+            runner16.capture()
+
+            def step16(i):
+                t_d, yy = dev_batches[i % len(dev_batches)]
+                return runner16(t_d[:, 0], t_d[:, 1], yy)
+            for i in range(args.warmup):
+                step16(i)
+            ms16, _, _ = timed(step16, args.steps)
+            bf16_variant = {"what": "same step, fused a_max forward with bf16 operands (mrg_amax_tc_fwd_bf16; stated "
+                                    "tolerance 2e-2 on the a_max output, tests/test_gpu_ops_lp.py::test_amax_bf16_variant)",
+                            "ms_per_step": ms16, "value": E * cells / (ms16 / 1e3), "unit": UNIT}
+            del runner16
+        finally:
+            _K.AMAX_PRECISION = "fp32"
+
     c4 = None
     if not args.no_c4:
         # BASELINE configs[3]: AM-shaped NC full-graph layers, destination-partitioned over these same N ranks
@@ -568,7 +594,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e, "triples_per_s": q_units * B / (ms_e2e / 1e3)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "parity": parity, "c4_partition": c4, "loss": float(last_loss)}
+                "parity": parity, "bf16_variant": bf16_variant, "c4_partition": c4, "loss": float(last_loss)}
         print(json.dumps(line), flush=True)
     if world > 1:
         # NCCL communicators referenced by a live CUDA graph can stall destroy_process_group(): leave together,
