@@ -16,6 +16,8 @@ LIB = os.path.join(LIB_DIR, "libmrgnas.so")
 SOURCES = ["rowops.cu", "segreduce.cu", "graph.cu", "gemm_tc.cu", "amax_bwd.cu", "gate_pipe.cu", "score.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("MRG_TC_PROF"):       # MMA-warp wait counters in the tcgen05 kernel (scripts/prof_amax_tc.py)
+    NVCC_FLAGS.append("-DMRG_TC_PROF")
 if os.environ.get("MRG_DW_PROF"):       # phase counters in the a_max dW kernel (scripts/prof_amax_bwd.py)
     NVCC_FLAGS.append("-DMRG_DW_PROF")
 

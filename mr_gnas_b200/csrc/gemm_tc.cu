@@ -180,6 +180,10 @@ __global__ void bf16_image_kernel(const float* __restrict__ W, int Dout, int Din
   }
 }
 
+#ifdef MRG_TC_PROF
+__device__ unsigned long long* g_tc_prof = nullptr;      // debugging aid: MMA-warp wait breakdown (scripts/prof_amax_tc.py)
+#endif
+
 struct AmaxParams {
   mrg_act x;                 // [rows, D] message source rows, read through act
   const int32_t* csr_eid;    // [E] row id per CSR position
@@ -497,18 +501,30 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
     // ================================ MMA ISSUER ================================
     const uint32_t idesc = BF ? umma_idesc_bf16(128, TILE_E) : umma_idesc(128, TILE_E);
     int q = 0, wq = 0;
+#ifdef MRG_TC_PROF
+    long long t_te = 0, t_w = 0, t_x = 0, t_iss = 0, t_m = clock64();
+#define TC_MARK(v) do { const long long n_ = clock64(); v += n_ - t_m; t_m = n_; } while (0)
+#else
+#define TC_MARK(v) do { } while (0)
+#endif
     for (int pr = 0; pr < npairs; ++pr) {
       const int ntp = min(2, my_tiles - 2 * pr);
+      TC_MARK(t_iss);
       for (int ts = 0; ts < ntp; ++ts) mbar_wait(&tempty_bar[ts], (pr & 1) ^ 1);
+      TC_MARK(t_te);
       tc_fence_after();
       for (int c = 0; c < p.nchunks; ++c, ++wq) {
         const int ws = wq % STAGES;
+        TC_MARK(t_iss);
         mbar_wait(&wfull_bar[ws], (wq / STAGES) & 1);
+        TC_MARK(t_w);
         const uint32_t wbase = smem_u32(smem_w + (size_t)ws * WSTAGE);
         const int ksteps = BF ? (min(KC, D - c * KC) + 15) / 16 : min(KCH, D - c * KCH) / 8;   // zero padded
         for (int ts = 0; ts < ntp; ++ts, ++q) {
           const int xs = q % XS;
+          TC_MARK(t_iss);
           mbar_wait(&xfull_bar[xs], (q / XS) & 1);
+          TC_MARK(t_x);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t xhi = smem_u32(smem_x + (size_t)xs * XSTAGE), xlo = xhi + TILE_BYTES;
@@ -536,6 +552,17 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         __syncwarp();
       }
     }
+#ifdef MRG_TC_PROF
+    TC_MARK(t_iss);
+    if (lane == 0 && EPI == EPI_AMAX && g_tc_prof) {
+      atomicAdd(g_tc_prof + 0, (unsigned long long)t_te);
+      atomicAdd(g_tc_prof + 1, (unsigned long long)t_w);
+      atomicAdd(g_tc_prof + 2, (unsigned long long)t_x);
+      atomicAdd(g_tc_prof + 3, (unsigned long long)t_iss);
+      atomicAdd(g_tc_prof + 4, (unsigned long long)(my_tiles * p.nchunks));
+    }
+#endif
+#undef TC_MARK
   } else {
     // ================================ EPILOGUE (2 warp sets, one per TMEM slot) ================================
     const int ts = (warp - EPI_WARP0) >> 2;           // slot served by this warp set
@@ -825,6 +852,13 @@ static int amax_tc_fwd_impl(int prec, mrg_act x, const float* W, const float* bi
   MRG_LAUNCH_CHECK("amax_tc_fwd");
   return MRG_OK;
 }
+
+#ifdef MRG_TC_PROF
+extern "C" int mrg_debug_set_tc_prof(unsigned long long* dev_buf) {
+  cudaMemcpyToSymbol(tc::g_tc_prof, &dev_buf, sizeof(dev_buf));
+  return MRG_OK;
+}
+#endif
 
 extern "C" int mrg_amax_tc_fwd(mrg_act x, const float* W, const float* bias, const int32_t* csr_eid,
                                const int32_t* dst, int64_t E, int64_t N, int32_t D, mrg_act residual, float* out,
