@@ -646,10 +646,17 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) s_loss[warp - EPI_WARP0] = acc;
     } else {
+#ifdef MRG_TC_PROF
+    long long e_pre = 0, e_wait = 0, e_scan = 0, e_m = clock64();
+#define EP_MARK(v) do { const long long n_ = clock64(); v += n_ - e_m; e_m = n_; } while (0)
+#else
+#define EP_MARK(v) do { } while (0)
+#endif
     for (int pr = 0; pr < npairs; ++pr) {
       if (2 * pr + ts >= my_tiles) break;
       const int64_t pos0 = tile_of(pr, ts) * TILE_E;
       const int cnt = (int)min((int64_t)TILE_E, p.E - pos0);
+      EP_MARK(e_scan);
       asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");   // previous tile's readers are done with sd/se
       {
         int32_t e = -1, d = -1;
@@ -668,7 +675,9 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         if (lane == 0) s_flag[ts * 4 + quad] = word;
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+      EP_MARK(e_pre);
       mbar_wait(&tfull_bar[ts], pr & 1);
+      EP_MARK(e_wait);
       tc_fence_after();
       for (int h = 0; h < MH; ++h) {
         const int f = h * 128 + et;
@@ -729,6 +738,15 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       tc_fence_before();
       mbar_arrive(&tempty_bar[ts]);
     }
+#ifdef MRG_TC_PROF
+    EP_MARK(e_scan);
+    if (et == 0 && ts == 0 && g_tc_prof) {
+      atomicAdd(g_tc_prof + 5, (unsigned long long)e_pre);
+      atomicAdd(g_tc_prof + 6, (unsigned long long)e_wait);
+      atomicAdd(g_tc_prof + 7, (unsigned long long)e_scan);
+    }
+#endif
+#undef EP_MARK
     }
   }
 

@@ -39,6 +39,9 @@ for prec in ("fp32", "bf16"):
     print(f"{prec}: call {e0.elapsed_time(e1) * 1e3:.0f} us; MMA warp cycles per item ({p[4]} items over 148 CTAs):")
     for name, v in zip(("wait TMEM drained (epilogue)", "wait W chunk", "wait X item", "issue + rest"), p[:4]):
         print(f"   {name:30s} {100 * v / tot:5.1f} %  {v / max(p[4], 1):8.0f} cycles/item")
+    tiles0 = p[4] / (7 if prec == "fp32" else 4) / 2      # tiles of slot 0
+    print("   epilogue thread 0 of slot 0, cycles per tile: prelude (edge ids, dst, flags, 3 barriers) %.0f, wait for the "
+          "accumulator %.0f, TMEM scan + atomics %.0f" % (p[5] / tiles0, p[6] / tiles0, p[7] / tiles0))
 os.environ.pop("MRG_TC_PROF")
 subprocess.run([sys.executable, "-c", "import os,sys; sys.path.insert(0, %r); from mr_gnas_b200 import build; build.build(force=True)" % ROOT],
                env={k: v for k, v in os.environ.items() if k != "MRG_TC_PROF"})
