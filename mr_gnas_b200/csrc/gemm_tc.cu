@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       if (lane == 0) s_loss[warp - EPI_WARP0] = acc;
     } else {
 #ifdef MRG_TC_PROF
-    long long e_pre = 0, e_wait = 0, e_scan = 0, e_m = clock64();
+    long long e_pre = 0, e_wait = 0, e_scan = 0, e_ld = 0, e_m = clock64();
 #define EP_MARK(v) do { const long long n_ = clock64(); v += n_ - e_m; e_m = n_; } while (0)
 #else
 #define EP_MARK(v) do { } while (0)
@@ -701,7 +701,13 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
           const int cb = 32 * w;
           if (cb >= cnt) break;   // warp-uniform
           uint32_t v[32];
+#ifdef MRG_TC_PROF
+          const long long t_ld0 = clock64();
+#endif
           tmem_ld32(taddr + cb, v);
+#ifdef MRG_TC_PROF
+          e_ld += clock64() - t_ld0;
+#endif
           const uint32_t fl = s_flag[ts * 4 + w];
           if (cb + 32 <= cnt) {
 #pragma unroll
@@ -744,6 +750,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
       atomicAdd(g_tc_prof + 5, (unsigned long long)e_pre);
       atomicAdd(g_tc_prof + 6, (unsigned long long)e_wait);
       atomicAdd(g_tc_prof + 7, (unsigned long long)e_scan);
+      atomicAdd(g_tc_prof + 8, (unsigned long long)e_ld);
     }
 #endif
 #undef EP_MARK

@@ -20,7 +20,7 @@ g = MRGraph.from_triples(N, synth_kg(N, R, T, seed=0), R, device=dev)
 torch.manual_seed(0)
 x = torch.relu(torch.randn(g.M, D, device=dev))
 lin = nn.Linear(D, D).to(dev)
-prof = torch.zeros(8, dtype=torch.int64, device=dev)
+prof = torch.zeros(16, dtype=torch.int64, device=dev)
 for prec in ("fp32", "bf16"):
     K.AMAX_PRECISION = prec
     for _ in range(3):
@@ -41,7 +41,7 @@ for prec in ("fp32", "bf16"):
         print(f"   {name:30s} {100 * v / tot:5.1f} %  {v / max(p[4], 1):8.0f} cycles/item")
     tiles0 = p[4] / (7 if prec == "fp32" else 4) / 2      # tiles of slot 0
     print("   epilogue thread 0 of slot 0, cycles per tile: prelude (edge ids, dst, flags, 3 barriers) %.0f, wait for the "
-          "accumulator %.0f, TMEM scan + atomics %.0f" % (p[5] / tiles0, p[6] / tiles0, p[7] / tiles0))
+          "accumulator %.0f, TMEM scan + atomics %.0f (of which tcgen05.ld + wait::ld %.0f)" % (p[5] / tiles0, p[6] / tiles0, p[7] / tiles0, p[8] / tiles0))
 os.environ.pop("MRG_TC_PROF")
 subprocess.run([sys.executable, "-c", "import os,sys; sys.path.insert(0, %r); from mr_gnas_b200 import build; build.build(force=True)" % ROOT],
                env={k: v for k, v in os.environ.items() if k != "MRG_TC_PROF"})
