@@ -139,6 +139,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Segmented running max of 32 consecutive TMEM columns (one feature per thread) with the lowest-column tie-break.
+// `fl` (warp-uniform) flags the columns where a new destination starts.  Groups of 8 columns without a flag -- most
+// of them: a destination has tens of in-edges -- take a branch-free path: a pairwise (value, column) tournament
+// whose strict `later > earlier` comparisons keep the earliest column on ties, merged into the running maximum by
+// one more strict comparison; 4 instructions per column with log-depth dependences instead of the ~11 of the
+// flag-testing path (BSSY/BSYNC pairs, moves) that the round-2 SASS showed for every column.
+template <class Close>
+__device__ __forceinline__ void seg_scan32(const uint32_t (&v)[32], uint32_t fl, int cb, float bias, float& best,
+                                           int& bcol, Close&& close_seg) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (((fl >> (8 * g)) & 0xffu) == 0u) {
+      float m[8];
+      int ix[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        m[j] = __uint_as_float(v[8 * g + j]) + bias;
+        ix[j] = cb + 8 * g + j;
+      }
+#pragma unroll
+      for (int w = 1; w < 8; w <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2 * w) {
+          const bool gt = m[j + w] > m[j];
+          m[j] = gt ? m[j + w] : m[j];
+          ix[j] = gt ? ix[j + w] : ix[j];
+        }
+      }
+      const bool gt = m[0] > best;
+      best = gt ? m[0] : best;
+      bcol = gt ? ix[0] : bcol;
+    } else {
+#pragma unroll
+      for (int j = 8 * g; j < 8 * g + 8; ++j) {
+        if (fl & (1u << j)) {   // warp-uniform
+          close_seg(cb + j);
+          best = 0.f;
+          bcol = cb + j;
+        }
+        const float val = __uint_as_float(v[j]) + bias;
+        const bool gt = val > best;
+        best = gt ? val : best;
+        bcol = gt ? cb + j : bcol;
+      }
+    }
+  }
+}
+
 // W [Dout, Din] fp32 -> hi/lo TF32 pair in the exact shared-memory image of the pipeline: per K chunk
 // [hi half0..MH-1 | lo half0..MH-1], each half a 128-row x 128-byte tile, K-major, 128B-swizzled
 // (16-byte unit j of row r stored at unit j ^ (r & 7)), zero padded.  One bulk copy per chunk then lands it.
@@ -202,6 +250,7 @@ struct AmaxParams {
   // EPI_STORE: store[(tile position) * lds + f] = acc + bias[f]   (plain Linear: out = x W^T + b)
   float* store;
   int64_t lds;
+  int l2_prefetch;           // CTA-pair kernel: prefetch the next tile's gathered rows to L2
 };
 
 enum { EPI_AMAX = 0, EPI_DISTMULT = 1, EPI_STORE = 2 };
@@ -710,18 +759,7 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
 #endif
           const uint32_t fl = s_flag[ts * 4 + w];
           if (cb + 32 <= cnt) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (fl & (1u << j)) {   // warp-uniform, rare
-                close_seg(cb + j);
-                best = 0.f;
-                bcol = cb + j;
-              }
-              const float val = __uint_as_float(v[j]) + bias;
-              const bool gt = val > best;
-              best = gt ? val : best;
-              bcol = gt ? cb + j : bcol;
-            }
+            seg_scan32(v, fl, cb, bias, best, bcol, close_seg);
           } else {   // ragged last tile
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -793,6 +831,425 @@ __global__ void amax_finalize_kernel(const unsigned long long* __restrict__ pack
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// CTA-PAIR form of the fused a_max forward (tcgen05 cta_group::2), 128 < D <= 256, 3xTF32.
+//
+// What the single-CTA kernel above taught (scripts/prof_amax_tc.py, profiles/r02_ncu_amax_tc.md): per
+// (128 edges x 32 K) item the MMA warp spends ~2,050 cycles issuing/back-pressured -- 24 MMAs that each read an
+// 8 KB operand pair from shared memory: 192 KB + 32 KB of producer stores + 32 KB of W landing = 256 KB at
+// 128 B/clk, i.e. the kernel is SHARED-MEMORY-BANDWIDTH bound, not tensor bound -- and ~1,150 cycles waiting
+// for the epilogue, because both TMEM slots of a tile pair finish together (the pair exists so that one W
+// chunk streamed from L2 feeds 256 edges).
+//
+// A CTA pair removes both: UMMA M = 256 puts feature half r on CTA r (each CTA loads and reads only ITS half of
+// every W chunk), UMMA N = 256 edges per tile of which CTA r gathers / converts rows [128 r, 128 r + 128) -- the
+// B operand is shared across the pair, so each SM's shared memory feeds 8 KB per MMA of twice the size
+// (64 B/clk) -- and a tile is 256 TMEM columns per CTA, so consecutive tiles alternate between two slots and the
+// epilogue of tile i overlaps the MMAs of tile i + 1.  W is still re-streamed once per 256 edges.
+//
+// Cross-CTA protocol (leader = cluster rank 0 issues every MMA):
+//   xfull[s]   leader   32 arrivals: one per producer warp of BOTH CTAs (rank 1 arrives remotely through mapa)
+//   wland[s]   local    the CTA's own W half landed (expect_tx); rank 1's idle MMA warp relays it to
+//   wfull[s]   leader   2 arrivals: own loader (arrive.expect_tx) + the relay
+//   xempty[s], wempty[s], tfull[slot]   in BOTH CTAs, arrived by tcgen05.commit ... multicast::cluster
+//   tempty[slot] leader 8 arrivals: the 4 epilogue warps of the slot in both CTAs
+// ------------------------------------------------------------------------------------------
+constexpr int TILE2 = 256;
+constexpr int XS2 = 3;
+constexpr int WS2 = 3;
+constexpr int PD2 = 2;          // items in flight per producer thread (2, 3, 4 measured alike: 285-292 us; 6 spills)
+constexpr uint32_t STAGE2 = 2 * TILE_BYTES;   // hi | lo, 128 rows x 128 B each
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (.release.cta)
+// semantics on purpose: .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR per arrival (measured: 2,600 cycles
+// per producer item).  What the arrival publishes is shared memory that the writer already made visible to the
+// async proxy (MEMBAR.CTA + FENCE.VIEW.ASYNC) and that only the tensor core reads, or TMEM reads that
+// tcgen05.fence::before_thread_sync ordered.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far retire) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2_kernel(const AmaxParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + WS2 * STAGE2;
+  uint8_t* tail = smem_x + XS2 * STAGE2;
+  uint64_t* xfull_bar = (uint64_t*)tail;          // [XS2]
+  uint64_t* xempty_bar = xfull_bar + XS2;         // [XS2]
+  uint64_t* wfull_bar = xempty_bar + XS2;         // [WS2]
+  uint64_t* wland_bar = wfull_bar + WS2;          // [WS2]
+  uint64_t* wempty_bar = wland_bar + WS2;         // [WS2]
+  uint64_t* tfull_bar = wempty_bar + WS2;         // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  float* s_scale = (float*)(tmem_slot + 4);       // [256]
+  float* s_shift = s_scale + 256;                 // [256]
+  float* s_bias = s_shift + 256;                  // [256]
+  int32_t* s_dst = (int32_t*)(s_bias + 256);      // [2 slots][256]
+  int32_t* s_eid = s_dst + 2 * TILE2;             // [2 slots][256]
+  uint32_t* s_flag = (uint32_t*)(s_eid + 2 * TILE2);  // [2 slots][8]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = p.D;
+  const uint32_t rank = cluster_ctarank();
+  const int ncl = (int)gridDim.x >> 1, cl = (int)blockIdx.x >> 1;
+
+  for (int c = threadIdx.x; c < 256; c += THREADS) {
+    s_scale[c] = (p.x.scale && c < D) ? p.x.scale[c] : 1.f;
+    s_shift[c] = (p.x.scale && c < D) ? p.x.shift[c] : 0.f;
+    s_bias[c] = (p.bias && c < D) ? p.bias[c] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < XS2; ++s) {
+      mbar_init(&xfull_bar[s], 2 * (PROD_THREADS / 32));   // one arrival per producer warp of both CTAs
+      mbar_init(&xempty_bar[s], 1);
+    }
+    for (int s = 0; s < WS2; ++s) {
+      mbar_init(&wfull_bar[s], 2);
+      mbar_init(&wland_bar[s], 1);
+      mbar_init(&wempty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // barriers of the peer are initialised, both TMEM halves allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_tiles = p.num_tiles > cl ? (p.num_tiles - 1 - cl) / ncl + 1 : 0;   // 256-edge tiles of this pair
+  const int nch = p.nchunks;
+  const int total = my_tiles * nch;
+  auto tile_pos0 = [&](int i) { return ((int64_t)cl + (int64_t)i * ncl) * TILE2; };
+
+  if (warp < EPI_WARP0) {
+    // ================================ X PRODUCERS (both CTAs, 128 rows each) ================================
+    constexpr int RPW = 32 / TPR;
+    const int r = warp * RPW + (lane % RPW);   // row of this CTA's half tile
+    const int half = lane / RPW;
+    const bool affine = p.x.scale != nullptr, relu = p.x.relu != 0;
+    const uint32_t roff = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+    uint32_t uoff[NU];
+    int ucol[NU];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      const int u = TPR * j + half;
+      uoff[j] = roff + (uint32_t)((u ^ (r & 7)) << 4);
+      ucol[j] = 4 * u;
+    }
+    float4 buf[PD2][NU];
+    int l_i = 0, l_c = 0, c_i = 0, c_c = 0, lq = 0;
+    const float* xrow = nullptr;
+    bool cvalid = false;
+    // Row ids run one tile ahead of the load cursor: the row pointer never waits on the id, and one item into a tile
+    // (the id has arrived by then) the 4 threads that share a row prefetch the NEXT tile's whole row to L2, two
+    // 128-byte lines each.  An item reads only 128 B of each row and comes back for the next piece ~2,000 cycles
+    // later; without the prefetch every piece is a separate DRAM visit whose latency the producers eat (round-2 ncu:
+    // 30 % of all stall samples on the first use of the gathered registers, independent of the ring depth).
+    auto eid_of = [&](int i) -> int32_t {
+      if (i >= my_tiles) return -1;
+      const int64_t pos = tile_pos0(i) + 128 * (int)rank + r;
+      if (pos >= p.E) return -1;
+      return p.csr_eid ? __ldg(p.csr_eid + pos) : (int32_t)pos;
+    };
+    int32_t e_nxt = eid_of(0);
+    const int pf_lines = (D * 4 + 127) / 128 + 1;     // rows are not 128-byte aligned
+    auto load = [&](float4(&b)[NU]) {
+      if (l_c == 0) {
+        xrow = e_nxt >= 0 ? p.x.data + (size_t)e_nxt * D : nullptr;
+        e_nxt = eid_of(l_i + 1);
+      } else if (l_c == 1 && p.l2_prefetch && e_nxt >= 0) {
+        const char* nrow = reinterpret_cast<const char*>(p.x.data + (size_t)e_nxt * D);
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+          if (2 * half + l < pf_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (2 * half + l) * 128));
+      }
+      const int c0 = l_c * KCH;
+#pragma unroll
+      for (int j = 0; j < NU; ++j)
+        b[j] = (xrow && c0 + ucol[j] < D) ? ld_stream4(xrow + c0 + ucol[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (++l_c == nch) { l_c = 0; ++l_i; }
+    };
+    auto consume = [&](float4(&b)[NU], int q) {
+      if (c_c == 0) cvalid = tile_pos0(c_i) + 128 * (int)rank + r < p.E;
+      const int c0 = c_c * KCH;
+      const int s = q % XS2;
+      const uint32_t ph = (q / XS2) & 1;
+      mbar_wait(&xempty_bar[s], ph ^ 1);
+      uint8_t* xhi = smem_x + (size_t)s * STAGE2;
+      uint8_t* xlo = xhi + TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        const int col = c0 + ucol[j];
+        float4 v = b[j];
+        if (cvalid && col < D) {
+          if (affine) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + col);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + col);
+            v.x = fmaf(sc.x, v.x, sh.x);
+            v.y = fmaf(sc.y, v.y, sh.y);
+            v.z = fmaf(sc.z, v.z, sh.z);
+            v.w = fmaf(sc.w, v.w, sh.w);
+          }
+          if (relu) {
+            v.x = v.x > 0.f ? v.x : 0.f;
+            v.y = v.y > 0.f ? v.y : 0.f;
+            v.z = v.z > 0.f ? v.z : 0.f;
+            v.w = v.w > 0.f ? v.w : 0.f;
+          }
+        }
+        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        *reinterpret_cast<float4*>(xhi + uoff[j]) = hi;
+        *reinterpret_cast<float4*>(xlo + uoff[j]) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&xfull_bar[s], 0);   // one arrival per warp, on the leader's barrier
+      if (++c_c == nch) { c_c = 0; ++c_i; }
+    };
+#pragma unroll
+    for (int u = 0; u < PD2; ++u) {
+      if (lq < total) load(buf[u]);
+      ++lq;
+    }
+    for (int q = 0; q < total; q += PD2) {
+#pragma unroll
+      for (int u = 0; u < PD2; ++u) {
+        if (q + u < total) {
+          consume(buf[u], q + u);
+          if (lq < total) load(buf[u]);
+          ++lq;
+        }
+      }
+    }
+  } else if (warp == WLD_WARP) {
+    // ================================ W LOADER (own feature half: hi tile, lo tile) ================================
+    if (lane == 0) {
+      for (int q = 0; q < total; ++q) {
+        const int s = q % WS2;
+        const uint32_t ph = (q / WS2) & 1;
+        const int c = q % nch;
+        mbar_wait(&wempty_bar[s], ph ^ 1);
+        uint64_t* bar = rank == 0 ? &wfull_bar[s] : &wland_bar[s];
+        mbar_expect_tx(bar, STAGE2);
+        // image of chunk c: [hi half 0 | hi half 1 | lo half 0 | lo half 1], 16 KB each
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)c * 4 * TILE_BYTES;
+        const uint32_t dst = smem_u32(smem_w + (size_t)s * STAGE2);
+        bulk_g2s(dst, src + (size_t)rank * TILE_BYTES, TILE_BYTES, bar);
+        bulk_g2s(dst + TILE_BYTES, src + (size_t)(2 + rank) * TILE_BYTES, TILE_BYTES, bar);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (rank != 0) {
+      // ---- relay: this CTA's W half has landed -> tell the leader
+      if (lane == 0) {
+        for (int q = 0; q < total; ++q) {
+          const int s = q % WS2;
+          mbar_wait(&wland_bar[s], (q / WS2) & 1);
+          mbar_arrive_cluster(&wfull_bar[s], 0);
+        }
+      }
+    } else {
+      // ================================ MMA ISSUER (leader CTA) ================================
+      const uint32_t idesc = umma_idesc(256, TILE2);
+      int q = 0;
+#ifdef MRG_TC_PROF
+      long long t_te = 0, t_w = 0, t_x = 0, t_iss = 0, t_m = clock64();
+#define TC_MARK(v) do { const long long n_ = clock64(); v += n_ - t_m; t_m = n_; } while (0)
+#else
+#define TC_MARK(v) do { } while (0)
+#endif
+      for (int i = 0; i < my_tiles; ++i) {
+        const int slot = i & 1;
+        TC_MARK(t_iss);
+        mbar_wait(&tempty_bar[slot], ((i >> 1) & 1) ^ 1);
+        TC_MARK(t_te);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * TILE2;
+        for (int c = 0; c < nch; ++c, ++q) {
+          const int ws = q % WS2, xs = q % XS2;
+          TC_MARK(t_iss);
+          mbar_wait(&wfull_bar[ws], (q / WS2) & 1);
+          TC_MARK(t_w);
+          mbar_wait(&xfull_bar[xs], (q / XS2) & 1);
+          TC_MARK(t_x);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t whi = smem_u32(smem_w + (size_t)ws * STAGE2), wlo = whi + TILE_BYTES;
+            const uint32_t xhi = smem_u32(smem_x + (size_t)xs * STAGE2), xlo = xhi + TILE_BYTES;
+            const int ksteps = min(KCH, D - c * KCH) / 8;   // zero padded to a multiple of 8
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t ko = k * 32;
+              const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+              umma2_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);   // small terms first
+              umma2_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
+              umma2_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+            }
+            umma2_commit(&xempty_bar[xs]);
+            umma2_commit(&wempty_bar[ws]);
+            if (c == nch - 1) umma2_commit(&tfull_bar[slot]);
+          }
+          __syncwarp();
+        }
+      }
+#ifdef MRG_TC_PROF
+      TC_MARK(t_iss);
+      if (lane == 0 && g_tc_prof) {
+        atomicAdd(g_tc_prof + 0, (unsigned long long)t_te);
+        atomicAdd(g_tc_prof + 1, (unsigned long long)t_w);
+        atomicAdd(g_tc_prof + 2, (unsigned long long)t_x);
+        atomicAdd(g_tc_prof + 3, (unsigned long long)t_iss);
+        atomicAdd(g_tc_prof + 4, (unsigned long long)total);
+      }
+#endif
+#undef TC_MARK
+    }
+  } else {
+    // ================================ EPILOGUE (4 warps per TMEM slot, thread = feature 128 rank + lane id) ==========
+    const int ts = (warp - EPI_WARP0) >> 2;
+    const int et = (threadIdx.x - PROD_THREADS) & 127;
+    const int quad = warp & 3;
+    int32_t* sd = s_dst + ts * TILE2;
+    int32_t* se = s_eid + ts * TILE2;
+    const int f = 128 * (int)rank + et;
+    const bool fvalid = f < D;
+    const float bias = s_bias[f];
+#ifdef MRG_TC_PROF
+    long long e_pre = 0, e_wait = 0, e_scan = 0, e_m = clock64();
+#define EP_MARK(v) do { const long long n_ = clock64(); v += n_ - e_m; e_m = n_; } while (0)
+#else
+#define EP_MARK(v) do { } while (0)
+#endif
+    for (int i = ts; i < my_tiles; i += 2) {
+      const int64_t pos0 = tile_pos0(i);
+      const int cnt = (int)min((int64_t)TILE2, p.E - pos0);
+      EP_MARK(e_scan);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");   // previous tile's readers are done with sd/se
+#pragma unroll
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        const int col = et + 128 * hcol;
+        int32_t e = -1, d = -1;
+        if (col < cnt) {
+          e = __ldg(p.csr_eid + pos0 + col);
+          d = __ldg(p.dst + e);
+        }
+        se[col] = e;
+        sd[col] = d;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+#pragma unroll
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        const int col = et + 128 * hcol;
+        const bool starts = col > 0 && col < cnt && sd[col] != sd[col - 1];
+        const uint32_t word = __ballot_sync(0xffffffffu, starts);
+        if (lane == 0) s_flag[ts * 8 + 4 * hcol + quad] = word;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + ts) : "memory");
+      EP_MARK(e_pre);
+      mbar_wait(&tfull_bar[ts], ((i >> 1) & 1));
+      EP_MARK(e_wait);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * TILE2;
+      float best = 0.f;
+      int bcol = 0;
+      auto close_seg = [&](int col) {
+        if (fvalid) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) |
+                                         (unsigned long long)(0xFFFFFFFFu - (uint32_t)se[bcol]);
+          atomicMax(p.packed + (size_t)sd[col - 1] * D + f, key);
+        }
+      };
+#pragma unroll 1
+      for (int w = 0; w < 8; ++w) {
+        const int cb = 32 * w;
+        if (cb >= cnt) break;
+        uint32_t v[32];
+        tmem_ld32(taddr + cb, v);
+        const uint32_t fl = s_flag[ts * 8 + w];
+        if (cb + 32 <= cnt) {
+          seg_scan32(v, fl, cb, bias, best, bcol, close_seg);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (cb + j < cnt) {
+              if (fl & (1u << j)) {
+                close_seg(cb + j);
+                best = 0.f;
+                bcol = cb + j;
+              }
+              const float val = __uint_as_float(v[j]) + bias;
+              const bool gt = val > best;
+              best = gt ? val : best;
+              bcol = gt ? cb + j : bcol;
+            }
+          }
+        }
+      }
+      if (cnt > 0) close_seg(cnt);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[ts], 0);
+    }
+#ifdef MRG_TC_PROF
+    EP_MARK(e_scan);
+    if (et == 0 && ts == 0 && rank == 0 && g_tc_prof) {
+      atomicAdd(g_tc_prof + 5, (unsigned long long)e_pre);
+      atomicAdd(g_tc_prof + 6, (unsigned long long)e_wait);
+      atomicAdd(g_tc_prof + 7, (unsigned long long)e_scan);
+    }
+#endif
+#undef EP_MARK
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // no remote arrival or peer shared-memory read may outlive either CTA
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace tc
 }  // namespace mrg
 
@@ -847,7 +1304,26 @@ static int amax_tc_fwd_impl(int prec, mrg_act x, const float* W, const float* bi
   p.ldl = 0;
   p.store = nullptr;
   p.lds = 0;
-  if (p.num_tiles > 0) {
+  p.l2_prefetch = 0;
+  // CTA-pair kernel (cta_group::2) for the 3xTF32 form at 128 < D <= 256; MRG_AMAX_PAIR=0 selects the single-CTA kernel
+  static const bool use_pair = [] {
+    const char* v = getenv("MRG_AMAX_PAIR");
+    return !(v && v[0] == '0');
+  }();
+  if (prec == 0 && MH == 2 && use_pair && E > 0) {
+    p.num_tiles = (int)((E + tc::TILE2 - 1) / tc::TILE2);
+    const size_t smem = (size_t)(tc::XS2 + tc::WS2) * tc::STAGE2 + 1024 /*align*/ + 8192 /*tail*/;
+    int grid = 2 * p.num_tiles < kNumSMs ? 2 * p.num_tiles : kNumSMs;
+    grid &= ~1;
+    static const int pf = [] {
+      const char* v = getenv("MRG_TC2_PREFETCH");
+      return v ? atoi(v) : 1;
+    }();
+    p.l2_prefetch = pf;
+    e = cudaFuncSetAttribute(tc::amax_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+    tc::amax_tc2_kernel<<<grid, tc::THREADS, smem, st>>>(p);
+  } else if (p.num_tiles > 0) {
     const size_t smem = prec == 2
         ? (size_t)3 * MH * tc::TILE_BYTES + (size_t)6 * tc::TILE_BYTES + 1024 + 8192
         : (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +

@@ -20,7 +20,7 @@ g = MRGraph.from_triples(N, synth_kg(N, R, T, seed=0), R, device=dev)
 torch.manual_seed(0)
 x = torch.relu(torch.randn(g.M, D, device=dev))
 lin = nn.Linear(D, D).to(dev)
-prof = torch.zeros(16, dtype=torch.int64, device=dev)
+prof = torch.zeros(32, dtype=torch.int64, device=dev)
 for prec in ("fp32", "bf16"):
     K.AMAX_PRECISION = prec
     for _ in range(3):
@@ -42,6 +42,13 @@ for prec in ("fp32", "bf16"):
     tiles0 = p[4] / (7 if prec == "fp32" else 4) / 2      # tiles of slot 0
     print("   epilogue thread 0 of slot 0, cycles per tile: prelude (edge ids, dst, flags, 3 barriers) %.0f, wait for the "
           "accumulator %.0f, TMEM scan + atomics %.0f (of which tcgen05.ld + wait::ld %.0f)" % (p[5] / tiles0, p[6] / tiles0, p[7] / tiles0, p[8] / tiles0))
+    if prec == "fp32" and os.environ.get("MRG_AMAX_PAIR", "1") != "0" and D > 128:
+        items_per_cta = p[4] / 74
+        for rk in (0, 1):
+            v = p[12 + 6 * rk: 18 + 6 * rk]
+            print("   producers of CTA rank %d (one thread per group, summed), cycles per item: issue loads %.0f, wait gathered data %.0f, "
+                  "wait free X stage %.0f, convert + store %.0f, fence.proxy.async %.0f, syncwarp + arrive %.0f"
+                  % ((rk,) + tuple(x / 74 / items_per_cta for x in v)))
 os.environ.pop("MRG_TC_PROF")
 subprocess.run([sys.executable, "-c", "import os,sys; sys.path.insert(0, %r); from mr_gnas_b200 import build; build.build(force=True)" % ROOT],
                env={k: v for k, v in os.environ.items() if k != "MRG_TC_PROF"})
