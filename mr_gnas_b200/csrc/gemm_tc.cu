@@ -855,10 +855,10 @@ __global__ void amax_finalize_kernel(const unsigned long long* __restrict__ pack
 //   tempty[slot] leader 8 arrivals: the 4 epilogue warps of the slot in both CTAs
 // ------------------------------------------------------------------------------------------
 constexpr int TILE2 = 256;
-constexpr int XS2 = 3;
-constexpr int WS2 = 3;
 constexpr int PD2 = 2;          // items in flight per producer thread (2, 3, 4 measured alike: 285-292 us; 6 spills)
-constexpr uint32_t STAGE2 = 2 * TILE_BYTES;   // hi | lo, 128 rows x 128 B each
+__host__ __device__ constexpr uint32_t tc2_stage_bytes(int prec) { return (prec == 2 ? 1 : 2) * TILE_BYTES; }   // [hi | lo] or bf16
+__host__ __device__ constexpr int tc2_xstages(int prec) { return prec == 2 ? 6 : 3; }
+__host__ __device__ constexpr int tc2_wstages(int prec) { return prec == 2 ? 4 : 3; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -891,6 +891,15 @@ __device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint
       : "memory");
 }
 // arrives (once the MMAs issued so far retire) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -898,8 +907,15 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
       : "memory");
 }
 
+// PREC 0: 3xTF32 (hi | lo tiles per stage, three MMAs per K step of 8); PREC 2: bf16 operands (one 16 KB tile per
+// stage holding 64 K elements per 128-byte row, one kind::f16 MMA per K step of 16, twice the stages)
+template <int PREC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2_kernel(const AmaxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr bool BF = PREC == 2;
+  constexpr int KC = BF ? 64 : KCH;
+  constexpr uint32_t STAGE2 = tc2_stage_bytes(PREC);
+  constexpr int XS2 = tc2_xstages(PREC), WS2 = tc2_wstages(PREC);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
   uint8_t* smem_x = smem + WS2 * STAGE2;
@@ -977,7 +993,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
       uoff[j] = roff + (uint32_t)((u ^ (r & 7)) << 4);
       ucol[j] = 4 * u;
     }
-    float4 buf[PD2][NU];
+    constexpr int NB = BF ? 2 * NU : NU;     // float4 pieces per item and thread (a bf16 unit packs two float4)
+    if (BF) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) ucol[j] *= 2;          // a 16-byte bf16 unit covers 8 columns
+    }
+    float4 buf[PD2][NB];
     int l_i = 0, l_c = 0, c_i = 0, c_c = 0, lq = 0;
     const float* xrow = nullptr;
     bool cvalid = false;
@@ -994,7 +1015,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
     };
     int32_t e_nxt = eid_of(0);
     const int pf_lines = (D * 4 + 127) / 128 + 1;     // rows are not 128-byte aligned
-    auto load = [&](float4(&b)[NU]) {
+    auto load = [&](float4(&b)[NB]) {
       if (l_c == 0) {
         xrow = e_nxt >= 0 ? p.x.data + (size_t)e_nxt * D : nullptr;
         e_nxt = eid_of(l_i + 1);
@@ -1004,44 +1025,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
         for (int l = 0; l < 2; ++l)
           if (2 * half + l < pf_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (2 * half + l) * 128));
       }
-      const int c0 = l_c * KCH;
+      const int c0 = l_c * KC;
+      if (BF) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j)
-        b[j] = (xrow && c0 + ucol[j] < D) ? ld_stream4(xrow + c0 + ucol[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NU; ++j) {
+          const int col = c0 + ucol[j];
+          b[2 * j] = (xrow && col < D) ? ld_stream4(xrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[2 * j + 1] = (xrow && col + 4 < D) ? ld_stream4(xrow + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NU; ++j)
+          b[j] = (xrow && c0 + ucol[j] < D) ? ld_stream4(xrow + c0 + ucol[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       if (++l_c == nch) { l_c = 0; ++l_i; }
     };
-    auto consume = [&](float4(&b)[NU], int q) {
+    auto activate = [&](float4 v, int col) {     // lazy BN affine + ReLU of 4 columns of a valid row
+      if (cvalid && col < D) {
+        if (affine) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + col);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + col);
+          v.x = fmaf(sc.x, v.x, sh.x);
+          v.y = fmaf(sc.y, v.y, sh.y);
+          v.z = fmaf(sc.z, v.z, sh.z);
+          v.w = fmaf(sc.w, v.w, sh.w);
+        }
+        if (relu) {
+          v.x = v.x > 0.f ? v.x : 0.f;
+          v.y = v.y > 0.f ? v.y : 0.f;
+          v.z = v.z > 0.f ? v.z : 0.f;
+          v.w = v.w > 0.f ? v.w : 0.f;
+        }
+      }
+      return v;
+    };
+    auto consume = [&](float4(&b)[NB], int q) {
       if (c_c == 0) cvalid = tile_pos0(c_i) + 128 * (int)rank + r < p.E;
-      const int c0 = c_c * KCH;
+      const int c0 = c_c * KC;
       const int s = q % XS2;
       const uint32_t ph = (q / XS2) & 1;
       mbar_wait(&xempty_bar[s], ph ^ 1);
       uint8_t* xhi = smem_x + (size_t)s * STAGE2;
       uint8_t* xlo = xhi + TILE_BYTES;
+      if (BF) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        const int col = c0 + ucol[j];
-        float4 v = b[j];
-        if (cvalid && col < D) {
-          if (affine) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + col);
-            const float4 sh = *reinterpret_cast<const float4*>(s_shift + col);
-            v.x = fmaf(sc.x, v.x, sh.x);
-            v.y = fmaf(sc.y, v.y, sh.y);
-            v.z = fmaf(sc.z, v.z, sh.z);
-            v.w = fmaf(sc.w, v.w, sh.w);
-          }
-          if (relu) {
-            v.x = v.x > 0.f ? v.x : 0.f;
-            v.y = v.y > 0.f ? v.y : 0.f;
-            v.z = v.z > 0.f ? v.z : 0.f;
-            v.w = v.w > 0.f ? v.w : 0.f;
-          }
+        for (int j = 0; j < NU; ++j) {
+          const int col = c0 + ucol[j];
+          const float4 a = activate(b[2 * j], col), c4 = activate(b[2 * j + 1], col + 4);
+          uint4 pk;      // 8 bf16: cvt.rn.bf16x2 packs (first operand -> upper half)
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(a.y), "f"(a.x));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(a.w), "f"(a.z));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.z) : "f"(c4.y), "f"(c4.x));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.w) : "f"(c4.w), "f"(c4.z));
+          *reinterpret_cast<uint4*>(xhi + uoff[j]) = pk;
         }
-        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        *reinterpret_cast<float4*>(xhi + uoff[j]) = hi;
-        *reinterpret_cast<float4*>(xlo + uoff[j]) = lo;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          const float4 v = activate(b[j], c0 + ucol[j]);
+          const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);   // exact; the MMA truncates to tf32
+          *reinterpret_cast<float4*>(xhi + uoff[j]) = hi;
+          *reinterpret_cast<float4*>(xlo + uoff[j]) = lo;
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -1073,11 +1119,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
         mbar_wait(&wempty_bar[s], ph ^ 1);
         uint64_t* bar = rank == 0 ? &wfull_bar[s] : &wland_bar[s];
         mbar_expect_tx(bar, STAGE2);
-        // image of chunk c: [hi half 0 | hi half 1 | lo half 0 | lo half 1], 16 KB each
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)c * 4 * TILE_BYTES;
+        // image of chunk c, 16 KB tiles: [hi half 0 | hi half 1 | lo half 0 | lo half 1]  (bf16: [half 0 | half 1])
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)c * (BF ? 2 : 4) * TILE_BYTES;
         const uint32_t dst = smem_u32(smem_w + (size_t)s * STAGE2);
         bulk_g2s(dst, src + (size_t)rank * TILE_BYTES, TILE_BYTES, bar);
-        bulk_g2s(dst + TILE_BYTES, src + (size_t)(2 + rank) * TILE_BYTES, TILE_BYTES, bar);
+        if (!BF) bulk_g2s(dst + TILE_BYTES, src + (size_t)(2 + rank) * TILE_BYTES, TILE_BYTES, bar);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -1092,7 +1138,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
       }
     } else {
       // ================================ MMA ISSUER (leader CTA) ================================
-      const uint32_t idesc = umma_idesc(256, TILE2);
+      const uint32_t idesc = BF ? umma_idesc_bf16(256, TILE2) : umma_idesc(256, TILE2);
       int q = 0;
 #ifdef MRG_TC_PROF
       long long t_te = 0, t_w = 0, t_x = 0, t_iss = 0, t_m = clock64();
@@ -1118,13 +1164,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
           if (lane == 0) {
             const uint32_t whi = smem_u32(smem_w + (size_t)ws * STAGE2), wlo = whi + TILE_BYTES;
             const uint32_t xhi = smem_u32(smem_x + (size_t)xs * STAGE2), xlo = xhi + TILE_BYTES;
-            const int ksteps = min(KCH, D - c * KCH) / 8;   // zero padded to a multiple of 8
+            const int ksteps = BF ? (min(KC, D - c * KC) + 15) / 16 : min(KC, D - c * KC) / 8;   // zero padded
             for (int k = 0; k < ksteps; ++k) {
-              const uint32_t ko = k * 32;
+              const uint32_t ko = k * 32;    // 8 tf32 / 16 bf16 = 32 bytes inside the swizzled 128-byte row
               const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-              umma2_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);   // small terms first
-              umma2_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
-              umma2_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+              if (BF) {
+                umma2_bf16(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, acc);
+              } else {
+                umma2_tf32(d_tmem, umma_desc(wlo + ko), umma_desc(xhi + ko), idesc, acc);   // small terms first
+                umma2_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xlo + ko), idesc, 1u);
+                umma2_tf32(d_tmem, umma_desc(whi + ko), umma_desc(xhi + ko), idesc, 1u);
+              }
             }
             umma2_commit(&xempty_bar[xs]);
             umma2_commit(&wempty_bar[ws]);
@@ -1310,9 +1360,10 @@ static int amax_tc_fwd_impl(int prec, mrg_act x, const float* W, const float* bi
     const char* v = getenv("MRG_AMAX_PAIR");
     return !(v && v[0] == '0');
   }();
-  if (prec == 0 && MH == 2 && use_pair && E > 0) {
+  if (MH == 2 && use_pair && E > 0) {
     p.num_tiles = (int)((E + tc::TILE2 - 1) / tc::TILE2);
-    const size_t smem = (size_t)(tc::XS2 + tc::WS2) * tc::STAGE2 + 1024 /*align*/ + 8192 /*tail*/;
+    const size_t smem = (size_t)(tc::tc2_xstages(prec) + tc::tc2_wstages(prec)) * tc::tc2_stage_bytes(prec) + 1024 /*align*/ +
+                        8192 /*tail*/;
     int grid = 2 * p.num_tiles < kNumSMs ? 2 * p.num_tiles : kNumSMs;
     grid &= ~1;
     static const int pf = [] {
@@ -1320,9 +1371,15 @@ static int amax_tc_fwd_impl(int prec, mrg_act x, const float* W, const float* bi
       return v ? atoi(v) : 1;
     }();
     p.l2_prefetch = pf;
-    e = cudaFuncSetAttribute(tc::amax_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
-    tc::amax_tc2_kernel<<<grid, tc::THREADS, smem, st>>>(p);
+    if (prec == 2) {
+      e = cudaFuncSetAttribute(tc::amax_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+      tc::amax_tc2_kernel<2><<<grid, tc::THREADS, smem, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(tc::amax_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "amax_tc_fwd smem attr");
+      tc::amax_tc2_kernel<0><<<grid, tc::THREADS, smem, st>>>(p);
+    }
   } else if (p.num_tiles > 0) {
     const size_t smem = prec == 2
         ? (size_t)3 * MH * tc::TILE_BYTES + (size_t)6 * tc::TILE_BYTES + 1024 + 8192
