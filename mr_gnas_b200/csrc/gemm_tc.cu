@@ -928,7 +928,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
   uint64_t* tfull_bar = wempty_bar + WS2;         // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
-  float* s_scale = (float*)(tmem_slot + 4);       // [256]
+  float* s_scale = (float*)(tail + 512);          // [256]  (16-byte aligned: read with 128-bit loads)
   float* s_shift = s_scale + 256;                 // [256]
   float* s_bias = s_shift + 256;                  // [256]
   int32_t* s_dst = (int32_t*)(s_bias + 256);      // [2 slots][256]

@@ -208,6 +208,43 @@ def _amax_expected_grads(x, W, b, arg, E, cot):
     return xo.grad, Wo.grad, bo.grad
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("D", [64, 136, 200, 256])
+def test_amax_tc_reads_its_input_through_lazy_bn(dev, D, prec):
+    """The fused a_max kernels read x through relu(scale * x + shift) (the lazy BatchNorm of the producing state,
+    DESIGN 3); the result must equal the same kernel on the materialised activation (one fmaf per element either
+    way, so bit-identical), rows / residual included.  D > 128 runs the CTA-pair kernel, D <= 128 the single-CTA one."""
+    from mr_gnas_b200 import functional as K
+    from mr_gnas_b200._lib import act, call, ptr, stream
+    from mr_gnas_b200.graph import MRGraph
+    N, R, T = 3000, 9, 20011
+    g = MRGraph.from_triples(N, O.synth_kg(N, R, T, seed=D), R, device=dev)
+    E, M = g.E, g.M
+    torch.manual_seed(D)
+    x = torch.randn(M, D, device=dev)
+    a = torch.rand(D, device=dev) + 0.5
+    b = torch.randn(D, device=dev) * 0.3
+    W = torch.randn(D, D, device=dev) / D ** 0.5
+    bias = torch.randn(D, device=dev) * 0.1
+    xm = torch.relu(torch.addcmul(b, x, a))          # fused multiply-add on the device, as the kernel's fmaf
+    ws = K._tc_workspace(N, D, dev)
+    name = "mrg_amax_tc_fwd_bf16" if prec == "bf16" else "mrg_amax_tc_fwd"
+    outs = []
+    for xa, ra in ((act(x, a, b, True), act(x[E:], a, b, True)), (act(xm), act(xm[E:]))):
+        out = torch.empty(N, D, device=dev)
+        arg = torch.empty(N, D, dtype=torch.int32, device=dev)
+        call(name, xa, ptr(W), ptr(bias), ptr(g.csr.idx), ptr(g.dst), E, N, D, ra, ptr(out), ptr(arg), ptr(ws),
+             ws.numel(), stream())
+        outs.append((out.clone(), arg.clone()))
+    torch.cuda.synchronize()
+    assert bool((outs[0][0] == outs[1][0]).all()) and bool((outs[0][1] == outs[1][1]).all())
+    ref = torch.relu(xm[:E].double() @ W.double().t() + bias.double())
+    full = torch.zeros(N, D, dtype=torch.float64, device=dev).index_reduce_(0, g.dst.long(), ref, "amax", include_self=True)
+    full += xm[E:].double()
+    tol = 2e-2 if prec == "bf16" else 1e-5
+    assert float((outs[0][0].double() - full).abs().max()) <= tol * float(full.abs().max())
+
+
 @pytest.mark.parametrize("D", [8, 64, 128, 200, 256])
 @pytest.mark.parametrize("shape", ["zipf", "hub", "tiny"])
 def test_amax_tensor_core_vs_simt_and_oracle(dev, D, shape):
