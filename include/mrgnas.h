@@ -380,6 +380,20 @@ size_t mrg_linear_tc_workspace_bytes(int32_t K);
 int mrg_linear_tc_fwd(const float* x, const float* W, const float* bias, int64_t rows, int32_t K, int32_t F, float* out,
                       int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Reduction GEMM on the tcgen05 main loop (3xTF32, fp32-class accuracy), the reduction running over the ROWS:
+ *   C[f1, f2] = sum_n A[n, f1] * B[n, f2]          A [rows, F1] (lda), B [rows, F2] (ldb), C [F1, F2] (ldc)
+ *   a_kmajor != 0: A is given transposed, At [F1, rows] (lda) -- the reduction index already contiguous.
+ * Replaces the fp32 SIMT library GEMMs behind autograd on the path: the weight gradient dW = dY^T X of every
+ * nn.Linear (model_lp.py:70-71,124; operations_lp.py:230-250,266-288,356-390; model.py:22-28) and the two backward
+ * GEMMs of sf_DisMult_op's `torch.mm(obj_emb, all_ent.transpose(1, 0))` (operations_lp.py:115-127): dq = dl . ent
+ * (a_kmajor, A = dl [B, N]) and dent = dl^T . q.  Split over the rows into per-CTA partials folded in a fixed order
+ * (deterministic).  Any F1, F2 >= 1; rows >= 0 (rows == 0 zeroes C).
+ * ---------------------------------------------------------------------------------- */
+size_t mrg_gemm_red_workspace_bytes(int64_t rows, int32_t F1, int32_t F2);
+int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int64_t rows, int32_t F1,
+                 int32_t F2, float* C, int64_t ldc, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

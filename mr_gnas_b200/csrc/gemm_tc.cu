@@ -1300,6 +1300,203 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Reduction GEMM on tcgen05 (3xTF32):  C[F1, F2] = sum_n A[n, F1] * B[n, F2]
+// -- the weight gradient dW = dY^T X of every nn.Linear on the path (model_lp.py:70-71,124; operations_lp.py
+// Linear candidates) and both backward GEMMs of sf_DisMult_op (operations_lp.py:115-127): dq = dl . ent (A given
+// K-major: dl is [B, N]) and dent = dl^T . q.  Round 2 had these on cuBLAS fp32 SIMT kernels (0.5 ms of the step).
+//
+// Both operands have the reduction index as their SLOW dimension, the opposite of what a K-major UMMA operand
+// wants, so the 16 producer warps transpose on the way into shared memory: lane = reduction row n, a thread loads
+// 8 consecutive features of its row (two 128-bit loads) and scatters them with 32-bit stores into 8 rows of the
+// 128B-swizzled K-major tile.  For a fixed tile row the 32 lanes hit word ((n >> 2) ^ (row & 7)) * 4 + (n & 3):
+// 32 distinct banks, no conflicts.  CTA tile = 256 x 128 of C (two M = 128 accumulators, 256 TMEM columns), the
+// reduction is split over `slices` CTAs per tile so that the grid fills the GPU; partials go to a workspace
+// TRANSPOSED ([slice][F2][F1]: TMEM lane = C row, so a warp writes 32 consecutive C rows of one column) and a second
+// kernel folds the slices in a fixed order while transposing back -- deterministic.
+// ------------------------------------------------------------------------------------------
+constexpr int RM = 256, RN = 128, RK = 32, RSTAGES = 2;
+constexpr uint32_t RA_TILE = 2 * TILE_BYTES;                 // 256 rows x 128 B
+constexpr uint32_t RB_TILE = TILE_BYTES;                     // 128 rows x 128 B
+constexpr uint32_t RSTAGE = 2 * RA_TILE + 2 * RB_TILE;       // A hi | A lo | B hi | B lo = 96 KB
+constexpr int RWARPS = 16;
+constexpr int RTHREADS = RWARPS * 32 + 32;                   // producer / epilogue warps + the MMA warp
+
+struct RedParams {
+  const float* A;       // [rows, F1] (lda), or with a_kmajor: At [F1, rows] (lda)
+  const float* B;       // [rows, F2] (ldb)
+  int64_t lda, ldb, rows;
+  int a_kmajor, a_vec, b_vec;   // *_vec: 128-bit loads allowed (16-byte aligned rows, feature count % 8 == 0)
+  int F1, F2, m_tiles, n_tiles, slices, cps, nchunks;
+  float* part;          // [slices][n_tiles * RN][m_tiles * RM]
+};
+
+__device__ __forceinline__ void red_load8(const float* row, int f0, int F, bool rvalid, bool vec, float (&v)[8]) {
+  if (rvalid && vec && f0 + 8 <= F) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row + f0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row + f0 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (rvalid && f0 + e < F) ? __ldg(row + f0 + e) : 0.f;
+  }
+}
+// 8 consecutive tile rows (R0 .. R0 + 7, R0 % 8 == 0), column = lane, hi and lo tiles
+__device__ __forceinline__ void red_scatter8(uint8_t* hi_tile, uint32_t lo_off, int R0, int lane, const float (&v)[8]) {
+  uint8_t* base = hi_tile + (uint32_t)(R0 >> 7) * TILE_BYTES + (uint32_t)((R0 & 127) >> 3) * 1024 + (uint32_t)(lane & 3) * 4;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    uint8_t* a = base + e * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)e) << 4);
+    const float h = tf32_rna(v[e]);
+    *reinterpret_cast<float*>(a) = h;
+    *reinterpret_cast<float*>(a + lo_off) = v[e] - h;
+  }
+}
+
+__global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* tail = smem + RSTAGES * RSTAGE;
+  uint64_t* full_bar = (uint64_t*)tail;            // [RSTAGES] 16 producer-warp arrivals
+  uint64_t* empty_bar = full_bar + RSTAGES;        // [RSTAGES] MMAs that read the stage retired
+  uint64_t* tfull_bar = empty_bar + RSTAGES;       // accumulators complete
+  uint32_t* tmem_slot = (uint32_t*)(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int mt = blockIdx.x % p.m_tiles, nt = (blockIdx.x / p.m_tiles) % p.n_tiles, sl = blockIdx.x / (p.m_tiles * p.n_tiles);
+  const int m0 = mt * RM, k0 = nt * RN;
+  const int c_begin = sl * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
+  const int nch = c_end - c_begin;                 // >= 1 by construction of `slices`
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RSTAGES; ++s) {
+      mbar_init(&full_bar[s], RWARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == RWARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < RWARPS) {
+    // ================================ PRODUCERS (transpose into K-major tiles) ================================
+    for (int ci = 0; ci < nch; ++ci) {
+      const int s = ci % RSTAGES;
+      const int64_t n = (int64_t)(c_begin + ci) * RK + lane;     // reduction row of this lane
+      const bool nvalid = n < p.rows;
+      float va0[8], va1[8], vb[8];
+      float ka[RM / RWARPS];
+      if (p.a_kmajor) {          // At[F1][rows]: a warp copies 16 tile rows, lane = reduction index (coalesced)
+#pragma unroll
+        for (int i = 0; i < RM / RWARPS; ++i) {
+          const int f = m0 + warp * (RM / RWARPS) + i;
+          ka[i] = (nvalid && f < p.F1) ? __ldg(p.A + (size_t)f * p.lda + n) : 0.f;
+        }
+      } else {
+        const float* arow = p.A + (size_t)(nvalid ? n : 0) * p.lda;
+        red_load8(arow, m0 + 8 * warp, p.F1, nvalid, p.a_vec != 0, va0);
+        red_load8(arow, m0 + 8 * (warp + RWARPS), p.F1, nvalid, p.a_vec != 0, va1);
+      }
+      red_load8(p.B + (size_t)(nvalid ? n : 0) * p.ldb, k0 + 8 * warp, p.F2, nvalid, p.b_vec != 0, vb);
+      mbar_wait(&empty_bar[s], ((ci / RSTAGES) & 1) ^ 1);
+      uint8_t* st = smem + (size_t)s * RSTAGE;
+      if (p.a_kmajor) {
+#pragma unroll
+        for (int i = 0; i < RM / RWARPS; ++i) {
+          const int R = warp * (RM / RWARPS) + i;
+          uint8_t* a = st + (uint32_t)(R >> 7) * TILE_BYTES + (uint32_t)((R & 127) >> 3) * 1024 + (uint32_t)(R & 7) * 128 +
+                       ((((uint32_t)lane >> 2) ^ (uint32_t)(R & 7)) << 4) + (uint32_t)(lane & 3) * 4;
+          const float h = tf32_rna(ka[i]);
+          *reinterpret_cast<float*>(a) = h;
+          *reinterpret_cast<float*>(a + RA_TILE) = ka[i] - h;
+        }
+      } else {
+        red_scatter8(st, RA_TILE, 8 * warp, lane, va0);
+        red_scatter8(st, RA_TILE, 8 * (warp + RWARPS), lane, va1);
+      }
+      red_scatter8(st + 2 * RA_TILE, RB_TILE, 8 * warp, lane, vb);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ================================ EPILOGUE (same warps): TMEM -> transposed partial ================================
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3, h = (warp >> 2) & 1, chalf = warp >> 3;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + h * RN + chalf * 64;
+    const int64_t M2 = (int64_t)p.m_tiles * RM, N2 = (int64_t)p.n_tiles * RN;
+    float* o = p.part + ((int64_t)sl * N2 + k0 + chalf * 64) * M2 + m0 + h * 128 + quad * 32 + lane;
+#pragma unroll 1
+    for (int cb = 0; cb < 64; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + cb, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[(int64_t)(cb + j) * M2] = __uint_as_float(v[j]);
+    }
+  } else {
+    // ================================ MMA ISSUER ================================
+    const uint32_t idesc = umma_idesc(128, RN);
+    for (int ci = 0; ci < nch; ++ci) {
+      const int s = ci % RSTAGES;
+      mbar_wait(&full_bar[s], (ci / RSTAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * RSTAGE);
+        const uint32_t bhi = st + 2 * RA_TILE, blo = bhi + RB_TILE;
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t ahi = st + h * TILE_BYTES, alo = ahi + RA_TILE;
+          const uint32_t d_tmem = tmem_base + h * RN;
+          for (int k = 0; k < RK / 8; ++k) {
+            const uint32_t ko = k * 32;
+            const uint32_t acc = (ci > 0 || k > 0) ? 1u : 0u;
+            umma_tf32(d_tmem, umma_desc(alo + ko), umma_desc(bhi + ko), idesc, acc);   // small terms first
+            umma_tf32(d_tmem, umma_desc(ahi + ko), umma_desc(blo + ko), idesc, 1u);
+            umma_tf32(d_tmem, umma_desc(ahi + ko), umma_desc(bhi + ko), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (ci == nch - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RWARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// C[f, k] = sum_s part[s][k][f]  (fixed slice order; 32 x 32 tiles transposed through shared memory)
+__global__ void __launch_bounds__(256) gemm_red_fold_kernel(const float* __restrict__ part, int slices, int64_t N2, int64_t M2,
+                                                            int F1, int F2, float* __restrict__ C, int64_t ldc) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ft = blockIdx.x * 32, kt = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int kk = ty + 8 * i;
+    float acc = 0.f;
+    if (kt + kk < F2 && ft + tx < F1)
+      for (int s = 0; s < slices; ++s) acc += part[((int64_t)s * N2 + kt + kk) * M2 + ft + tx];
+    tile[kk][tx] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ff = ty + 8 * i;
+    if (ft + ff < F1 && kt + tx < F2) C[(int64_t)(ft + ff) * ldc + kt + tx] = tile[tx][ff];
+  }
+}
+
 }  // namespace tc
 }  // namespace mrg
 
@@ -1557,5 +1754,69 @@ extern "C" int mrg_linear_tc_fwd(const float* x, const float* W, const float* bi
     }
   }
   MRG_LAUNCH_CHECK("linear_tc_fwd");
+  return MRG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Reduction GEMM  C[F1, F2] = sum_n A[n, F1] * B[n, F2]   (tc::gemm_red_kernel)
+// ------------------------------------------------------------------------------------------
+static void gemm_red_plan(int64_t rows, int32_t F1, int32_t F2, int* m_tiles, int* n_tiles, int* slices, int* cps,
+                          int* nchunks) {
+  *m_tiles = (F1 + tc::RM - 1) / tc::RM;
+  *n_tiles = (F2 + tc::RN - 1) / tc::RN;
+  *nchunks = (int)((rows + tc::RK - 1) / tc::RK);
+  int want = kNumSMs / (*m_tiles * *n_tiles);
+  if (want < 1) want = 1;
+  if (want > *nchunks) want = *nchunks;
+  *cps = (*nchunks + want - 1) / want;
+  *slices = (*nchunks + *cps - 1) / *cps;
+}
+
+extern "C" size_t mrg_gemm_red_workspace_bytes(int64_t rows, int32_t F1, int32_t F2) {
+  if (rows <= 0 || F1 <= 0 || F2 <= 0) return 0;
+  int mt, nt, sl, cps, nch;
+  gemm_red_plan(rows, F1, F2, &mt, &nt, &sl, &cps, &nch);
+  return (size_t)sl * nt * tc::RN * mt * tc::RM * sizeof(float);
+}
+
+extern "C" int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int64_t rows,
+                            int32_t F1, int32_t F2, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  MRG_CHECK_ARG(F1 > 0 && F2 > 0 && rows >= 0 && C, "gemm_red: bad shape");
+  MRG_CHECK_ARG(ldc >= F2, "gemm_red: ldc < F2");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {
+    cudaError_t e0 = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)F2 * sizeof(float), F1, st);
+    if (e0 != cudaSuccess) return cuda_fail(e0, "gemm_red memset");
+    return MRG_OK;
+  }
+  MRG_CHECK_ARG(A && B && workspace, "gemm_red: null pointer");
+  MRG_CHECK_ARG(a_kmajor ? lda >= rows : lda >= F1, "gemm_red: lda too small");
+  MRG_CHECK_ARG(ldb >= F2, "gemm_red: ldb < F2");
+  if (workspace_bytes < mrg_gemm_red_workspace_bytes(rows, F1, F2)) {
+    set_error("gemm_red: workspace too small");
+    return MRG_ERR_WORKSPACE;
+  }
+  tc::RedParams p;
+  p.A = A;
+  p.B = B;
+  p.lda = lda;
+  p.ldb = ldb;
+  p.rows = rows;
+  p.a_kmajor = a_kmajor ? 1 : 0;
+  p.a_vec = (!a_kmajor && lda % 4 == 0 && ((uintptr_t)A & 15) == 0) ? 1 : 0;
+  p.b_vec = (ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
+  p.F1 = F1;
+  p.F2 = F2;
+  gemm_red_plan(rows, F1, F2, &p.m_tiles, &p.n_tiles, &p.slices, &p.cps, &p.nchunks);
+  p.part = (float*)workspace;
+  const size_t smem = (size_t)tc::RSTAGES * tc::RSTAGE + 1024 /*align*/ + 256 /*tail*/;
+  cudaError_t e = cudaFuncSetAttribute(tc::gemm_red_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_red smem attr");
+  tc::gemm_red_kernel<<<p.m_tiles * p.n_tiles * p.slices, tc::RTHREADS, smem, st>>>(p);
+  dim3 fg((F1 + 31) / 32, (F2 + 31) / 32);
+  tc::gemm_red_fold_kernel<<<fg, 256, 0, st>>>(p.part, p.slices, (int64_t)p.n_tiles * tc::RN, (int64_t)p.m_tiles * tc::RM, F1,
+                                               F2, C, ldc);
+  MRG_LAUNCH_CHECK("gemm_red");
   return MRG_OK;
 }

@@ -583,10 +583,33 @@ def _linear_tc(x, W, bias, out_cols=None):
     return out
 
 
+_red_ws = {}
+USE_TC_GEMM_RED = True      # False: torch.mm (library GEMM) for the reductions over the rows
+
+
+def gemm_red(A, B, a_kmajor=False):
+    """A^T B with the reduction over the rows on the tensor cores (mrg_gemm_red, 3xTF32): A [rows, F1], B [rows, F2]
+    -> [F1, F2]; a_kmajor: A is passed as At [F1, rows].  Weight gradients and the DistMult backward GEMMs."""
+    A, B = _f32c(A), _f32c(B)
+    rows, F2 = B.shape
+    F1 = A.shape[0] if a_kmajor else A.shape[1]
+    if not (USE_TC_GEMM_RED and A.is_cuda and rows >= 256):
+        return torch.mm(A if a_kmajor else A.t(), B)
+    lib = _lib.load()
+    nbytes = int(lib.mrg_gemm_red_workspace_bytes(rows, F1, F2))
+    key = str(A.device)
+    if key not in _red_ws or _red_ws[key].numel() < nbytes:
+        _red_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    ws = _red_ws[key]
+    C = torch.empty(F1, F2, dtype=torch.float32, device=A.device)
+    call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(ws),
+         ws.numel(), stream(), nbytes=rows * (F1 + F2) * 4)
+    return C
+
+
 class LinearTC(torch.autograd.Function):
-    """nn.Linear forward and input gradient on the tensor cores with fp32-class accuracy (3xTF32): the cell's
-    `concat` Linear and `linear_e` (model_lp.py:70-71,124).  The weight gradient (reduction over the rows) stays a
-    library GEMM."""
+    """nn.Linear forward, input gradient and weight gradient on the tensor cores with fp32-class accuracy (3xTF32):
+    the cell's `concat` Linear and `linear_e` (model_lp.py:70-71,124), the Linear candidates."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -604,7 +627,7 @@ class LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _linear_tc(gy, weight.t().contiguous(), None)      # dY [rows, F] x W [F, K]
         if ctx.needs_input_grad[1]:
-            dw = torch.mm(gy.t(), x)
+            dw = gemm_red(gy, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = gy.sum(0)
         return dx, dw, db
@@ -632,7 +655,7 @@ _dm_ws = {}
 class DistMultBCE(torch.autograd.Function):
     """loss = BCELoss(sigmoid((sub_emb * rel_emb) @ all_ent.T), label) in ONE tcgen05 kernel (mrg_distmult_bce_fwd):
     sf_DisMult_op.forward (operations_lp.py:115-127) + nn.BCELoss (mr_lp_train.py:116) for the training loss.
-    Backward: dlogit from the stored logits (mrg_sigmoid_bce_bwd), then the two plain library GEMMs."""
+    Backward: dlogit from the stored logits (mrg_sigmoid_bce_bwd), then the two reduction GEMMs (mrg_gemm_red)."""
 
     @staticmethod
     def forward(ctx, all_ent, sub_emb, rel_emb, label):
@@ -660,8 +683,8 @@ class DistMultBCE(torch.autograd.Function):
         dl = torch.empty_like(logit)
         gs = gl.reshape(1).float().contiguous()
         call("mrg_sigmoid_bce_bwd", ptr(logit), ptr(label), logit.numel(), ptr(gs), ptr(dl), stream())
-        dq = torch.mm(dl, all_ent)
-        dent = torch.mm(dl.t(), query) if ctx.needs_input_grad[0] else None
+        dq = gemm_red(dl, all_ent, a_kmajor=True)
+        dent = gemm_red(dl, query) if ctx.needs_input_grad[0] else None
         return dent, dq * rel_emb, dq * sub_emb, None
 
 

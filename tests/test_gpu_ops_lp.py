@@ -499,6 +499,51 @@ def test_linear_tc_vs_fp64(dev, rows, K, F):
     _check("db", lin.bias.grad, b64.grad.float())
 
 
+@pytest.mark.parametrize("rows,F1,F2,kmajor", [
+    (14541, 200, 800, False), (14541, 200, 200, False),      # weight gradients of `concat` and `linear_e` at C1
+    (14541, 256, 200, True),                                  # DistMult dq = dl . ent   (dl [B, N] is the K-major operand)
+    (256, 14541, 200, False),                                 # DistMult dent = dl^T . q (odd leading dimension: scalar loads)
+    (16, 803, 64, False), (1000, 64, 64, False), (2500, 520, 136, False), (33, 8, 8, True), (4097, 24, 300, True)])
+def test_gemm_red_vs_fp64(dev, rows, F1, F2, kmajor):
+    """mrg_gemm_red: C = A^T B with the reduction over the rows (3xTF32, split over the rows, deterministic fold)
+    against fp64, the fp32 library GEMM as the yardstick; ragged tiles, rows not a multiple of 32, odd leading
+    dimensions, both operand forms; bit-identical when repeated."""
+    from mr_gnas_b200._lib import call, ptr, stream, load
+    torch.manual_seed(rows + F1 + F2)
+    A = torch.randn(rows, F1, device=dev)
+    B = torch.randn(rows, F2, device=dev)
+    Ain = A.t().contiguous() if kmajor else A
+    lib = load()
+    ws = torch.empty(max(int(lib.mrg_gemm_red_workspace_bytes(rows, F1, F2)), 16), dtype=torch.uint8, device=dev)
+    outs = []
+    for _ in range(2):
+        C = torch.full((F1, F2 + 3), 7.0, device=dev)          # ldc > F2: the padding columns must stay untouched
+        call("mrg_gemm_red", ptr(Ain), Ain.shape[1], 1 if kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2 + 3,
+             ptr(ws), ws.numel(), stream())
+        outs.append(C)
+    torch.cuda.synchronize()
+    assert bool((outs[0] == outs[1]).all())
+    assert bool((outs[0][:, F2:] == 7.0).all())
+    ref = A.double().t() @ B.double()
+    lib32 = A.t() @ B
+    scale = float(ref.abs().max())
+    e_tc = float((outs[0][:, :F2].double() - ref).abs().max()) / scale
+    e_lib = float((lib32.double() - ref).abs().max()) / scale
+    print(f"gemm_red rows={rows} F1={F1} F2={F2} kmajor={kmajor}: err vs fp64 {e_tc:.2e} (library fp32 GEMM {e_lib:.2e})")
+    assert e_tc <= max(1e-5, 4 * e_lib)
+
+
+def test_gemm_red_zero_rows(dev):
+    from mr_gnas_b200._lib import call, ptr, stream
+    C = torch.full((8, 16), 3.0, device=dev)
+    A = torch.zeros(1, 8, device=dev)
+    B = torch.zeros(1, 16, device=dev)
+    ws = torch.empty(16, dtype=torch.uint8, device=dev)
+    call("mrg_gemm_red", ptr(A), 8, 0, ptr(B), 16, 0, 8, 16, ptr(C), 16, ptr(ws), ws.numel(), stream())
+    torch.cuda.synchronize()
+    assert bool((C == 0).all())
+
+
 @pytest.mark.parametrize("D", [64, 200, 256])
 def test_amax_bf16_variant(dev, D):
     """Reduced-precision variant of the fused a_max forward (mrg_amax_tc_fwd_bf16: activated rows and W rounded to
