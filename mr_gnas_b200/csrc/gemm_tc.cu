@@ -1328,17 +1328,20 @@ struct RedParams {
   int64_t lda, ldb, rows;
   int a_kmajor, a_vec, b_vec;   // *_vec: 128-bit loads allowed (16-byte aligned rows, feature count % 8 == 0)
   int F1, F2, m_tiles, n_tiles, slices, cps, nchunks;
+  int ones_col;         // 1: B gets a virtual column F2 of ones (column sums of A = the bias gradient) -> F2 + 1 columns
   float* part;          // [slices][n_tiles * RN][m_tiles * RM]
 };
 
-__device__ __forceinline__ void red_load8(const float* row, int f0, int F, bool rvalid, bool vec, float (&v)[8]) {
+// `ones_at` >= 0: the virtual feature of that index reads as 1 for valid rows (bias-gradient column)
+__device__ __forceinline__ void red_load8(const float* row, int f0, int F, bool rvalid, bool vec, float (&v)[8],
+                                          int ones_at = -1) {
   if (rvalid && vec && f0 + 8 <= F) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(row + f0));
     const float4 b = __ldg(reinterpret_cast<const float4*>(row + f0 + 4));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (rvalid && f0 + e < F) ? __ldg(row + f0 + e) : 0.f;
+    for (int e = 0; e < 8; ++e) v[e] = (rvalid && f0 + e < F) ? __ldg(row + f0 + e) : ((rvalid && f0 + e == ones_at) ? 1.f : 0.f);
   }
 }
 // 8 consecutive tile rows (R0 .. R0 + 7, R0 % 8 == 0), column = lane, hi and lo tiles
@@ -1405,7 +1408,7 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
         red_load8(arow, m0 + 8 * warp, p.F1, nvalid, p.a_vec != 0, va0);
         red_load8(arow, m0 + 8 * (warp + RWARPS), p.F1, nvalid, p.a_vec != 0, va1);
       }
-      red_load8(p.B + (size_t)(nvalid ? n : 0) * p.ldb, k0 + 8 * warp, p.F2, nvalid, p.b_vec != 0, vb);
+      red_load8(p.B + (size_t)(nvalid ? n : 0) * p.ldb, k0 + 8 * warp, p.F2, nvalid, p.b_vec != 0, vb, p.ones_col ? p.F2 : -1);
       mbar_wait(&empty_bar[s], ((ci / RSTAGES) & 1) ^ 1);
       uint8_t* st = smem + (size_t)s * RSTAGE;
       if (p.a_kmajor) {
@@ -1476,8 +1479,18 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
 }
 
 // C[f, k] = sum_s part[s][k][f]  (fixed slice order; 32 x 32 tiles transposed through shared memory)
+// colsum (optional): column F2 of the partials = sum_n A[n, f] (the virtual ones column of B)
 __global__ void __launch_bounds__(256) gemm_red_fold_kernel(const float* __restrict__ part, int slices, int64_t N2, int64_t M2,
-                                                            int F1, int F2, float* __restrict__ C, int64_t ldc) {
+                                                            int F1, int F2, float* __restrict__ C, int64_t ldc,
+                                                            float* __restrict__ colsum) {
+  if (colsum && blockIdx.y == 0 && threadIdx.x < 32) {
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    if (f < F1) {
+      float acc = 0.f;
+      for (int s = 0; s < slices; ++s) acc += part[((int64_t)s * N2 + F2) * M2 + f];
+      colsum[f] = acc;
+    }
+  }
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ft = blockIdx.x * 32, kt = blockIdx.y * 32;
@@ -1763,7 +1776,7 @@ extern "C" int mrg_linear_tc_fwd(const float* x, const float* W, const float* bi
 static void gemm_red_plan(int64_t rows, int32_t F1, int32_t F2, int* m_tiles, int* n_tiles, int* slices, int* cps,
                           int* nchunks) {
   *m_tiles = (F1 + tc::RM - 1) / tc::RM;
-  *n_tiles = (F2 + tc::RN - 1) / tc::RN;
+  *n_tiles = (F2 + 1 + tc::RN - 1) / tc::RN;      // room for the virtual ones column (bias gradient)
   *nchunks = (int)((rows + tc::RK - 1) / tc::RK);
   int want = kNumSMs / (*m_tiles * *n_tiles);
   if (want < 1) want = 1;
@@ -1780,13 +1793,15 @@ extern "C" size_t mrg_gemm_red_workspace_bytes(int64_t rows, int32_t F1, int32_t
 }
 
 extern "C" int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int64_t rows,
-                            int32_t F1, int32_t F2, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            int32_t F1, int32_t F2, float* C, int64_t ldc, float* colsum, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   MRG_CHECK_ARG(F1 > 0 && F2 > 0 && rows >= 0 && C, "gemm_red: bad shape");
   MRG_CHECK_ARG(ldc >= F2, "gemm_red: ldc < F2");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) {
     cudaError_t e0 = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)F2 * sizeof(float), F1, st);
+    if (e0 != cudaSuccess) return cuda_fail(e0, "gemm_red memset");
+    if (colsum) e0 = cudaMemsetAsync(colsum, 0, (size_t)F1 * sizeof(float), st);
     if (e0 != cudaSuccess) return cuda_fail(e0, "gemm_red memset");
     return MRG_OK;
   }
@@ -1808,6 +1823,7 @@ extern "C" int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const
   p.b_vec = (ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
   p.F1 = F1;
   p.F2 = F2;
+  p.ones_col = colsum ? 1 : 0;
   gemm_red_plan(rows, F1, F2, &p.m_tiles, &p.n_tiles, &p.slices, &p.cps, &p.nchunks);
   p.part = (float*)workspace;
   const size_t smem = (size_t)tc::RSTAGES * tc::RSTAGE + 1024 /*align*/ + 256 /*tail*/;
@@ -1816,7 +1832,7 @@ extern "C" int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const
   tc::gemm_red_kernel<<<p.m_tiles * p.n_tiles * p.slices, tc::RTHREADS, smem, st>>>(p);
   dim3 fg((F1 + 31) / 32, (F2 + 31) / 32);
   tc::gemm_red_fold_kernel<<<fg, 256, 0, st>>>(p.part, p.slices, (int64_t)p.n_tiles * tc::RN, (int64_t)p.m_tiles * tc::RM, F1,
-                                               F2, C, ldc);
+                                               F2, C, ldc, colsum);
   MRG_LAUNCH_CHECK("gemm_red");
   return MRG_OK;
 }

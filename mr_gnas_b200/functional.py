@@ -587,14 +587,16 @@ _red_ws = {}
 USE_TC_GEMM_RED = True      # False: torch.mm (library GEMM) for the reductions over the rows
 
 
-def gemm_red(A, B, a_kmajor=False):
+def gemm_red(A, B, a_kmajor=False, colsum=False):
     """A^T B with the reduction over the rows on the tensor cores (mrg_gemm_red, 3xTF32): A [rows, F1], B [rows, F2]
-    -> [F1, F2]; a_kmajor: A is passed as At [F1, rows].  Weight gradients and the DistMult backward GEMMs."""
+    -> [F1, F2]; a_kmajor: A is passed as At [F1, rows].  Weight gradients and the DistMult backward GEMMs.
+    colsum: also return A.sum(0) (the bias gradient), computed by the same launch."""
     A, B = _f32c(A), _f32c(B)
     rows, F2 = B.shape
     F1 = A.shape[0] if a_kmajor else A.shape[1]
     if not (USE_TC_GEMM_RED and A.is_cuda and rows >= 256):
-        return torch.mm(A if a_kmajor else A.t(), B)
+        C = torch.mm(A if a_kmajor else A.t(), B)
+        return (C, A.sum(1 if a_kmajor else 0)) if colsum else C
     lib = _lib.load()
     nbytes = int(lib.mrg_gemm_red_workspace_bytes(rows, F1, F2))
     key = str(A.device)
@@ -602,9 +604,10 @@ def gemm_red(A, B, a_kmajor=False):
         _red_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
     ws = _red_ws[key]
     C = torch.empty(F1, F2, dtype=torch.float32, device=A.device)
-    call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(ws),
+    cs = torch.empty(F1, dtype=torch.float32, device=A.device) if colsum else None
+    call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(cs), ptr(ws),
          ws.numel(), stream(), nbytes=rows * (F1 + F2) * 4)
-    return C
+    return (C, cs) if colsum else C
 
 
 class LinearTC(torch.autograd.Function):
@@ -626,9 +629,12 @@ class LinearTC(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = _linear_tc(gy, weight.t().contiguous(), None)      # dY [rows, F] x W [F, K]
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = gemm_red(gy, x)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dw = gemm_red(gy, x, colsum=want_db)
+            if want_db:
+                dw, db = dw
+        elif want_db:
             db = gy.sum(0)
         return dx, dw, db
 

@@ -518,9 +518,11 @@ def test_gemm_red_vs_fp64(dev, rows, F1, F2, kmajor):
     outs = []
     for _ in range(2):
         C = torch.full((F1, F2 + 3), 7.0, device=dev)          # ldc > F2: the padding columns must stay untouched
+        cs = torch.full((F1,), 7.0, device=dev)
         call("mrg_gemm_red", ptr(Ain), Ain.shape[1], 1 if kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2 + 3,
-             ptr(ws), ws.numel(), stream())
+             ptr(cs), ptr(ws), ws.numel(), stream())
         outs.append(C)
+        sums = cs
     torch.cuda.synchronize()
     assert bool((outs[0] == outs[1]).all())
     assert bool((outs[0][:, F2:] == 7.0).all())
@@ -531,6 +533,8 @@ def test_gemm_red_vs_fp64(dev, rows, F1, F2, kmajor):
     e_lib = float((lib32.double() - ref).abs().max()) / scale
     print(f"gemm_red rows={rows} F1={F1} F2={F2} kmajor={kmajor}: err vs fp64 {e_tc:.2e} (library fp32 GEMM {e_lib:.2e})")
     assert e_tc <= max(1e-5, 4 * e_lib)
+    cref = A.double().sum(0)         # the virtual ones column: column sums of A (bias gradient)
+    assert float((sums.double() - cref).abs().max()) <= 1e-5 * max(float(cref.abs().max()), float(A.abs().sum(0).max()) * 1e-2)
 
 
 def test_gemm_red_zero_rows(dev):
@@ -539,7 +543,7 @@ def test_gemm_red_zero_rows(dev):
     A = torch.zeros(1, 8, device=dev)
     B = torch.zeros(1, 16, device=dev)
     ws = torch.empty(16, dtype=torch.uint8, device=dev)
-    call("mrg_gemm_red", ptr(A), 8, 0, ptr(B), 16, 0, 8, 16, ptr(C), 16, ptr(ws), ws.numel(), stream())
+    call("mrg_gemm_red", ptr(A), 8, 0, ptr(B), 16, 0, 8, 16, ptr(C), 16, None, ptr(ws), ws.numel(), stream())
     torch.cuda.synchronize()
     assert bool((C == 0).all())
 
