@@ -245,6 +245,27 @@ int mrg_mixed_bwd_scale(float* coef, float* dgamma, float* dbeta, const float* a
                         void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K9b  MixedOp over the PRE candidate list with ONE shared read of its inputs (cell_lp.py:25-33 over
+ * PRE_OPS = pre_mult / pre_sub / pre_add, operations_lp.py:71-98):
+ *   out = sum_k w_k relu(BN_k(comp_k(a, b))),  comps[k] in MRG_COMP_{SUB, MULT, ADD}, K <= 3.
+ * No candidate output is ever written: statistics of all K compositions in one pass over (a, b), then (after one
+ * mrg_bn_finalize per candidate: scale / shift [K, D]) the mixed sum in a second pass; the backward mirrors it
+ * (column sums of all K BatchNorm backwards in one pass over (dout, a, b); after mrg_bn_bwd_finalize +
+ * mrg_mixed_bwd_scale per candidate: coef [K, 3, D]; then da, db in one pass).  stats / bwd_stats:
+ * [K][mrg_stats_nparts(rows)][2][D] doubles.  da or db may be NULL.
+ * ---------------------------------------------------------------------------------- */
+int mrg_mixed_pre_stats(const float* a, const float* b, int64_t rows, int32_t D, const int32_t* comps, int32_t K,
+                        double* stats, void* stream);
+int mrg_mixed_pre_fwd(const float* a, const float* b, int64_t rows, int32_t D, const int32_t* comps, int32_t K,
+                      const float* scale, const float* shift, const float* w, float* out, void* stream);
+int mrg_mixed_pre_bwd_stats(const float* dout, const float* a, const float* b, int64_t rows, int32_t D,
+                            const int32_t* comps, int32_t K, const float* scale, const float* shift, double* bwd_stats,
+                            void* stream);
+int mrg_mixed_pre_bwd(const float* dout, const float* a, const float* b, int64_t rows, int32_t D, const int32_t* comps,
+                      int32_t K, const float* scale, const float* shift, const float* coef, float* da, float* db,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K5/K11  segmented reduction of gathered rows.  One kernel family serves
  *   (i)  DGL update_all(copy_e, max|sum|mean) over the dst-CSR (operations_lp.py:233,248,
  *        262; compgcn.py:87) and the NC UDF reducers incl. std (operations.py:105-190);

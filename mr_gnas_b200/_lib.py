@@ -90,6 +90,10 @@ _SIGNATURES = {
     "mrg_linear_tc_supported": (I32, [I32]),
     "mrg_linear_tc_workspace_bytes": (SZ, [I32]),
     "mrg_linear_tc_fwd": (I32, [P, P, P, I64, I32, I32, P, I64, P, SZ, P]),
+    "mrg_mixed_pre_stats": (I32, [P, P, I64, I32, P, I32, P, P]),
+    "mrg_mixed_pre_fwd": (I32, [P, P, I64, I32, P, I32, P, P, P, P, P]),
+    "mrg_mixed_pre_bwd_stats": (I32, [P, P, P, I64, I32, P, I32, P, P, P, P]),
+    "mrg_mixed_pre_bwd": (I32, [P, P, P, I64, I32, P, I32, P, P, P, P, P, P]),
     "mrg_gemm_red_workspace_bytes": (SZ, [I64, I32, I32]),
     "mrg_gemm_red": (I32, [P, I64, I32, P, I64, I64, I32, I32, P, I64, P, P, SZ, P]),
     "mrg_transe_fwd": (I32, [P, P, I64, I64, I32, F32, P, P]),

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmrgnas.so")
-SOURCES = ["rowops.cu", "segreduce.cu", "graph.cu", "gemm_tc.cu", "amax_bwd.cu", "gate_pipe.cu", "score.cu"]
+SOURCES = ["rowops.cu", "segreduce.cu", "graph.cu", "gemm_tc.cu", "amax_bwd.cu", "gate_pipe.cu", "score.cu", "mixed_pre.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 if os.environ.get("MRG_TC_PROF"):       # MMA-warp wait counters in the tcgen05 kernel (scripts/prof_amax_tc.py)

@@ -1,6 +1,8 @@
 """torch.autograd glue over the libmrgnas C ABI: one Function per kernel family.  torch is
 used for device memory, streams and the tape only; all arithmetic on [rows, D] feature
 matrices happens in the hand-written CUDA kernels (no eager / CPU fallback)."""
+import ctypes
+
 import torch
 
 from . import _lib
@@ -835,6 +837,94 @@ class MixedSum(torch.autograd.Function):
             call("mrg_bn_bwd_apply", ptr(dout), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
             grads += [dy, dgamma, dbeta]
         return (dw, None, None, None, None, None, *grads)
+
+
+class MixedPre(torch.autograd.Function):
+    """MixedOp over composition candidates (PRE_OPS) with one shared read of (a, b): cell_lp.py:25-33 applied to
+    pre_mult / pre_sub / pre_add (operations_lp.py:71-98).  No candidate output is materialised (mixed_pre.cu):
+    statistics pass -> K BatchNorm finalizes -> mixed-sum pass; the backward mirrors it."""
+
+    @staticmethod
+    def forward(ctx, w, training, eps, momentum, bns, comps, a, b, *gamma_beta):
+        a, b, w = _f32c(a), _f32c(b), _f32c(w)
+        rows, D = a.shape
+        dev = a.device
+        K_ = len(comps)
+        gammas, betas = gamma_beta[0::2], gamma_beta[1::2]
+        comps_t = torch.tensor(list(comps), dtype=torch.int32)      # host array read at enqueue time
+        ctx.comps_t = comps_t
+        cp = ctypes.c_void_p(comps_t.data_ptr())
+        scale = torch.empty(K_, D, dtype=torch.float32, device=dev)
+        shift = torch.empty_like(scale)
+        mean = torch.empty_like(scale)
+        invstd = torch.empty_like(scale)
+        if training:
+            nparts = stats_nparts(rows)
+            st = torch.empty(K_, nparts, 2, D, dtype=torch.float64, device=dev)
+            call("mrg_mixed_pre_stats", ptr(a), ptr(b), rows, D, cp, K_, ptr(st), stream(), nbytes=2 * rows * D * 4)
+            for k in range(K_):
+                rm, rv = bns[k]
+                call("mrg_bn_finalize", ptr(st[k]), nparts, rows, D, ptr(gammas[k]), ptr(betas[k]), float(eps),
+                     float(momentum), ptr(rm), ptr(rv), ptr(mean[k]), ptr(invstd[k]), ptr(scale[k]), ptr(shift[k]), stream())
+        else:
+            for k in range(K_):
+                rm, rv = bns[k]
+                invstd[k] = torch.rsqrt(rv + eps)
+                mean[k] = rm
+                scale[k] = gammas[k] * invstd[k]
+                shift[k] = betas[k] - scale[k] * rm
+        out = torch.empty_like(a)
+        call("mrg_mixed_pre_fwd", ptr(a), ptr(b), rows, D, cp, K_, ptr(scale), ptr(shift), ptr(w), ptr(out), stream(),
+             nbytes=3 * rows * D * 4)
+        ctx.K_, ctx.training = K_, training
+        ctx.save_for_backward(a, b, w, scale, shift, mean, invstd, *gammas)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, b, w, scale, shift, mean, invstd, *gammas = ctx.saved_tensors
+        K_ = ctx.K_
+        dout = _f32c(dout)
+        rows, D = dout.shape
+        dev = dout.device
+        cp = ctypes.c_void_p(ctx.comps_t.data_ptr())
+        nparts = stats_nparts(rows)
+        bst = torch.empty(K_, nparts, 2, D, dtype=torch.float64, device=dev)
+        call("mrg_mixed_pre_bwd_stats", ptr(dout), ptr(a), ptr(b), rows, D, cp, K_, ptr(scale), ptr(shift), ptr(bst),
+             stream(), nbytes=3 * rows * D * 4)
+        coef = torch.empty(K_, 3 * D, dtype=torch.float32, device=dev)
+        dw = torch.empty(K_, dtype=torch.float32, device=dev)
+        grads = []
+        for k in range(K_):
+            dgamma = torch.empty(D, dtype=torch.float32, device=dev)
+            dbeta = torch.empty_like(dgamma)
+            call("mrg_bn_bwd_finalize", ptr(bst[k]), nparts, rows, D, ptr(gammas[k]), ptr(mean[k]), ptr(invstd[k]),
+                 ptr(dgamma), ptr(dbeta), ptr(coef[k]), stream())
+            call("mrg_mixed_bwd_scale", ptr(coef[k]), ptr(dgamma), ptr(dbeta), ptr(scale[k]), ptr(shift[k]), ptr(mean[k]),
+                 ptr(invstd[k]), ptr(w), k, ptr(dw), D, 1 if ctx.training else 0, stream())
+            grads += [dgamma, dbeta]
+        need_a, need_b = ctx.needs_input_grad[6], ctx.needs_input_grad[7]
+        da = torch.empty_like(a) if need_a else None
+        db = torch.empty_like(b) if need_b else None
+        if need_a or need_b:
+            call("mrg_mixed_pre_bwd", ptr(dout), ptr(a), ptr(b), rows, D, cp, K_, ptr(scale), ptr(shift), ptr(coef), ptr(da),
+                 ptr(db), stream(), nbytes=5 * rows * D * 4)
+        return (dw, None, None, None, None, None, da, db, *grads)
+
+
+MIXED_PRE_FUSED = True      # False: per-candidate outputs + mixed_sum (the round-1 form)
+
+
+def mixed_pre(weights, a, b, comps, bn_modules):
+    """sum_k weights[k] * ReLU(bn_k(comp_k(a, b))) without materialising the candidates (MixedPre)."""
+    training = bn_modules[0].training
+    bns, flat = [], []
+    for bn in bn_modules:
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        bns.append((bn.running_mean, bn.running_var))
+        flat += [bn.weight, bn.bias]
+    return MixedPre.apply(weights, training, bn_modules[0].eps, bn_momentum(bn_modules[0]), bns, tuple(comps), a, b, *flat)
 
 
 def mixed_sum(weights, ys, bn_modules):

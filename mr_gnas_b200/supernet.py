@@ -11,6 +11,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as K
+from .operations_lp import _pre_op
+
+_pre_forward = _pre_op.forward
 
 
 class MixedOp(nn.Module):
@@ -29,6 +32,11 @@ class MixedOp(nn.Module):
         self._ops = nn.ModuleList(stacks)
 
     def forward(self, weights, g, h, h_in):
+        comps = [getattr(stack[0], 'comp', None) for stack in self._ops]
+        if K.MIXED_PRE_FUSED and not self._with_linear and h.is_cuda and len(comps) <= 3 and h.shape == h_in.shape \
+                and all(c is not None and type(stack[0]).forward is _pre_forward for c, stack in zip(comps, self._ops)):
+            # every candidate is an elementwise composition of the SAME two rows: one shared read, no candidate outputs
+            return K.mixed_pre(weights, h, h_in, comps, [stack[-2] for stack in self._ops])
         ys, bns = [], []
         for stack in self._ops:
             y = stack[0](g, h, h_in)

@@ -65,6 +65,65 @@ def test_mixed_op_golden(golden_dir, tag):
             assert int(v) == int(c["state"][k]) + 1
 
 
+@pytest.mark.parametrize("names", [["pre_mult", "pre_sub", "pre_add"], ["pre_sub", "pre_mult"], ["pre_add"]])
+@pytest.mark.parametrize("train", [True, False])
+def test_mixed_pre_fused_equals_per_candidate_form(names, train):
+    """a-11: the PRE-list MixedOp with ONE shared read of its inputs (mrg_mixed_pre_*: no candidate output is ever
+    written) against the per-candidate form (K compositions + K BatchNorms + mixed sum) on the same module:
+    output, both input gradients, dalpha, every BatchNorm gradient and the running statistics, at D = 200 with a
+    ragged row count; and against an fp64 evaluation of the reference formula (cell_lp.py:25-33)."""
+    from mr_gnas_b200 import functional as K
+    from mr_gnas_b200.cell_lp import MixedOp
+    torch.manual_seed(3)
+    rows, D = 5003, 200
+    x0, r0 = torch.randn(rows, D, device=DEV), torch.randn(rows, D, device=DEV)
+    cot = torch.randn(rows, D, device=DEV)
+    alpha0 = torch.randn(len(names), device=DEV)
+    res = {}
+    base = MixedOp(D, 0.0, names).to(DEV)
+    for stack in base._ops:
+        stack[-2].weight.data.uniform_(0.5, 1.5)
+        stack[-2].bias.data.normal_(0, 0.3)
+        stack[-2].running_mean.normal_(0, 0.5)
+        stack[-2].running_var.uniform_(0.5, 2.0)
+    state = {k: v.clone() for k, v in base.state_dict().items()}
+    for fused in (True, False):
+        K.MIXED_PRE_FUSED = fused
+        mo = MixedOp(D, 0.0, names).to(DEV)
+        mo.load_state_dict(state)
+        mo.train(train)
+        x, r, alpha = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True), alpha0.clone().requires_grad_(True)
+        out = mo(torch.softmax(alpha, 0), None, x, r)
+        out.backward(cot)
+        res[fused] = dict(out=out.detach(), dx=x.grad, dr=r.grad, dalpha=alpha.grad,
+                          **{"d" + k: p.grad for k, p in mo.named_parameters()},
+                          **{k: v.clone() for k, v in mo.state_dict().items() if "running" in k or "tracked" in k})
+    K.MIXED_PRE_FUSED = True
+    for k in res[True]:
+        a, b = res[True][k], res[False][k]
+        if a.dtype.is_floating_point:
+            _check(k, a, b)
+        else:
+            assert torch.equal(a, b), k
+    # fp64 statement of the reference formula
+    x, r, alpha = x0.double().requires_grad_(True), r0.double().requires_grad_(True), alpha0.double().requires_grad_(True)
+    w = torch.softmax(alpha, 0)
+    tot = 0
+    for k, name in enumerate(names):
+        v = {"pre_mult": x * r, "pre_sub": x - r, "pre_add": x + r}[name]
+        gam, bet = state[f"_ops.{k}.1.weight"].double(), state[f"_ops.{k}.1.bias"].double()
+        if train:
+            mu, var = v.mean(0), v.var(0, unbiased=False)
+        else:
+            mu, var = state[f"_ops.{k}.1.running_mean"].double(), state[f"_ops.{k}.1.running_var"].double()
+        tot = tot + w[k] * torch.relu((v - mu) / torch.sqrt(var + 1e-5) * gam + bet)
+    tot.backward(cot.double())
+    _check("out vs fp64", res[True]["out"], tot.detach().float())
+    _check("dx vs fp64", res[True]["dx"], x.grad.float())
+    _check("dr vs fp64", res[True]["dr"], r.grad.float())
+    _check("dalpha vs fp64", res[True]["dalpha"], alpha.grad.float())
+
+
 # ------------------------------------------------------------------------------ LP supernet
 def test_search_lp_golden(golden_dir):
     from mr_gnas_b200.graph import MRGraph
