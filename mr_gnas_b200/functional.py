@@ -2,6 +2,7 @@
 used for device memory, streams and the tape only; all arithmetic on [rows, D] feature
 matrices happens in the hand-written CUDA kernels (no eager / CPU fallback)."""
 import ctypes
+import os
 
 import torch
 
@@ -587,6 +588,7 @@ def _linear_tc(x, W, bias, out_cols=None):
 
 _red_ws = {}
 USE_TC_GEMM_RED = True      # False: torch.mm (library GEMM) for the reductions over the rows
+USE_TC_MATMUL = os.environ.get("MRG_MATMUL_TC", "1") != "0"     # small dense table products (K.matmul) on mrg_gemm_red
 
 
 def gemm_red(A, B, a_kmajor=False, colsum=False):
@@ -596,7 +598,7 @@ def gemm_red(A, B, a_kmajor=False, colsum=False):
     A, B = _f32c(A), _f32c(B)
     rows, F2 = B.shape
     F1 = A.shape[0] if a_kmajor else A.shape[1]
-    if not (USE_TC_GEMM_RED and A.is_cuda and rows >= 256):
+    if not (USE_TC_GEMM_RED and A.is_cuda and rows >= 64):
         C = torch.mm(A if a_kmajor else A.t(), B)
         return (C, A.sum(1 if a_kmajor else 0)) if colsum else C
     lib = _lib.load()
@@ -610,6 +612,33 @@ def gemm_red(A, B, a_kmajor=False, colsum=False):
     call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(cs), ptr(ws),
          ws.numel(), stream(), nbytes=rows * (F1 + F2) * 4)
     return (C, cs) if colsum else C
+
+
+class MatmulTC(torch.autograd.Function):
+    """X @ Y for small dense tables on mrg_gemm_red (X [m, k] is its own K-major operand, Y [k, n] the row-major one):
+    `rel_wt @ embedding_e.weight` and `rel_embed @ w_rel` (model_lp.py:125,133), whose inner dimension (2R+1 = 475) rules
+    out the K % 8 == 0 Linear kernel.  Backward: dX = dC Y^T and dY = X^T dC on the same entry point."""
+
+    @staticmethod
+    def forward(ctx, X, Y):
+        X, Y = _f32c(X), _f32c(Y)
+        ctx.save_for_backward(X, Y)
+        return gemm_red(X, Y, a_kmajor=True)
+
+    @staticmethod
+    def backward(ctx, dC):
+        X, Y = ctx.saved_tensors
+        dC = _f32c(dC)
+        dX = gemm_red(dC, Y.t().contiguous(), a_kmajor=True) if ctx.needs_input_grad[0] else None
+        dY = gemm_red(X, dC) if ctx.needs_input_grad[1] else None
+        return dX, dY
+
+
+def matmul(X, Y):
+    """X @ Y (2-D, fp32) on the tensor cores when both are CUDA tensors, else torch.mm."""
+    if USE_TC_GEMM_RED and USE_TC_MATMUL and X.is_cuda and X.dim() == 2 and Y.dim() == 2:
+        return MatmulTC.apply(X, Y)
+    return torch.mm(X, Y)
 
 
 class LinearTC(torch.autograd.Function):

@@ -164,11 +164,11 @@ class Network(nn.Module):
             return D_.AllGatherRows.apply(ent_local, g.part), rel_embed
         g.require_tables(self._num_ent, self._num_rel)
         all_ent_emb = K.linear(self.linear_e, self.embedding_h.weight)  # == embedding_h(arange(N))
-        rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
+        rel_embed = K.matmul(self.rel_wt, self.embedding_e.weight)
         for cell in self.cells:
             all_ent_emb = cell.forward_fused(g, all_ent_emb, rel_embed)
             all_ent_emb = F.dropout(all_ent_emb, self._dropout, training=self.training)
-            rel_embed = torch.matmul(rel_embed, self.w_rel)
+            rel_embed = K.matmul(rel_embed, self.w_rel)
         return all_ent_emb, rel_embed
 
     def _embed_partitioned(self, g):
@@ -179,14 +179,14 @@ class Network(nn.Module):
         part = g.part
         g.require_tables(self._num_ent, self._num_rel)
         table = K.linear(self.linear_e, self.embedding_h.weight)
-        rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
+        rel_embed = K.matmul(self.rel_wt, self.embedding_e.weight)
         with D_.use(part):
             for k, cell in enumerate(self.cells):
                 if k > 0:
                     table = D_.AllGatherRows.apply(local, part)
                 local = cell.forward_fused(g, table, rel_embed)
                 local = F.dropout(local, self._dropout, training=self.training)
-                rel_embed = torch.matmul(rel_embed, self.w_rel)
+                rel_embed = K.matmul(rel_embed, self.w_rel)
         return local, rel_embed
 
     def _forward_lp(self, g, subj, rel):

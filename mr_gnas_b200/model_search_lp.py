@@ -89,7 +89,7 @@ class Network(nn.Module):
         """reference: model_search_lp.py:131-163."""
         dev = self.embedding_h.weight.device
         all_ent_emb = self.linear_e(self.embedding_h.weight)
-        rel_embed = torch.mm(self.rel_wt, self.embedding_e.weight)
+        rel_embed = K.matmul(self.rel_wt, self.embedding_e.weight)
         nodes = g_train.nodes().to(dev)
         src_in_final = torch.cat((src_in, nodes), dim=0)
         src_id_final = node_id[src_in_final].reshape(-1)
@@ -103,7 +103,7 @@ class Network(nn.Module):
             relu = not (i == 0 and len(self.cells) != 1)  # layer 0 of a deeper net is not activated (:146-148)
             ent_emb = K.bn_act(ent_emb, self.batchnorm_h, relu=relu)
             ent_emb = F.dropout(ent_emb, self._dropout, training=self.training)
-            rel_embed = torch.matmul(rel_embed, self.w_rel)
+            rel_embed = K.matmul(rel_embed, self.w_rel)
         return ent_emb, rel_embed
 
     def forward(self, g_train, node_id, src_in, edge_type):

@@ -537,6 +537,25 @@ def test_gemm_red_vs_fp64(dev, rows, F1, F2, kmajor):
     assert float((sums.double() - cref).abs().max()) <= 1e-5 * max(float(cref.abs().max()), float(A.abs().sum(0).max()) * 1e-2)
 
 
+def test_matmul_tc_vs_fp64(dev):
+    """K.matmul (rel_wt @ embedding_e.weight and rel_embed @ w_rel, model_lp.py:125,133) forward and both gradients
+    on mrg_gemm_red against fp64."""
+    from mr_gnas_b200 import functional as K_
+    torch.manual_seed(9)
+    for m, k, n in ((475, 475, 200), (475, 200, 200), (23, 23, 64)):
+        X = torch.randn(m, k, device=dev, requires_grad=True)
+        Y = torch.randn(k, n, device=dev, requires_grad=True)
+        cot = torch.randn(m, n, device=dev)
+        C = K_.matmul(X, Y)
+        C.backward(cot)
+        X64, Y64 = X.detach().double().requires_grad_(True), Y.detach().double().requires_grad_(True)
+        C64 = X64 @ Y64
+        C64.backward(cot.double())
+        _check("C", C, C64.float())
+        _check("dX", X.grad, X64.grad.float())
+        _check("dY", Y.grad, Y64.grad.float())
+
+
 def test_gemm_red_zero_rows(dev):
     from mr_gnas_b200._lib import call, ptr, stream
     C = torch.full((8, 16), 3.0, device=dev)
