@@ -1391,24 +1391,30 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
 
   if (warp < RWARPS) {
     // ================================ PRODUCERS (transpose into K-major tiles) ================================
-    for (int ci = 0; ci < nch; ++ci) {
-      const int s = ci % RSTAGES;
+    // The loads of chunk ci + 1 are issued before chunk ci is scattered (two register sets, loop unrolled by two): the
+    // first version loaded, waited and stored per chunk and ran at 5,600 cycles per chunk against 2,040 of MMA work.
+    struct Regs {
+      float a0[8], a1[8], b[8];
+      float ka[RM / RWARPS];
+    };
+    auto load = [&](Regs& r, int ci) {
       const int64_t n = (int64_t)(c_begin + ci) * RK + lane;     // reduction row of this lane
       const bool nvalid = n < p.rows;
-      float va0[8], va1[8], vb[8];
-      float ka[RM / RWARPS];
       if (p.a_kmajor) {          // At[F1][rows]: a warp copies 16 tile rows, lane = reduction index (coalesced)
 #pragma unroll
         for (int i = 0; i < RM / RWARPS; ++i) {
           const int f = m0 + warp * (RM / RWARPS) + i;
-          ka[i] = (nvalid && f < p.F1) ? __ldg(p.A + (size_t)f * p.lda + n) : 0.f;
+          r.ka[i] = (nvalid && f < p.F1) ? __ldg(p.A + (size_t)f * p.lda + n) : 0.f;
         }
       } else {
         const float* arow = p.A + (size_t)(nvalid ? n : 0) * p.lda;
-        red_load8(arow, m0 + 8 * warp, p.F1, nvalid, p.a_vec != 0, va0);
-        red_load8(arow, m0 + 8 * (warp + RWARPS), p.F1, nvalid, p.a_vec != 0, va1);
+        red_load8(arow, m0 + 8 * warp, p.F1, nvalid, p.a_vec != 0, r.a0);
+        red_load8(arow, m0 + 8 * (warp + RWARPS), p.F1, nvalid, p.a_vec != 0, r.a1);
       }
-      red_load8(p.B + (size_t)(nvalid ? n : 0) * p.ldb, k0 + 8 * warp, p.F2, nvalid, p.b_vec != 0, vb, p.ones_col ? p.F2 : -1);
+      red_load8(p.B + (size_t)(nvalid ? n : 0) * p.ldb, k0 + 8 * warp, p.F2, nvalid, p.b_vec != 0, r.b, p.ones_col ? p.F2 : -1);
+    };
+    auto store = [&](const Regs& r, int ci) {
+      const int s = ci % RSTAGES;
       mbar_wait(&empty_bar[s], ((ci / RSTAGES) & 1) ^ 1);
       uint8_t* st = smem + (size_t)s * RSTAGE;
       if (p.a_kmajor) {
@@ -1417,18 +1423,28 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
           const int R = warp * (RM / RWARPS) + i;
           uint8_t* a = st + (uint32_t)(R >> 7) * TILE_BYTES + (uint32_t)((R & 127) >> 3) * 1024 + (uint32_t)(R & 7) * 128 +
                        ((((uint32_t)lane >> 2) ^ (uint32_t)(R & 7)) << 4) + (uint32_t)(lane & 3) * 4;
-          const float h = tf32_rna(ka[i]);
+          const float h = tf32_rna(r.ka[i]);
           *reinterpret_cast<float*>(a) = h;
-          *reinterpret_cast<float*>(a + RA_TILE) = ka[i] - h;
+          *reinterpret_cast<float*>(a + RA_TILE) = r.ka[i] - h;
         }
       } else {
-        red_scatter8(st, RA_TILE, 8 * warp, lane, va0);
-        red_scatter8(st, RA_TILE, 8 * (warp + RWARPS), lane, va1);
+        red_scatter8(st, RA_TILE, 8 * warp, lane, r.a0);
+        red_scatter8(st, RA_TILE, 8 * (warp + RWARPS), lane, r.a1);
       }
-      red_scatter8(st + 2 * RA_TILE, RB_TILE, 8 * warp, lane, vb);
+      red_scatter8(st + 2 * RA_TILE, RB_TILE, 8 * warp, lane, r.b);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+    };
+    Regs r0, r1;
+    load(r0, 0);
+    for (int ci = 0; ci < nch; ci += 2) {
+      if (ci + 1 < nch) load(r1, ci + 1);
+      store(r0, ci);
+      if (ci + 1 < nch) {
+        if (ci + 2 < nch) load(r0, ci + 2);
+        store(r1, ci + 1);
+      }
     }
     // ================================ EPILOGUE (same warps): TMEM -> transposed partial ================================
     mbar_wait(tfull_bar, 0);
@@ -1487,7 +1503,13 @@ __global__ void __launch_bounds__(256) gemm_red_fold_kernel(const float* __restr
     const int f = blockIdx.x * 32 + threadIdx.x;
     if (f < F1) {
       float acc = 0.f;
-      for (int s = 0; s < slices; ++s) acc += part[((int64_t)s * N2 + F2) * M2 + f];
+      for (int s0 = 0; s0 < slices; s0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = s0 + u < slices ? __ldg(part + ((int64_t)(s0 + u) * N2 + F2) * M2 + f) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
       colsum[f] = acc;
     }
   }
@@ -1498,8 +1520,16 @@ __global__ void __launch_bounds__(256) gemm_red_fold_kernel(const float* __restr
   for (int i = 0; i < 4; ++i) {
     const int kk = ty + 8 * i;
     float acc = 0.f;
-    if (kt + kk < F2 && ft + tx < F1)
-      for (int s = 0; s < slices; ++s) acc += part[((int64_t)s * N2 + kt + kk) * M2 + ft + tx];
+    if (kt + kk < F2 && ft + tx < F1) {
+      const float* src = part + ((int64_t)kt + kk) * M2 + ft + tx;
+      for (int s0 = 0; s0 < slices; s0 += 8) {      // 8 independent loads in flight, added in the fixed slice order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = s0 + u < slices ? __ldg(src + (int64_t)(s0 + u) * N2 * M2) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+    }
     tile[kk][tx] = acc;
   }
   __syncthreads();
