@@ -215,7 +215,7 @@ def algo_bytes(key, M, E, N, D):
 # C-ABI call -> the kernels it launches that move HBM data (ncu names, template arguments dropped)
 CALL_KERNELS = {
     "mrg_amax_bwd": ["amax_bwd_dw_kernel", "amax_bwd_dx_kernel", "amax_route_kernel"],
-    "mrg_amax_tc_fwd": ["tc::amax_tc_kernel"],
+    "mrg_amax_tc_fwd": ["tc::amax_tc2_kernel", "tc::amax_tc_kernel"],
     "mrg_sparse_gate_bwd_fused": ["gate_bwd_pipe_kernel"],
     "mrg_sparse_gate_fwd": ["sparse_gate_fwd_kernel"],
     "mrg_bn_bwd_apply": ["bn_bwd_apply_kernel"],
@@ -239,6 +239,8 @@ def ncu_traffic(call_key):
         if hits:
             total += max(hits)      # the full-size launch (small node-level launches share the kernel name)
             found = True
+            if call_key.startswith("mrg_amax_tc_fwd"):
+                break               # one main kernel per call: the CTA pair when captured, else the single-CTA kernel
     return (total if found else None), src
 
 

