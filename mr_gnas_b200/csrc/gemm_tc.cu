@@ -1094,64 +1094,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
       if (lane == 0) mbar_arrive_cluster(&xfull_bar[s], 0);   // one arrival per warp, on the leader's barrier
       if (++c_c == nch) { c_c = 0; ++c_i; }
     };
-    if (!BF && p.l2_prefetch >= 2) {
-      // ---- asynchronous landing (3xTF32 only: the raw fp32 piece fits the X-hi tile): the 128-byte row pieces of an
-      // item are copied with cp.async straight into their swizzled units of the (free) X stage two items ahead, and
-      // converted IN PLACE once their commit group has landed -- every thread reads back exactly the units it copied, so
-      // no barrier is needed, and cp.async.wait_group waits for the OLDEST group only (loads through registers share
-      // scoreboards: waiting for one item also waits for the younger ones, which is why a deeper register ring bought nothing).
-      int a_i = 0, a_c = 0;
-      const float* arow = nullptr;
-      auto issue = [&](int q) {
-        if (a_c == 0) {
-          arow = e_nxt >= 0 ? p.x.data + (size_t)e_nxt * D : nullptr;
-          e_nxt = eid_of(a_i + 1);
-        } else if (a_c == 1 && e_nxt >= 0) {
-          const char* nrow = reinterpret_cast<const char*>(p.x.data + (size_t)e_nxt * D);
-#pragma unroll
-          for (int l = 0; l < 2; ++l)
-            if (2 * half + l < pf_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (2 * half + l) * 128));
-        }
-        const int s = q % XS2;
-        mbar_wait(&xempty_bar[s], ((q / XS2) & 1) ^ 1);
-        const uint32_t xhi = smem_u32(smem_x + (size_t)s * STAGE2);
-        const int c0 = a_c * KC;
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-          const bool ok = arow && c0 + ucol[j] < D;
-          const float* src = ok ? arow + c0 + ucol[j] : p.x.data;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xhi + uoff[j]), "l"(src), "r"(ok ? 16 : 0) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (++a_c == nch) { a_c = 0; ++a_i; }
-      };
-      auto convert = [&](int q) {
-        if (c_c == 0) cvalid = tile_pos0(c_i) + 128 * (int)rank + r < p.E;
-        if (q + 1 < total) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const int c0 = c_c * KC;
-        const int s = q % XS2;
-        uint8_t* xhi = smem_x + (size_t)s * STAGE2;
-        uint8_t* xlo = xhi + TILE_BYTES;
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-          const float4 v = activate(*reinterpret_cast<const float4*>(xhi + uoff[j]), c0 + ucol[j]);
-          const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-          const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-          *reinterpret_cast<float4*>(xhi + uoff[j]) = hi;
-          *reinterpret_cast<float4*>(xlo + uoff[j]) = lo;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&xfull_bar[s], 0);
-        if (++c_c == nch) { c_c = 0; ++c_i; }
-      };
-      if (total > 0) issue(0);
-      for (int q = 0; q < total; ++q) {
-        if (q + 1 < total) issue(q + 1);      // two groups in flight while item q is converted
-        convert(q);
-      }
-    } else {
 #pragma unroll
     for (int u = 0; u < PD2; ++u) {
       if (lq < total) load(buf[u]);
@@ -1166,7 +1108,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) amax_tc2
           ++lq;
         }
       }
-    }
     }
   } else if (warp == WLD_WARP) {
     // ================================ W LOADER (own feature half: hi tile, lo tile) ================================
