@@ -410,11 +410,14 @@ int mrg_linear_tc_fwd(const float* x, const float* W, const float* bias, int64_t
  * GEMMs of sf_DisMult_op's `torch.mm(obj_emb, all_ent.transpose(1, 0))` (operations_lp.py:115-127): dq = dl . ent
  * (a_kmajor, A = dl [B, N]) and dent = dl^T . q.  Split over the rows into per-CTA partials folded in a fixed order
  * (deterministic).  Any F1, F2 >= 1; rows >= 0 (rows == 0 zeroes C).  colsum (may be NULL): [F1] = sum_n A[n, f1], the
- * bias gradient `dY.sum(0)` of the same Linear, computed as one extra (virtual, all-ones) column of B.
+ * bias gradient `dY.sum(0)` of the same Linear, computed as one extra (virtual, all-ones) column of B.  bias (may be
+ * NULL): [F2], added to every row of C -- with a_kmajor this is nn.Linear's forward x W^T + b (A = x [rows_out, K] as the
+ * K-major operand, B = W^T) and, with B = W, its input gradient dY W.
  * ---------------------------------------------------------------------------------- */
 size_t mrg_gemm_red_workspace_bytes(int64_t rows, int32_t F1, int32_t F2);
 int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int64_t rows, int32_t F1,
-                 int32_t F2, float* C, int64_t ldc, float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+                 int32_t F2, float* C, int64_t ldc, float* colsum, const float* bias, void* workspace, size_t workspace_bytes,
+                 void* stream);
 
 #ifdef __cplusplus
 }

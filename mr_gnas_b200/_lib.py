@@ -95,7 +95,7 @@ _SIGNATURES = {
     "mrg_mixed_pre_bwd_stats": (I32, [P, P, P, I64, I32, P, I32, P, P, P, P]),
     "mrg_mixed_pre_bwd": (I32, [P, P, P, I64, I32, P, I32, P, P, P, P, P, P]),
     "mrg_gemm_red_workspace_bytes": (SZ, [I64, I32, I32]),
-    "mrg_gemm_red": (I32, [P, I64, I32, P, I64, I64, I32, I32, P, I64, P, P, SZ, P]),
+    "mrg_gemm_red": (I32, [P, I64, I32, P, I64, I64, I32, I32, P, I64, P, P, P, SZ, P]),
     "mrg_transe_fwd": (I32, [P, P, I64, I64, I32, F32, P, P]),
     "mrg_transe_bwd_workspace_bytes": (SZ, [I64, I64, I32]),
     "mrg_transe_bwd": (I32, [P, P, P, I64, I64, I32, P, P, P, SZ, P]),

@@ -1330,6 +1330,11 @@ struct RedParams {
   int F1, F2, m_tiles, n_tiles, slices, cps, nchunks;
   int ones_col;         // 1: B gets a virtual column F2 of ones (column sums of A = the bias gradient) -> F2 + 1 columns
   float* part;          // [slices][n_tiles * RN][m_tiles * RM]
+  float* C;             // direct epilogue (slices == 1): C [F1, F2] (ldc) written by the main kernel, no fold pass
+  float* colsum;
+  const float* bias;    // [F2] added to every row of C (nn.Linear forward), or null
+  int64_t ldc;
+  int direct;
 };
 
 // `ones_at` >= 0: the virtual feature of that index reads as 1 for valid rows (bias-gradient column)
@@ -1452,13 +1457,40 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
     const int quad = warp & 3, h = (warp >> 2) & 1, chalf = warp >> 3;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + h * RN + chalf * 64;
     const int64_t M2 = (int64_t)p.m_tiles * RM, N2 = (int64_t)p.n_tiles * RN;
-    float* o = p.part + ((int64_t)sl * N2 + k0 + chalf * 64) * M2 + m0 + h * 128 + quad * 32 + lane;
+    if (p.direct) {
+      // one slice: no partials.  TMEM lane = C row, so the warp's 32 x 64 block is transposed through shared memory
+      // (the operand stages are free: every MMA has retired) and leaves as 256-byte row segments.
+      float* tb = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * 65;
 #pragma unroll 1
-    for (int cb = 0; cb < 64; cb += 32) {
-      uint32_t v[32];
-      tmem_ld32(taddr + cb, v);
+      for (int cb = 0; cb < 64; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + cb, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o[(int64_t)(cb + j) * M2] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) tb[lane * 65 + cb + j] = __uint_as_float(v[j]);
+      }
+      __syncwarp();
+      const int f0 = m0 + h * 128 + quad * 32, kc0 = k0 + chalf * 64;
+#pragma unroll 1
+      for (int rr = 0; rr < 32; ++rr) {
+        const int f = f0 + rr;
+        if (f >= p.F1) break;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int k = kc0 + lane + 32 * t;
+          const float val = tb[rr * 65 + lane + 32 * t];
+          if (k < p.F2) p.C[(int64_t)f * p.ldc + k] = p.bias ? val + __ldg(p.bias + k) : val;
+          else if (k == p.F2 && p.colsum) p.colsum[f] = val;
+        }
+      }
+    } else {
+      float* o = p.part + ((int64_t)sl * N2 + k0 + chalf * 64) * M2 + m0 + h * 128 + quad * 32 + lane;
+#pragma unroll 1
+      for (int cb = 0; cb < 64; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + cb, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[(int64_t)(cb + j) * M2] = __uint_as_float(v[j]);
+      }
     }
   } else {
     // ================================ MMA ISSUER ================================
@@ -1498,7 +1530,7 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
 // colsum (optional): column F2 of the partials = sum_n A[n, f] (the virtual ones column of B)
 __global__ void __launch_bounds__(256) gemm_red_fold_kernel(const float* __restrict__ part, int slices, int64_t N2, int64_t M2,
                                                             int F1, int F2, float* __restrict__ C, int64_t ldc,
-                                                            float* __restrict__ colsum) {
+                                                            float* __restrict__ colsum, const float* __restrict__ bias) {
   if (colsum && blockIdx.y == 0 && threadIdx.x < 32) {
     const int f = blockIdx.x * 32 + threadIdx.x;
     if (f < F1) {
@@ -1536,7 +1568,7 @@ __global__ void __launch_bounds__(256) gemm_red_fold_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int ff = ty + 8 * i;
-    if (ft + ff < F1 && kt + tx < F2) C[(int64_t)(ft + ff) * ldc + kt + tx] = tile[tx][ff];
+    if (ft + ff < F1 && kt + tx < F2) C[(int64_t)(ft + ff) * ldc + kt + tx] = tile[tx][ff] + (bias ? __ldg(bias + kt + tx) : 0.f);
   }
 }
 
@@ -1823,8 +1855,8 @@ extern "C" size_t mrg_gemm_red_workspace_bytes(int64_t rows, int32_t F1, int32_t
 }
 
 extern "C" int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const float* B, int64_t ldb, int64_t rows,
-                            int32_t F1, int32_t F2, float* C, int64_t ldc, float* colsum, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            int32_t F1, int32_t F2, float* C, int64_t ldc, float* colsum, const float* bias,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   MRG_CHECK_ARG(F1 > 0 && F2 > 0 && rows >= 0 && C, "gemm_red: bad shape");
   MRG_CHECK_ARG(ldc >= F2, "gemm_red: ldc < F2");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1856,13 +1888,20 @@ extern "C" int mrg_gemm_red(const float* A, int64_t lda, int32_t a_kmajor, const
   p.ones_col = colsum ? 1 : 0;
   gemm_red_plan(rows, F1, F2, &p.m_tiles, &p.n_tiles, &p.slices, &p.cps, &p.nchunks);
   p.part = (float*)workspace;
+  p.C = C;
+  p.colsum = colsum;
+  p.bias = bias;
+  p.ldc = ldc;
+  p.direct = p.slices == 1 ? 1 : 0;
   const size_t smem = (size_t)tc::RSTAGES * tc::RSTAGE + 1024 /*align*/ + 256 /*tail*/;
   cudaError_t e = cudaFuncSetAttribute(tc::gemm_red_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "gemm_red smem attr");
   tc::gemm_red_kernel<<<p.m_tiles * p.n_tiles * p.slices, tc::RTHREADS, smem, st>>>(p);
-  dim3 fg((F1 + 31) / 32, (F2 + 31) / 32);
-  tc::gemm_red_fold_kernel<<<fg, 256, 0, st>>>(p.part, p.slices, (int64_t)p.n_tiles * tc::RN, (int64_t)p.m_tiles * tc::RM, F1,
-                                               F2, C, ldc, colsum);
+  if (!p.direct) {
+    dim3 fg((F1 + 31) / 32, (F2 + 31) / 32);
+    tc::gemm_red_fold_kernel<<<fg, 256, 0, st>>>(p.part, p.slices, (int64_t)p.n_tiles * tc::RN, (int64_t)p.m_tiles * tc::RM,
+                                                 F1, F2, C, ldc, colsum, bias);
+  }
   MRG_LAUNCH_CHECK("gemm_red");
   return MRG_OK;
 }

@@ -588,10 +588,12 @@ def _linear_tc(x, W, bias, out_cols=None):
 
 _red_ws = {}
 USE_TC_GEMM_RED = True      # False: torch.mm (library GEMM) for the reductions over the rows
+LINEAR_FWD_ON_GEMM_RED = os.environ.get("MRG_LINEAR_FWD_RED", "1") != "0"
+LINEAR_DX_ON_GEMM_RED = os.environ.get("MRG_LINEAR_DX_RED", "1") != "0"
 USE_TC_MATMUL = os.environ.get("MRG_MATMUL_TC", "1") != "0"     # small dense table products (K.matmul) on mrg_gemm_red
 
 
-def gemm_red(A, B, a_kmajor=False, colsum=False):
+def gemm_red(A, B, a_kmajor=False, colsum=False, bias=None):
     """A^T B with the reduction over the rows on the tensor cores (mrg_gemm_red, 3xTF32): A [rows, F1], B [rows, F2]
     -> [F1, F2]; a_kmajor: A is passed as At [F1, rows].  Weight gradients and the DistMult backward GEMMs.
     colsum: also return A.sum(0) (the bias gradient), computed by the same launch."""
@@ -600,6 +602,8 @@ def gemm_red(A, B, a_kmajor=False, colsum=False):
     F1 = A.shape[0] if a_kmajor else A.shape[1]
     if not (USE_TC_GEMM_RED and A.is_cuda and rows >= 64):
         C = torch.mm(A if a_kmajor else A.t(), B)
+        if bias is not None:
+            C = C + bias
         return (C, A.sum(1 if a_kmajor else 0)) if colsum else C
     lib = _lib.load()
     nbytes = int(lib.mrg_gemm_red_workspace_bytes(rows, F1, F2))
@@ -609,8 +613,8 @@ def gemm_red(A, B, a_kmajor=False, colsum=False):
     ws = _red_ws[key]
     C = torch.empty(F1, F2, dtype=torch.float32, device=A.device)
     cs = torch.empty(F1, dtype=torch.float32, device=A.device) if colsum else None
-    call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(cs), ptr(ws),
-         ws.numel(), stream(), nbytes=rows * (F1 + F2) * 4)
+    call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(cs), ptr(bias),
+         ptr(ws), ws.numel(), stream(), nbytes=rows * (F1 + F2) * 4)
     return (C, cs) if colsum else C
 
 
@@ -651,6 +655,8 @@ class LinearTC(torch.autograd.Function):
         bias = _f32c(bias) if bias is not None else None
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        if USE_TC_GEMM_RED and LINEAR_FWD_ON_GEMM_RED:
+            return gemm_red(x, weight.t().contiguous(), a_kmajor=True, bias=bias)   # x [rows, K] is its own K-major operand
         return _linear_tc(x, weight, bias)
 
     @staticmethod
@@ -659,7 +665,10 @@ class LinearTC(torch.autograd.Function):
         gy = _f32c(gy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _linear_tc(gy, weight.t().contiguous(), None)      # dY [rows, F] x W [F, K]
+            if USE_TC_GEMM_RED and LINEAR_DX_ON_GEMM_RED:
+                dx = gemm_red(gy, weight, a_kmajor=True)            # dY [rows, F] is its own K-major operand, W [F, K] row-major
+            else:
+                dx = _linear_tc(gy, weight.t().contiguous(), None)      # dY [rows, F] x W [F, K]
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             dw = gemm_red(gy, x, colsum=want_db)

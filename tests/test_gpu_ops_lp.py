@@ -513,6 +513,7 @@ def test_gemm_red_vs_fp64(dev, rows, F1, F2, kmajor):
     A = torch.randn(rows, F1, device=dev)
     B = torch.randn(rows, F2, device=dev)
     Ain = A.t().contiguous() if kmajor else A
+    bias = torch.randn(F2, device=dev)
     lib = load()
     ws = torch.empty(max(int(lib.mrg_gemm_red_workspace_bytes(rows, F1, F2)), 16), dtype=torch.uint8, device=dev)
     outs = []
@@ -520,14 +521,14 @@ def test_gemm_red_vs_fp64(dev, rows, F1, F2, kmajor):
         C = torch.full((F1, F2 + 3), 7.0, device=dev)          # ldc > F2: the padding columns must stay untouched
         cs = torch.full((F1,), 7.0, device=dev)
         call("mrg_gemm_red", ptr(Ain), Ain.shape[1], 1 if kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2 + 3,
-             ptr(cs), ptr(ws), ws.numel(), stream())
+             ptr(cs), ptr(bias), ptr(ws), ws.numel(), stream())
         outs.append(C)
         sums = cs
     torch.cuda.synchronize()
     assert bool((outs[0] == outs[1]).all())
     assert bool((outs[0][:, F2:] == 7.0).all())
-    ref = A.double().t() @ B.double()
-    lib32 = A.t() @ B
+    ref = A.double().t() @ B.double() + bias.double()
+    lib32 = A.t() @ B + bias
     scale = float(ref.abs().max())
     e_tc = float((outs[0][:, :F2].double() - ref).abs().max()) / scale
     e_lib = float((lib32.double() - ref).abs().max()) / scale
@@ -562,7 +563,7 @@ def test_gemm_red_zero_rows(dev):
     A = torch.zeros(1, 8, device=dev)
     B = torch.zeros(1, 16, device=dev)
     ws = torch.empty(16, dtype=torch.uint8, device=dev)
-    call("mrg_gemm_red", ptr(A), 8, 0, ptr(B), 16, 0, 8, 16, ptr(C), 16, None, ptr(ws), ws.numel(), stream())
+    call("mrg_gemm_red", ptr(A), 8, 0, ptr(B), 16, 0, 8, 16, ptr(C), 16, None, None, ptr(ws), ws.numel(), stream())
     torch.cuda.synchronize()
     assert bool((C == 0).all())
 
