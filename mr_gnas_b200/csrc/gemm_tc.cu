@@ -661,31 +661,42 @@ __global__ void __launch_bounds__(THREADS, 1) amax_tc_kernel(const AmaxParams p)
         const int cnt = (int)min((int64_t)TILE_E, p.E - pos0);
         mbar_wait(&tfull_bar[ts], pr & 1);
         tc_fence_after();
+        // TMEM lane = query row, so a thread holds 32 consecutive entities of ITS row: read / written straight from
+        // there, a warp touches 32 different rows of label and logit per instruction (4 useful bytes per sector; the
+        // round-2 profile had this kernel latency bound at 134 us).  Each 32 x 16 block therefore goes through a small
+        // shared-memory tile and leaves transposed: 2 rows x 16 consecutive entities per instruction.
+        float* tb = reinterpret_cast<float*>(tail + 8192) + (size_t)(warp - EPI_WARP0) * 32 * 17;
+        const int cc = lane & 15, r2 = lane >> 4;
         for (int h = 0; h < MH; ++h) {
-          const int b = h * 128 + et;
-          const bool bvalid = b < p.Dout;
+          const int brow0 = h * 128 + quad * 32;      // first query row of this warp's TMEM lanes
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * (MH * TILE_E) + h * TILE_E;
-          const float* lab = p.label + (size_t)b * p.ldl + pos0;
-          float* lo = p.logit + (size_t)b * p.ldl + pos0;
 #pragma unroll 1
           for (int w = 0; w < 4; ++w) {
             const int cb = 32 * w;
             if (cb >= cnt) break;   // warp-uniform
             uint32_t v[32];
             tmem_ld32(taddr + cb, v);
-            if (bvalid) {
-              float facc = 0.f;
+            float facc = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (cb + j < cnt) {
-                  const float z = __uint_as_float(v[j]);
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) tb[lane * 17 + j] = __uint_as_float(v[16 * hh + j]);
+              __syncwarp();
+              const int col = cb + 16 * hh + cc;
+#pragma unroll 4
+              for (int it = 0; it < 16; ++it) {
+                const int rr = 2 * it + r2, b = brow0 + rr;
+                if (b < p.Dout && col < cnt) {
+                  const float z = tb[rr * 17 + cc];
+                  const size_t off = (size_t)b * p.ldl + pos0 + col;
                   float pr_;
-                  facc += bce_term(z, __ldg(lab + cb + j), &pr_);
-                  lo[cb + j] = z;
+                  facc += bce_term(z, __ldg(p.label + off), &pr_);
+                  p.logit[off] = z;
                 }
               }
-              acc += (double)facc;
+              __syncwarp();
             }
+            acc += (double)facc;
           }
         }
         tc_fence_before();
@@ -1758,7 +1769,7 @@ extern "C" int mrg_distmult_bce_fwd(const float* query, const float* ent, const 
     p.store = nullptr;
     p.lds = 0;
     const size_t smem = (size_t)tc::STAGES * 2 * MH * tc::TILE_BYTES + (size_t)(MH == 1 ? 4 : 2) * 2 * tc::TILE_BYTES +
-                        1024 /*align*/ + 8192 /*tail*/;
+                        1024 /*align*/ + 8192 /*tail*/ + 8 * 32 * 17 * sizeof(float) /*epilogue transpose tiles*/;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     if (MH == 1) {
       e = cudaFuncSetAttribute(tc::amax_tc_kernel<1, tc::EPI_DISTMULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
