@@ -235,6 +235,8 @@ int mrg_dense_gate_bwd(const float* dy, const float* z, mrg_act x, int64_t rows,
  *   out = sum_k w[k] * relu?(scale_k * y_k + shift_k)     (left-to-right, as Python's sum())
  * i.e. every candidate's BatchNorm-apply + ReLU and the softmax(alpha)-weighted sum in one
  * pass over the rows.  The backward reuses mrg_bn_bwd_reduce/apply per candidate (ds_k = w_k*dout).
+ * A candidate whose output is identically zero (f_zero_op, operations_lp.py:214-220) is passed with data == NULL and
+ * its BatchNorm affine in scale / shift: it is never materialised (mrg_bn_bwd_reduce accepts the same view).
  * ---------------------------------------------------------------------------------- */
 int mrg_mixed_sum_fwd(mrg_act_list ys, const float* w, int64_t rows, int32_t D, float* out, void* stream);
 /* MixedOp backward, candidate k, after mrg_bn_bwd_finalize of its BatchNorm: dw[k] = sum(dout * relu(a y + b)) from

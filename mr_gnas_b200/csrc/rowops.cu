@@ -240,15 +240,19 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
   ay.init(y, lane, D4);
   ColStats<NV> cs;
   cs.init(smem_d, D, D4);
+  // y.data == nullptr: the state is identically zero (the f_zero candidate of a MixedOp, never materialised)
+  const bool has_y = y.data != nullptr;
   RowBuf<NV> ny, ng;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) ny.v[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (warp0 < rows) {
-    ny.load(y.data, warp0, D, D4, lane);
+    if (has_y) ny.load(y.data, warp0, D, D4, lane);
     ng.load(ds, warp0, D, D4, lane);
   }
   for (int64_t row = warp0; row < rows; row += nwarps) {
     const RowBuf<NV> cy = ny, cg = ng;
     if (row + nwarps < rows) {
-      ny.load(y.data, row + nwarps, D, D4, lane);
+      if (has_y) ny.load(y.data, row + nwarps, D, D4, lane);
       ng.load(ds, row + nwarps, D, D4, lane);
     }
 #pragma unroll
@@ -915,7 +919,7 @@ __global__ void __launch_bounds__(kThreads) mixed_sum_kernel(mrg_act_list ys, co
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = 0; k < ys.n; ++k) {
           const mrg_act& a = ys.acts[k];
-          float4 x = ld_stream4(a.data + off);
+          float4 x = a.data ? ld_stream4(a.data + off) : make_float4(0.f, 0.f, 0.f, 0.f);   // null: an all-zero candidate
           if (a.scale) {
             const float4 sc = ldg4(a.scale + 4 * c4), sh = ldg4(a.shift + 4 * c4);
             x.x = fmaf(sc.x, x.x, sh.x); x.y = fmaf(sc.y, x.y, sh.y);
@@ -1028,7 +1032,7 @@ extern "C" int mrg_affine_act(mrg_act x, int64_t rows, int32_t D, float* out, vo
 
 extern "C" int mrg_bn_bwd_reduce(const float* ds, mrg_act y, int64_t rows, int32_t D, double* bwd_stats,
                                  void* stream) {
-  MRG_CHECK_ARG(ds && y.data && bwd_stats, "bn_bwd_reduce: null pointer");
+  MRG_CHECK_ARG(ds && bwd_stats && (y.data || y.scale), "bn_bwd_reduce: null pointer");
   MRG_CHECK_ARG(valid_D(D), "bn_bwd_reduce: D");
   const int want = stats_grid(rows);
   MRG_DISPATCH_NV(D, { const int grid = resident_grid(bn_bwd_reduce_kernel<NV>, stats_smem(D), want);
@@ -1227,7 +1231,7 @@ extern "C" int mrg_filtered_rank(const float* pred, const float* label, const in
 extern "C" int mrg_mixed_sum_fwd(mrg_act_list ys, const float* w, int64_t rows, int32_t D, float* out, void* stream) {
   MRG_CHECK_ARG(w && out && ys.n > 0 && ys.n <= MRG_MAX_MIXED, "mixed_sum_fwd: arguments");
   MRG_CHECK_ARG(valid_D(D), "mixed_sum_fwd: D");
-  for (int k = 0; k < ys.n; ++k) MRG_CHECK_ARG(ys.acts[k].data, "mixed_sum_fwd: null candidate");
+  for (int k = 0; k < ys.n; ++k) MRG_CHECK_ARG(ys.acts[k].data || ys.acts[k].scale, "mixed_sum_fwd: null candidate");
   if (rows <= 0) return MRG_OK;
   MRG_DISPATCH_NV(D, mixed_sum_kernel<NV><<<resident_grid(mixed_sum_kernel<NV>, 0, stats_grid(rows)), kThreads, 0, (cudaStream_t)stream>>>(ys, w, rows, D, out));
   MRG_LAUNCH_CHECK("mixed_sum_fwd");

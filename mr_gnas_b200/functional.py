@@ -587,10 +587,14 @@ def _linear_tc(x, W, bias, out_cols=None):
 
 
 _red_ws = {}
-USE_TC_GEMM_RED = True      # False: torch.mm (library GEMM) for the reductions over the rows
+USE_TC_GEMM_RED = os.environ.get("MRG_GEMM_RED", "1") != "0"      # False: torch.mm (library GEMM) for the reductions over the rows
 LINEAR_FWD_ON_GEMM_RED = os.environ.get("MRG_LINEAR_FWD_RED", "1") != "0"
 LINEAR_DX_ON_GEMM_RED = os.environ.get("MRG_LINEAR_DX_RED", "1") != "0"
-USE_TC_MATMUL = os.environ.get("MRG_MATMUL_TC", "1") != "0"     # small dense table products (K.matmul) on mrg_gemm_red
+# Small dense table products (K.matmul: rel_wt @ embedding_e, rel_embed @ w_rel) on mrg_gemm_red: OFF by default.  They
+# cost 10-16 us either way, but every edge of the graph reads one of the few rows of their result, so their rounding is
+# coherent over all edges: 3xTF32's ~1e-6 (against ~1e-7 for an fp32 FMA GEMM) showed up 70x above the reference's own
+# fp32 error in a cancellation-heavy BatchNorm bias gradient of the C3 supernet (test_c3_supernet_step_vs_real_reference).
+USE_TC_MATMUL = os.environ.get("MRG_MATMUL_TC", "0") != "0"
 
 
 def gemm_red(A, B, a_kmajor=False, colsum=False, bias=None):
@@ -655,8 +659,10 @@ class LinearTC(torch.autograd.Function):
         bias = _f32c(bias) if bias is not None else None
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        if USE_TC_GEMM_RED and LINEAR_FWD_ON_GEMM_RED:
-            return gemm_red(x, weight.t().contiguous(), a_kmajor=True, bias=bias)   # x [rows, K] is its own K-major operand
+        if USE_TC_GEMM_RED and LINEAR_FWD_ON_GEMM_RED and x.shape[1] >= 128:
+            # x [rows, K] is its own K-major operand.  (Short reductions, e.g. the D = 64 Linear on 12 M edge rows of the NC
+            # path, keep the persistent kernel: a 256-row CTA tile would do two K chunks of work per launch overhead.)
+            return gemm_red(x, weight.t().contiguous(), a_kmajor=True, bias=bias)
         return _linear_tc(x, weight, bias)
 
     @staticmethod
@@ -665,7 +671,7 @@ class LinearTC(torch.autograd.Function):
         gy = _f32c(gy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            if USE_TC_GEMM_RED and LINEAR_DX_ON_GEMM_RED:
+            if USE_TC_GEMM_RED and LINEAR_DX_ON_GEMM_RED and gy.shape[1] >= 128:
                 dx = gemm_red(gy, weight, a_kmajor=True)            # dY [rows, F] is its own K-major operand, W [F, K] row-major
             else:
                 dx = _linear_tc(gy, weight.t().contiguous(), None)      # dY [rows, F] x W [F, K]
@@ -806,17 +812,18 @@ class MixedSum(torch.autograd.Function):
     """cell_lp.py:25-33 / cell.py:23-31.  Inputs: w [K] (a softmax(alpha) row), then per candidate
     (y_k, gamma_k, beta_k).  BN statistics, normalisation, ReLU and the weighted sum are fused; the
     backward folds w_k into each candidate's BatchNorm backward (no [rows,D] temporaries per candidate
-    besides the returned dy_k)."""
+    besides the returned dy_k).  y_k = None stands for an identically-zero candidate (f_zero_op): its BatchNorm sees
+    zero statistics, its output relu(beta) is added from the affine alone and nothing of it is ever materialised."""
 
     @staticmethod
-    def forward(ctx, w, training, eps, momentum, bns, stats_list, *tensors):
+    def forward(ctx, w, training, eps, momentum, bns, stats_list, like, *tensors):
         K_ = len(tensors) // 3
-        ys = [_f32c(t) for t in tensors[0::3]]
+        ys = [_f32c(t) if t is not None else None for t in tensors[0::3]]
         gammas, betas = tensors[1::3], tensors[2::3]
-        rows, D = ys[0].shape
-        dev = ys[0].device
+        rows, D = like.shape
+        dev = like.device
         w = _f32c(w)
-        acts, saved = [], []
+        saved = []
         lst = _lib.MrgActList()
         lst.n = K_
         for k in range(K_):
@@ -826,7 +833,9 @@ class MixedSum(torch.autograd.Function):
             if training:
                 st = stats_list[k]
                 nparts = stats_nparts(rows)
-                if st is None:
+                if ys[k] is None:
+                    st, nparts = torch.zeros(1, 2, D, dtype=torch.float64, device=dev), 1
+                elif st is None:
                     st = _stats_buf(nparts, D, dev)
                     call("mrg_colstats", act(ys[k]), rows, D, ptr(st), stream())
                 else:
@@ -839,9 +848,9 @@ class MixedSum(torch.autograd.Function):
                 mean = rm
                 a = (gammas[k] * invstd).contiguous()
                 b = (betas[k] - a * mean).contiguous()
-            lst.acts[k] = act(ys[k], a, b, True)
+            lst.acts[k] = act(ys[k], a, b, True) if ys[k] is not None else _lib.MrgAct(None, a.data_ptr(), b.data_ptr(), 1)
             saved += [ys[k], gammas[k], mean, invstd, a, b]
-        out = torch.empty_like(ys[0])
+        out = torch.empty(rows, D, dtype=torch.float32, device=dev)
         call("mrg_mixed_sum_fwd", lst, ptr(w), rows, D, ptr(out), stream())
         ctx.K_, ctx.training = K_, training
         ctx.save_for_backward(w, *saved)
@@ -859,7 +868,7 @@ class MixedSum(torch.autograd.Function):
         nparts = stats_nparts(rows)
         for k in range(K_):
             y, gamma, mean, invstd, a, b = saved[6 * k:6 * k + 6]
-            yact = act(y, a, b, True)
+            yact = act(y, a, b, True) if y is not None else _lib.MrgAct(None, a.data_ptr(), b.data_ptr(), 1)
             bst = _stats_buf(nparts, D, dev)
             call("mrg_bn_bwd_reduce", ptr(dout), yact, rows, D, ptr(bst), stream())
             dgamma = torch.empty(D, dtype=torch.float32, device=dev)
@@ -871,10 +880,12 @@ class MixedSum(torch.autograd.Function):
             # coef / dgamma / dbeta scaled by w[k] (eval: dy = w_k * a * dz) -- one launch
             call("mrg_mixed_bwd_scale", ptr(coef), ptr(dgamma), ptr(dbeta), ptr(a), ptr(b), ptr(mean), ptr(invstd),
                  ptr(w), k, ptr(dw), D, 1 if ctx.training else 0, stream())
-            dy = torch.empty_like(y)
-            call("mrg_bn_bwd_apply", ptr(dout), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
+            dy = None
+            if y is not None:
+                dy = torch.empty_like(y)
+                call("mrg_bn_bwd_apply", ptr(dout), yact, ptr(coef), rows, D, ptr(dy), 0, stream())
             grads += [dy, dgamma, dbeta]
-        return (dw, None, None, None, None, None, *grads)
+        return (dw, None, None, None, None, None, None, *grads)
 
 
 class MixedPre(torch.autograd.Function):
@@ -950,7 +961,7 @@ class MixedPre(torch.autograd.Function):
         return (dw, None, None, None, None, None, da, db, *grads)
 
 
-MIXED_PRE_FUSED = True      # False: per-candidate outputs + mixed_sum (the round-1 form)
+MIXED_PRE_FUSED = os.environ.get("MRG_MIXED_PRE", "1") != "0"      # False: per-candidate outputs + mixed_sum (the round-1 form)
 
 
 def mixed_pre(weights, a, b, comps, bn_modules):
@@ -965,15 +976,18 @@ def mixed_pre(weights, a, b, comps, bn_modules):
     return MixedPre.apply(weights, training, bn_modules[0].eps, bn_momentum(bn_modules[0]), bns, tuple(comps), a, b, *flat)
 
 
-def mixed_sum(weights, ys, bn_modules):
-    """sum_k weights[k] * ReLU(bn_k(ys[k])) with nn.BatchNorm1d modules supplying parameters/buffers."""
+def mixed_sum(weights, ys, bn_modules, like=None):
+    """sum_k weights[k] * ReLU(bn_k(ys[k])) with nn.BatchNorm1d modules supplying parameters/buffers.  ys[k] may be None
+    (an identically-zero candidate); `like` then supplies shape and device."""
     training = bn_modules[0].training
     bns, flat, stats = [], [], []
+    if like is None:
+        like = next(y for y in ys if y is not None)
     for y, bn in zip(ys, bn_modules):
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         bns.append((bn.running_mean, bn.running_var))
-        stats.append(getattr(y, 'mrg_stats', None))
+        stats.append(getattr(y, 'mrg_stats', None) if y is not None else None)
         flat += [y, bn.weight, bn.bias]
     mom = bn_momentum(bn_modules[0])
-    return MixedSum.apply(weights, training, bn_modules[0].eps, mom, bns, stats, *flat)
+    return MixedSum.apply(weights, training, bn_modules[0].eps, mom, bns, stats, like.detach(), *flat)

@@ -543,6 +543,7 @@ def test_matmul_tc_vs_fp64(dev):
     on mrg_gemm_red against fp64."""
     from mr_gnas_b200 import functional as K_
     torch.manual_seed(9)
+    K_.USE_TC_MATMUL = True          # off by default (see functional.py): the library GEMM serves these tiny products
     for m, k, n in ((475, 475, 200), (475, 200, 200), (23, 23, 64)):
         X = torch.randn(m, k, device=dev, requires_grad=True)
         Y = torch.randn(k, n, device=dev, requires_grad=True)
@@ -555,6 +556,7 @@ def test_matmul_tc_vs_fp64(dev):
         _check("C", C, C64.float())
         _check("dX", X.grad, X64.grad.float())
         _check("dY", Y.grad, Y64.grad.float())
+    K_.USE_TC_MATMUL = False
 
 
 def test_gemm_red_zero_rows(dev):
