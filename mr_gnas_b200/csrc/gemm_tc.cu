@@ -1366,11 +1366,12 @@ __device__ __forceinline__ void red_scatter8(uint8_t* hi_tile, uint32_t lo_off, 
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     uint8_t* a = base + e * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)e) << 4);
-    // lo is ROUNDED to tf32 here: left as the exact fp32 difference, the MMA truncates it toward zero, a bias that grows
-    // with the reduction length (measured at 14,541 rows: 5e-6 of max|C| against 7e-7 for the fp32 library GEMM)
+    // lo = the exact fp32 difference; the MMA truncates it to tf32.  (Rounding it here instead changed nothing: 5.1e-6 vs
+    // 5.3e-6 of max|C| at 14,541 rows -- the error of this kernel is the TMEM accumulator's, which does not round to nearest
+    // and grows with the number of MMAs accumulated per CTA.)
     const float h = tf32_rna(v[e]);
     *reinterpret_cast<float*>(a) = h;
-    *reinterpret_cast<float*>(a + lo_off) = tf32_rna(v[e] - h);
+    *reinterpret_cast<float*>(a + lo_off) = v[e] - h;
   }
 }
 
@@ -1443,7 +1444,7 @@ __global__ void __launch_bounds__(RTHREADS, 1) gemm_red_kernel(const RedParams p
                        ((((uint32_t)lane >> 2) ^ (uint32_t)(R & 7)) << 4) + (uint32_t)(lane & 3) * 4;
           const float h = tf32_rna(r.ka[i]);
           *reinterpret_cast<float*>(a) = h;
-          *reinterpret_cast<float*>(a + RA_TILE) = tf32_rna(r.ka[i] - h);
+          *reinterpret_cast<float*>(a + RA_TILE) = r.ka[i] - h;
         }
       } else {
         red_scatter8(st, RA_TILE, 8 * warp, lane, r.a0);
