@@ -116,6 +116,66 @@ class GatherCompose(torch.autograd.Function):
         return dh, dr, None, None
 
 
+class GatherRows(torch.autograd.Function):
+    """table[idx] over the M edge-expanded rows of a graph whose segment list `seg` groups those rows by idx (the src-CSC
+    for entity rows, the relation segments for relation rows): model_search_lp.py:139-145 `all_ent_emb[src_id_final]`,
+    `ent_emb[src_in]`, `rel_embed[edge_type_final]`.  The backward is the deterministic segmented sum the LP network's
+    fused gather already uses (mrg_seg_reduce_fwd) instead of ATen's sort-based index_put: with ~23 relation rows
+    behind 60,000 gathered rows that kernel serialises on the duplicates -- 7 launches of 16.9 ms were 78 % of the GPU
+    time of the C3 supernet step at graph_batch_size 30,000 (profiles/r02b_search_c3.jsonl)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, seg):
+        table = _f32c(table)
+        if table.shape[0] != seg.nseg or idx.numel() != seg.total:
+            raise RuntimeError(f"gather_rows: table has {table.shape[0]} rows / {idx.numel()} gathered rows, the graph's "
+                               f"segment list covers {seg.nseg} / {seg.total}")
+        ctx.seg = seg
+        return table.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        seg = ctx.seg
+        dy = _f32c(dy)
+        D = dy.shape[1]
+        dt = torch.empty(seg.nseg, D, dtype=torch.float32, device=dy.device)
+        seg_reduce_raw(seg, 0, act(dy), D, dt)
+        return dt, None, None
+
+
+def gather_rows(table, idx, seg):
+    return GatherRows.apply(table, idx, seg)
+
+
+class GatherFew(torch.autograd.Function):
+    """table[idx] for a table of FEW rows gathered MANY times (model_search_lp.py:171 `rel_embedding[triplets[:, 1]]`:
+    330,000 scored triplets over 11 relations at C3).  ATen's index_put backward serialises on the duplicates (tens of
+    milliseconds); here the backward is the reduction GEMM onehot(idx)^T . dy on the tensor cores (mrg_gemm_red: the
+    one-hot entries are exact in tf32, so this is an fp32-class deterministic segmented sum)."""
+
+    @staticmethod
+    def forward(ctx, table, idx):
+        table = _f32c(table)
+        ctx.save_for_backward(idx)
+        ctx.n_rows = table.shape[0]
+        return table.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx, = ctx.saved_tensors
+        dy = _f32c(dy)
+        onehot = torch.zeros(idx.numel(), ctx.n_rows, dtype=torch.float32, device=dy.device)
+        onehot.scatter_(1, idx.view(-1, 1).long(), 1.0)
+        return gemm_red(onehot, dy), None
+
+
+def gather_few(table, idx):
+    """table[idx]; tables of at most 64 rows on a CUDA device take the GatherFew path."""
+    if table.is_cuda and table.dim() == 2 and table.shape[0] <= 64 and idx.dim() == 1:
+        return GatherFew.apply(table, idx)
+    return table[idx]
+
+
 # ------------------------------------------------------------------------------------------
 # BatchNorm1d (+ReLU) over rows
 # ------------------------------------------------------------------------------------------

@@ -96,10 +96,25 @@ class Network(nn.Module):
         edge_self = torch.full((nodes.numel(),), self._num_rel - 1, dtype=torch.long, device=dev)
         edge_type_final = torch.cat((edge_type.long(), edge_self), dim=0)
         ent_emb = None
+        # The gathers below read the graph's own edge-expanded index arrays (rows [0, E) = the edges in the graph's order,
+        # rows [E, E + N) = the self loops), so their backward can be the graph's deterministic segmented sums instead of
+        # ATen's index_put (K.GatherRows).  That holds when src_in / edge_type ARE the graph's arrays -- what
+        # utils_rgcn hands to the search scripts -- and is verified once per graph object (one device comparison).
+        own = getattr(g_train, 'csc', None) is not None and g_train.M == src_in_final.numel() \
+            and g_train.n_rel_rows == rel_embed.shape[0] and node_id.numel() == g_train.N
+        if own and not getattr(g_train, '_gather_verified', False):
+            own = bool(torch.equal(src_in.to(torch.int32), g_train.src) & torch.equal(edge_type.to(torch.int32), g_train.etype))
+            g_train._gather_verified = own
         for i, cell in enumerate(self.cells):
             W_zero, W_first, W_middle, W_last = self.show_weights(i)
-            ent_emb_in = all_ent_emb[src_id_final] if i == 0 else torch.cat((ent_emb[src_in], ent_emb), dim=0)
-            ent_emb = cell(g_train, ent_emb_in, rel_embed[edge_type_final], W_zero, W_first, W_middle, W_last)
+            if own:
+                nodes_emb = all_ent_emb[node_id.reshape(-1)] if i == 0 else ent_emb      # unique ids: a plain row gather
+                ent_emb_in = K.gather_rows(nodes_emb, g_train.src_final, g_train.csc)
+                hr = K.gather_rows(rel_embed, g_train.et_final, g_train.rel)
+            else:
+                ent_emb_in = all_ent_emb[src_id_final] if i == 0 else torch.cat((ent_emb[src_in], ent_emb), dim=0)
+                hr = rel_embed[edge_type_final]
+            ent_emb = cell(g_train, ent_emb_in, hr, W_zero, W_first, W_middle, W_last)
             relu = not (i == 0 and len(self.cells) != 1)  # layer 0 of a deeper net is not activated (:146-148)
             ent_emb = K.bn_act(ent_emb, self.batchnorm_h, relu=relu)
             ent_emb = F.dropout(ent_emb, self._dropout, training=self.training)
@@ -112,7 +127,7 @@ class Network(nn.Module):
     def calc_score(self, ent_embedding, rel_embedding, triplets):
         """triplet-wise DistMult sum_d s*r*o (model_search_lp.py:169-176)"""
         s = ent_embedding[triplets[:, 0]]
-        r = rel_embedding[triplets[:, 1]]
+        r = K.gather_few(rel_embedding, triplets[:, 1])
         o = ent_embedding[triplets[:, 2]]
         return torch.sum(s * r * o, dim=1)
 
