@@ -124,6 +124,36 @@ def test_mixed_pre_fused_equals_per_candidate_form(names, train):
     _check("dalpha vs fp64", res[True]["dalpha"], alpha.grad.float())
 
 
+def test_gather_rows_and_gather_few_match_torch_indexing():
+    """The search network's gathers (model_search_lp.py:139-145,171): K.gather_rows (backward = the graph's segmented sum)
+    and K.gather_few (backward = one-hot reduction GEMM) against torch indexing and its index_put backward in fp64."""
+    from mr_gnas_b200 import functional as K
+    from mr_gnas_b200.graph import MRGraph
+    import oracle.mrg_oracle as O
+    N, R, D = 700, 5, 200
+    g = MRGraph.from_triples(N, O.synth_kg(N, R, 3000, seed=2), R, device=DEV)
+    torch.manual_seed(4)
+    ent = torch.randn(N, D, device=DEV, requires_grad=True)
+    rel = torch.randn(2 * R + 1, D, device=DEV, requires_grad=True)
+    cot = torch.randn(g.M, D, device=DEV)
+    ye, yr = K.gather_rows(ent, g.src_final, g.csc), K.gather_rows(rel, g.et_final, g.rel)
+    assert torch.equal(ye, ent[g.src_final.long()]) and torch.equal(yr, rel[g.et_final.long()])
+    (ye * cot + yr * cot.flip(0)).sum().backward()
+    e64, r64 = ent.detach().double().requires_grad_(True), rel.detach().double().requires_grad_(True)
+    (e64[g.src_final.long()] * cot.double() + r64[g.et_final.long()] * cot.double().flip(0)).sum().backward()
+    _check("d ent", ent.grad, e64.grad.float())
+    _check("d rel", rel.grad, r64.grad.float())
+    idx = torch.randint(0, 2 * R + 1, (33000,), device=DEV)
+    cot2 = torch.randn(33000, D, device=DEV)
+    rel.grad = None
+    yf = K.gather_few(rel, idx)
+    assert torch.equal(yf, rel[idx])
+    (yf * cot2).sum().backward()
+    r64.grad = None
+    (r64[idx] * cot2.double()).sum().backward()
+    _check("d rel (few rows, many gathers)", rel.grad, r64.grad.float())
+
+
 # ------------------------------------------------------------------------------ LP supernet
 def test_search_lp_golden(golden_dir):
     from mr_gnas_b200.graph import MRGraph
