@@ -147,6 +147,26 @@ def gather_rows(table, idx, seg):
     return GatherRows.apply(table, idx, seg)
 
 
+def key_segments(keys, nseg, owner, name):
+    """Segment list (graph._Segments) grouping the positions of `keys` [rows] by key value in [0, nseg): built with one
+    stable sort the first time `owner` (a graph / block object) is seen with this key tensor, then cached on it -- the NC
+    path's full-graph blocks are static, so the relation gather's backward costs one segmented sum per step."""
+    from .graph import _Segments
+    cache = getattr(owner, '_key_segments', None)
+    if cache is None:
+        cache = owner._key_segments = {}
+    hit = cache.get(name)
+    if hit is not None and hit[0] is keys and hit[1].nseg == nseg:
+        return hit[1]
+    k = keys.long()
+    order = torch.argsort(k, stable=True).to(torch.int32).contiguous()
+    ptr = torch.zeros(nseg + 1, dtype=torch.int32, device=keys.device)
+    ptr[1:] = torch.bincount(k, minlength=nseg).cumsum(0).to(torch.int32)
+    seg = _Segments(ptr, order, nseg, k.numel(), keys.device)
+    cache[name] = (keys, seg)
+    return seg
+
+
 class GatherFew(torch.autograd.Function):
     """table[idx] for a table of FEW rows gathered MANY times (model_search_lp.py:171 `rel_embedding[triplets[:, 1]]`:
     330,000 scored triplets over 11 relations at C3).  ATen's index_put backward serialises on the duplicates (tens of
@@ -655,6 +675,9 @@ LINEAR_DX_ON_GEMM_RED = os.environ.get("MRG_LINEAR_DX_RED", "1") != "0"
 # coherent over all edges: 3xTF32's ~1e-6 (against ~1e-7 for an fp32 FMA GEMM) showed up 70x above the reference's own
 # fp32 error in a cancellation-heavy BatchNorm bias gradient of the C3 supernet (test_c3_supernet_step_vs_real_reference).
 USE_TC_MATMUL = os.environ.get("MRG_MATMUL_TC", "0") != "0"
+# NC path: Linear on the relation TABLE, then gather (instead of gather, then Linear on every edge row), with the gather's
+# backward as a segmented sum over the block's edge-type segments (model.py)
+NC_REL_REORDER = os.environ.get("MRG_NC_REL_REORDER", "1") != "0"
 
 
 def gemm_red(A, B, a_kmajor=False, colsum=False, bias=None):

@@ -101,6 +101,17 @@ def remap_sources(next_src, dst_nid, num_nodes):
     return table[next_src]
 
 
+def edge_type_features(linear, rel_table, etype, block):
+    """`embedding_e_init(rel_table[etype])` (model.py:168-170).  The Linear is row-wise, so it is applied to the few rows of
+    the relation table and THEN gathered per edge -- E_b x init_dim fewer GEMM rows forward and backward -- and the gather's
+    backward is the deterministic segmented sum over the block's edge-type segments instead of ATen's sort-based index_put,
+    which serialises on the duplicates (millions of edges over a few hundred relations)."""
+    if not (K.NC_REL_REORDER and rel_table.is_cuda and etype.numel() > 0):
+        return linear(rel_table[etype])
+    feat = linear(rel_table)
+    return K.gather_rows(feat, etype, K.key_segments(etype, feat.shape[0], block, 'etype'))
+
+
 class Network(nn.Module):
     """reference: model.py:107-199"""
 
@@ -146,7 +157,7 @@ class Network(nn.Module):
                     src_embed = self.embedding_h_init(self.embedding_h(src_ls[i]))
                 else:
                     src_embed = D_.AllGatherRows.apply(node_embed, part)[src_ls[i]]
-                edges_embed = self.embedding_e_init(rel_table[et_ls[i]])
+                edges_embed = edge_type_features(self.embedding_e_init, rel_table, et_ls[i], block[i])
                 node_embed = self._cell(i, cell, block[i], src_embed, edges_embed)
             return K.bn_act(node_embed, self.batchnorm_h, relu=True)
 
@@ -169,7 +180,7 @@ class Network(nn.Module):
         for i, cell in enumerate(self.cells):
             if i == 0:
                 src_embed = self.embedding_h_init(self.embedding_h(src_ls[i]))
-            edges_embed = self.embedding_e_init(rel_table[et_ls[i]])
+            edges_embed = edge_type_features(self.embedding_e_init, rel_table, et_ls[i], block[i])
             node_embed = self._cell(i, cell, block[i], src_embed, edges_embed)
             if i < len(src_ls) - 1:
                 src_embed = node_embed[remap_sources(src_ls[i + 1], block[i].dstdata['_ID'], self._in_dim_n)]
