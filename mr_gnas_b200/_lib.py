@@ -108,7 +108,7 @@ _OPTIONAL = {}
 
 _lib = None
 # kernels enqueued per C-ABI call (default 1); used for the gpu_launches count bench.py reports
-KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_amax_tc_fwd_bf16": 3, "mrg_amax_bwd": 5, "mrg_distmult_bce_fwd": 3, "mrg_linear_tc_fwd": 2, "mrg_gemm_red": 2, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_transe_bwd": 3, "mrg_graph_build": 12, "mrg_graph_build_part": 10, "mrg_chunk_build": 3}
+KERNELS_PER_CALL = {"mrg_amax_tc_fwd": 3, "mrg_amax_tc_fwd_bf16": 3, "mrg_amax_bwd": 5, "mrg_distmult_bce_fwd": 3, "mrg_linear_tc_fwd": 2, "mrg_gemm_red": 1, "mrg_seg_reduce_fwd": 2, "mrg_sigmoid_bce_fwd": 2, "mrg_transe_bwd": 3, "mrg_graph_build": 12, "mrg_graph_build_part": 10, "mrg_chunk_build": 3}
 launch_count = 0   # libmrgnas kernels launched so far
 _profile = None    # when a list: (name, start_event, end_event) per call (bench.py per-kernel timing)
 

@@ -702,6 +702,8 @@ def gemm_red(A, B, a_kmajor=False, colsum=False, bias=None):
     cs = torch.empty(F1, dtype=torch.float32, device=A.device) if colsum else None
     call("mrg_gemm_red", ptr(A), A.shape[1], 1 if a_kmajor else 0, ptr(B), F2, rows, F1, F2, ptr(C), F2, ptr(cs), ptr(bias),
          ptr(ws), ws.numel(), stream(), nbytes=rows * (F1 + F2) * 4)
+    if nbytes > 16:
+        _lib.launch_count += 1      # split reduction: main kernel + fold kernel (one slice: the main kernel alone)
     return (C, cs) if colsum else C
 
 
